@@ -1,0 +1,158 @@
+/* include/ndnet_b200.h — C ABI of libndnet_b200.so (B200 / sm_100a).
+ *
+ * Two groups of entry points:
+ *
+ * (1) LEGACY, host-pointer symbols with the exact signatures of the reference's libndnet.so, so that
+ *     /root/reference/ndnet/preprocessing/ndt_legacy.py:28-43,153-163,186-232 binds to this library
+ *     unchanged (only the path in its LoadLibrary call changes).  Each replaces:
+ *       ndt_downsample       core_legacy/include/ndnet_core/ndt.h:100-110   (src/ndt.c:119-222)
+ *       prune_nds            core_legacy/include/ndnet_core/ndt.h:59-62     (src/ndt.c:28-73)
+ *       to_point_cloud       core_legacy/include/ndnet_core/ndt.h:76-82     (src/ndt.c:75-117)
+ *       free_nds             core_legacy/include/ndnet_core/ndt.h:116       (src/ndt.c:224-239)
+ *       free_kl_divergences  core_legacy/include/ndnet_core/kullback_leibler.h:74 (src/kullback_leibler.c:204-207)
+ *       print_matrix         core_legacy/include/ndnet_core/matrix.h:40     (src/matrix.c:28-35)
+ *     The two struct pointers are opaque tokens here (the reference's Python never dereferences them,
+ *     ndt_legacy.py:5-25 declares inert `__fields__`).  All work runs on the GPU; there is no CPU path.
+ *     Error convention as the reference: negative int + a line on stderr; additionally -100 - cudaError
+ *     for CUDA failures.
+ *
+ * (2) BATCHED, device-pointer entry points (ours): one call voxelises, searches, prunes and packs a whole
+ *     batch of clouds on a CUDA stream, and runs the PointNet/NDT-Net forward.  Replaces the per-cloud
+ *     Python loop of ndnet/preprocessing/ndtnet_preprocessing.py:27-63.
+ *
+ * Plain pointers and sizes only; no torch types.
+ */
+#ifndef NDNET_B200_H
+#define NDNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ (1) legacy ABI (host pointers) */
+struct normal_distribution_t; /* opaque */
+struct kl_divergence_t;       /* opaque */
+
+int ndt_downsample(double *point_cloud, unsigned short point_dim, unsigned long num_points,
+                   unsigned int *len_x, unsigned int *len_y, unsigned int *len_z,
+                   double *offset_x, double *offset_y, double *offset_z,
+                   double *voxel_size,
+                   unsigned short *classes, unsigned short num_classes,
+                   unsigned long num_desired_points,
+                   double *downsampled_point_cloud, unsigned long *num_downsampled_points,
+                   double *covariances,
+                   unsigned short *downsampled_classes,
+                   struct normal_distribution_t **nd_array, unsigned long *num_valid_nds,
+                   struct kl_divergence_t **kl_divergences, unsigned long *num_kl_divergences);
+
+int prune_nds(struct normal_distribution_t *nd_array,
+              unsigned int len_x, unsigned int len_y, unsigned int len_z,
+              unsigned long num_desired_nds, unsigned long *num_valid_nds,
+              struct kl_divergence_t *kl_divergences, unsigned long *num_kl_divergences);
+
+int to_point_cloud(struct normal_distribution_t *nd_array,
+                   unsigned int len_x, unsigned int len_y, unsigned int len_z,
+                   double offset_x, double offset_y, double offset_z,
+                   double voxel_size,
+                   double *point_cloud, unsigned long *num_points,
+                   double *covariances,
+                   unsigned short *classes);
+
+void free_nds(struct normal_distribution_t *nd_array, unsigned long num_nds);
+void free_kl_divergences(struct kl_divergence_t *kl_divergences);
+void print_matrix(double *matrix, int rows, int cols);
+
+/* ------------------------------------------------------------------ (2) batched ABI (device pointers) */
+
+typedef struct ndnet_b200_ctx ndnet_b200_ctx;
+
+#define NDNET_B200_F32 0
+#define NDNET_B200_F64 1
+
+/* flags for ndnet_b200_downsample_batch */
+#define NDNET_B200_NAN_TO_NUM 1u /* NaN/+-inf -> 0 in the f32 features (ndtnet_preprocessing.py:66-69) */
+
+/* Per-cloud record written by ndnet_b200_downsample_batch (device memory, one per cloud). */
+typedef struct ndnet_b200_cloud_info {
+    int32_t status;        /* 0 ok; -1 grid too large (stands in for malloc failure, ndt.c:151-155);
+                              -3 voxel-size search did not converge (ndt.c:191-194) */
+    int32_t prune_status;  /* 0, or -2 when the walk hit the end of the list (ndt.c:53-56) */
+    int32_t evaluations;   /* estimate passes the search made (<= 15) */
+    uint32_t len[3];       /* accepted grid */
+    uint32_t num_voxels;   /* occupied voxels before pruning (num_valid_nds before prune) */
+    uint32_t num_valid;    /* after pruning */
+    uint32_t num_kl;       /* divergence-list entries before pruning */
+    uint32_t num_kl_after; /* list entries that remain after the walk */
+    uint32_t num_out;      /* rows written (clamped to num_desired) */
+    uint32_t num_survivors;/* rows the reference would have written (may exceed num_desired, A15) */
+    double voxel_size;
+    double offset[3];
+    double limits[6];      /* max x,y,z, min x,y,z */
+} ndnet_b200_cloud_info;
+
+/* Create / destroy a context (owns the device workspace; one per host thread / stream). */
+int ndnet_b200_create(ndnet_b200_ctx **ctx, int device);
+void ndnet_b200_destroy(ndnet_b200_ctx *ctx);
+const char *ndnet_b200_last_error(const ndnet_b200_ctx *ctx);
+const char *ndnet_b200_version(void);
+
+/* NDT voxelise + voxel-size search + neighbour pseudo-KL prune + 12-D feature pack for B clouds.
+ *   points      device, [B, N, 3] contiguous, dtype f32 or f64 (NDNET_B200_F32/F64)
+ *   labels      device, [B, N] uint16 point classes, or NULL
+ *   num_classes classes are 0..num_classes inclusive (normal_distributions.c:115,158)
+ *   num_desired n_desired_nds (D)
+ *   out_feat    device, [B, D, 12] f32: mean(3) then row-major 3x3 "covariance"(9); rows >= num_out are 0
+ *   out_feat64  device, [B, D, 12] f64 or NULL (bit-exact values, no nan_to_num)
+ *   out_labels  device, [B, D] uint16 or NULL
+ *   out_voxel   device, [B, D] int32 linear voxel index of each row (-1 for padding) or NULL
+ *   info        device, [B] ndnet_b200_cloud_info or NULL
+ *   stream      cudaStream_t (as void*); all work is enqueued, nothing synchronises
+ * Returns 0 or -100-cudaError / -200-.. argument errors. */
+int ndnet_b200_downsample_batch(ndnet_b200_ctx *ctx, const void *points, int dtype, const uint16_t *labels,
+                                int B, long N, int num_classes, long num_desired, unsigned flags,
+                                float *out_feat, double *out_feat64, uint16_t *out_labels, int32_t *out_voxel,
+                                ndnet_b200_cloud_info *info, void *stream);
+
+/* Same, from/to HOST buffers (pinned or pageable): H2D of the points (+labels), the kernels, D2H of the
+ * features (+labels, info), then a stream synchronise.  This is the call the reference-facing Python
+ * wrapper makes for CPU tensors and the one bench.py times as `e2e`. */
+int ndnet_b200_downsample_batch_host(ndnet_b200_ctx *ctx, const void *points, int dtype, const uint16_t *labels,
+                                     int B, long N, int num_classes, long num_desired, unsigned flags,
+                                     float *out_feat, double *out_feat64, uint16_t *out_labels, int32_t *out_voxel,
+                                     ndnet_b200_cloud_info *info, void *stream);
+
+/* Debug/inspection: copy per-point voxel ids of the last batch ([B,N] int32, -1 = never voxelised) to a
+ * device buffer.  Used by the parity tests ("voxel ids and per-voxel membership bit-exact"). */
+int ndnet_b200_last_point_voxels(ndnet_b200_ctx *ctx, int32_t *out_dev, void *stream);
+/* Debug/inspection: the pre-prune divergence list of cloud b of the last batch, in list order.
+ * Host buffers of capacity `cap`; returns the number of entries or a negative error. */
+long ndnet_b200_last_kl_list(ndnet_b200_ctx *ctx, int b, double *div, int32_t *p_voxel, int32_t *q_voxel, long cap);
+
+/* ---- PointNet / NDT-Net forward (ndnet/models/ndtnet.py:33-62,112-164,181-196,218-243) ------------ */
+
+typedef struct ndnet_b200_model ndnet_b200_model;
+
+/* kinds */
+#define NDNET_B200_NDTNET_CLS 0
+#define NDNET_B200_NDTNET_SEG 1
+
+/* Build a model from a flat list of named fp32 host tensors (the reference state_dict: names follow
+ * ndtnet.py module attributes, e.g. "feature_extractor.t1.conv1.weight").  BatchNorm is folded with its
+ * running statistics (eval mode).  feature_dim / num_classes are read from the tensor shapes. */
+int ndnet_b200_model_create(ndnet_b200_ctx *ctx, ndnet_b200_model **model, int kind, int n_tensors,
+                            const char *const *names, const float *const *data, const int64_t *const *shapes,
+                            const int *ndims);
+void ndnet_b200_model_destroy(ndnet_b200_model *model);
+
+/* Forward over B clouds of D distributions.  feat: device [B, D, 12] f32.
+ * cls: out device [B, num_classes] f32 (softmax);  seg: out device [B, D, num_classes+1] f32 (log_softmax). */
+int ndnet_b200_model_forward(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const float *feat, int B, int D,
+                             float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDNET_B200_H */

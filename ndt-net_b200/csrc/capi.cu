@@ -1,0 +1,459 @@
+// capi.cu — the C ABI of libndnet_b200.so (include/ndnet_b200.h): contexts, workspaces, the batched
+// device/host entry points and the legacy host-pointer symbols of the reference's libndnet.so.
+#include "../../include/ndnet_b200.h"
+#include "ndt_host.h"
+#include "mlp_host.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using ndt::NdtCloudInfo;
+using ndt::Workspace;
+
+static_assert(sizeof(NdtCloudInfo) == sizeof(ndnet_b200_cloud_info), "info layout mismatch");
+
+struct ndnet_b200_ctx {
+    int device = 0;
+    Workspace ws;
+    std::string err;
+    // staging for the *_host entry point
+    void *d_points = nullptr; size_t d_points_bytes = 0;
+    uint16_t *d_labels = nullptr; size_t d_labels_bytes = 0;
+    float *d_feat = nullptr; size_t d_feat_bytes = 0;
+    double *d_feat64 = nullptr; size_t d_feat64_bytes = 0;
+    uint16_t *d_olab = nullptr; size_t d_olab_bytes = 0;
+    int32_t *d_ovox = nullptr; size_t d_ovox_bytes = 0;
+    NdtCloudInfo *d_info = nullptr; size_t d_info_bytes = 0;
+    mlp::Scratch mlp_scratch;
+};
+
+namespace {
+
+int fail(ndnet_b200_ctx *ctx, cudaError_t e, const char *where) {
+    if (ctx) ctx->err = std::string(where) + ": " + cudaGetErrorString(e);
+    fprintf(stderr, "ndnet_b200: %s: %s\n", where, cudaGetErrorString(e));
+    return -100 - (int)e;
+}
+
+template <typename T>
+cudaError_t grow(T *&p, size_t &have, size_t need) {
+    if (need <= have) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; have = 0;
+    cudaError_t e = cudaMalloc((void **)&p, need ? need : 1);
+    if (e == cudaSuccess) have = need;
+    return e;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------
+namespace ndt {
+
+template <typename T>
+static cudaError_t alloc(T *&p, size_t count) {
+    return cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
+}
+
+void Workspace::release() {
+    void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, slot_rank, tile_cnt, hist, point_voxel, sorted,
+                    mean, cov, cov_final, cls, kl_div, kl_flag, key, seq, firstpos, removed, list_div, list_seq};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    *this = Workspace();
+}
+
+cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
+    const unsigned need_vcap = (unsigned)((double)D * 1.2) + 2;
+    if (B <= B_cap && N <= N_cap && need_vcap <= vcap && bins <= bins_cap) return cudaSuccess;
+    const int nB = B > B_cap ? B : B_cap;
+    const long nN = N > N_cap ? N : N_cap;
+    const long nD = D > D_cap ? D : D_cap;
+    const int nbins = bins > bins_cap ? bins : bins_cap;
+    release();
+    B_cap = nB; N_cap = nN; D_cap = nD; bins_cap = nbins;
+    vcap = (unsigned)((double)nD * 1.2) + 2;
+    // Bitmap words per cloud: enough for kMaxGridCells when the batch is small, never less than 64K
+    // cells; the search answers -1 (as the reference does when malloc fails) beyond what is held.
+    bitmap_stride = (size_t)(1u << 25) / 32;
+    ntiles_cap = (int)((nN + 2047) / 2048);
+    const size_t kcap = (size_t)vcap * 6;
+    cudaError_t e;
+#define A(ptr, count) if ((e = alloc(ptr, (size_t)(count))) != cudaSuccess) return e
+    if ((e = cudaMalloc((void **)&states, cloud_state_size() * nB)) != cudaSuccess) return e;
+    A(lim_enc, (size_t)nB * 6);
+    A(bitmap, (size_t)nB * bitmap_stride);
+    A(vox_cell, (size_t)nB * vcap);
+    A(vox_n, (size_t)nB * vcap);
+    A(vox_start, (size_t)nB * (vcap + 1));
+    A(slot_rank, (size_t)nB * nN);
+    A(tile_cnt, (size_t)nB * ntiles_cap * vcap);
+    A(hist, (size_t)nB * vcap * (nbins > 0 ? nbins : 1));
+    A(point_voxel, (size_t)nB * nN);
+    if ((e = cudaMalloc(&sorted, (size_t)nB * nN * 3 * sizeof(double) + 16)) != cudaSuccess) return e;
+    A(mean, (size_t)nB * vcap * 3);
+    A(cov, (size_t)nB * vcap * 9);
+    A(cov_final, (size_t)nB * vcap * 9);
+    A(cls, (size_t)nB * vcap);
+    A(kl_div, (size_t)nB * kcap);
+    A(kl_flag, (size_t)nB * kcap);
+    A(key, (size_t)nB * kcap);
+    A(seq, (size_t)nB * kcap);
+    A(firstpos, (size_t)nB * vcap);
+    A(removed, (size_t)nB * vcap);
+    A(list_div, (size_t)nB * kcap);
+    A(list_seq, (size_t)nB * kcap);
+#undef A
+    return cudaSuccess;
+}
+
+}  // namespace ndt
+
+// ------------------------------------------------------------------------------------------------
+// contexts
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *ndnet_b200_version(void) { return "ndnet_b200 0.1 (sm_100a)"; }
+
+extern "C" int ndnet_b200_create(ndnet_b200_ctx **out, int device) {
+    if (!out) return -200;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return fail(nullptr, e, "cudaGetDeviceCount");
+    if (count == 0 || device < 0 || device >= count) {
+        fprintf(stderr, "ndnet_b200: no CUDA device %d (found %d); this library has no CPU path\n", device, count);
+        return -201;
+    }
+    ndnet_b200_ctx *c = new (std::nothrow) ndnet_b200_ctx();
+    if (!c) return -202;
+    c->device = device;
+    *out = c;
+    return 0;
+}
+
+extern "C" void ndnet_b200_destroy(ndnet_b200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    c->ws.release();
+    c->mlp_scratch.release();
+    void *ptrs[] = {c->d_points, c->d_labels, c->d_feat, c->d_feat64, c->d_olab, c->d_ovox, c->d_info};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete c;
+}
+
+extern "C" const char *ndnet_b200_last_error(const ndnet_b200_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+// ------------------------------------------------------------------------------------------------
+// batched entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int ndnet_b200_downsample_batch(ndnet_b200_ctx *c, const void *points, int dtype, const uint16_t *labels,
+                                           int B, long N, int num_classes, long D, unsigned flags, float *out_feat,
+                                           double *out_feat64, uint16_t *out_labels, int32_t *out_voxel,
+                                           ndnet_b200_cloud_info *info, void *stream) {
+    if (!c || !points || B <= 0 || N < 0 || D <= 0 || (dtype != 0 && dtype != 1) || num_classes < 0) return -200;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, e, "cudaSetDevice");
+    e = c->ws.reserve(B, N, D, num_classes + 1);
+    if (e != cudaSuccess) return fail(c, e, "workspace allocation");
+    c->ws.last_B = B; c->ws.last_N = N; c->ws.last_D = D;
+    e = ndt::run_batch(c->ws, points, dtype, labels, B, N, num_classes, D, flags, out_feat, out_feat64, out_labels,
+                       out_voxel, (NdtCloudInfo *)info, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(c, e, "ndt::run_batch");
+    return 0;
+}
+
+extern "C" int ndnet_b200_downsample_batch_host(ndnet_b200_ctx *c, const void *points, int dtype, const uint16_t *labels,
+                                                int B, long N, int num_classes, long D, unsigned flags, float *out_feat,
+                                                double *out_feat64, uint16_t *out_labels, int32_t *out_voxel,
+                                                ndnet_b200_cloud_info *info, void *stream) {
+    if (!c || !points || B <= 0 || N < 0 || D <= 0 || (dtype != 0 && dtype != 1)) return -200;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, e, "cudaSetDevice");
+    const size_t esz = dtype == 0 ? 4 : 8;
+    const size_t pbytes = (size_t)B * N * 3 * esz;
+#define G(ptr, have, need) if ((e = grow(ptr, have, need)) != cudaSuccess) return fail(c, e, "staging allocation")
+    G(c->d_points, c->d_points_bytes, pbytes);
+    if (labels) G(c->d_labels, c->d_labels_bytes, (size_t)B * N * 2);
+    if (out_feat) G(c->d_feat, c->d_feat_bytes, (size_t)B * D * 12 * 4);
+    if (out_feat64) G(c->d_feat64, c->d_feat64_bytes, (size_t)B * D * 12 * 8);
+    if (out_labels) G(c->d_olab, c->d_olab_bytes, (size_t)B * D * 2);
+    if (out_voxel) G(c->d_ovox, c->d_ovox_bytes, (size_t)B * D * 4);
+    if (info) G(c->d_info, c->d_info_bytes, (size_t)B * sizeof(NdtCloudInfo));
+#undef G
+    if ((e = cudaMemcpyAsync(c->d_points, points, pbytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(c, e, "H2D points");
+    if (labels && (e = cudaMemcpyAsync(c->d_labels, labels, (size_t)B * N * 2, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return fail(c, e, "H2D labels");
+    int r = ndnet_b200_downsample_batch(c, c->d_points, dtype, labels ? c->d_labels : nullptr, B, N, num_classes, D, flags,
+                                        out_feat ? c->d_feat : nullptr, out_feat64 ? c->d_feat64 : nullptr,
+                                        out_labels ? c->d_olab : nullptr, out_voxel ? c->d_ovox : nullptr,
+                                        info ? (ndnet_b200_cloud_info *)c->d_info : nullptr, stream);
+    if (r != 0) return r;
+#define D2H(dst, src, bytes) if (dst && (e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(c, e, "D2H")
+    D2H(out_feat, c->d_feat, (size_t)B * D * 12 * 4);
+    D2H(out_feat64, c->d_feat64, (size_t)B * D * 12 * 8);
+    D2H(out_labels, c->d_olab, (size_t)B * D * 2);
+    D2H(out_voxel, c->d_ovox, (size_t)B * D * 4);
+    D2H(info, c->d_info, (size_t)B * sizeof(NdtCloudInfo));
+#undef D2H
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(c, e, "stream synchronise");
+    return 0;
+}
+
+extern "C" int ndnet_b200_last_point_voxels(ndnet_b200_ctx *c, int32_t *out_dev, void *stream) {
+    if (!c || !out_dev || c->ws.last_B == 0) return -200;
+    cudaError_t e = cudaMemcpyAsync(out_dev, c->ws.point_voxel, (size_t)c->ws.last_B * c->ws.last_N * 4,
+                                    cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail(c, e, "last_point_voxels");
+}
+
+extern "C" long ndnet_b200_last_kl_list(ndnet_b200_ctx *c, int b, double *div, int32_t *p_voxel, int32_t *q_voxel, long cap) {
+    if (!c || b < 0 || b >= c->ws.last_B) return -200;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail(c, e, "synchronise");
+    ndt::CloudSummary cs;
+    if ((e = ndt::read_cloud_summary(c->ws, b, &cs)) != cudaSuccess) return fail(c, e, "read state");
+    if (cs.status != 0) return 0;
+    const unsigned K = cs.K, V = cs.V;
+    const int *len = cs.len;
+    const size_t kcap = (size_t)c->ws.vcap * 6;
+    std::vector<double> d(K);
+    std::vector<unsigned> s(K), cell(V);
+    if (K) {
+        if ((e = cudaMemcpy(d.data(), c->ws.list_div + (size_t)b * kcap, K * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return fail(c, e, "D2H list");
+        if ((e = cudaMemcpy(s.data(), c->ws.list_seq + (size_t)b * kcap, K * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) return fail(c, e, "D2H list");
+    }
+    if (V && (e = cudaMemcpy(cell.data(), c->ws.vox_cell + (size_t)b * c->ws.vcap, V * 4, cudaMemcpyDeviceToHost)) != cudaSuccess)
+        return fail(c, e, "D2H cells");
+    static const int dx[6] = {1, -1, 0, 0, 0, 0}, dy[6] = {0, 0, 1, -1, 0, 0}, dz[6] = {0, 0, 0, 0, 1, -1};
+    for (unsigned i = 0; i < K && (long)i < cap; i++) {
+        const unsigned slot = s[i] / 6, dir = s[i] % 6;
+        const unsigned pc = cell[slot];
+        const int lx = len[0], ly = len[1];
+        const int z = pc / (lx * ly), y = (pc % (lx * ly)) / lx, x = pc % lx;
+        if (div) div[i] = d[i];
+        if (p_voxel) p_voxel[i] = (int32_t)pc;
+        if (q_voxel) q_voxel[i] = (int32_t)((z + dz[dir]) * lx * ly + (y + dy[dir]) * lx + (x + dx[dir]));
+    }
+    return (long)K;
+}
+
+// ------------------------------------------------------------------------------------------------
+// legacy ABI (host pointers; signatures of core_legacy/include/ndnet_core/ndt.h)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr uint32_t kMagicNd = 0x4e444e44u, kMagicKl = 0x4b4c4b4cu;
+
+struct Session;
+struct NdToken { uint32_t magic; Session *owner; };
+struct KlToken { uint32_t magic; Session *owner; };
+
+// Retained state of one ndt_downsample call (what the reference keeps in nd_array / kl_divergences),
+// device resident so that prune_nds / to_point_cloud continue on the GPU.
+struct Session {
+    NdToken nd{kMagicNd, nullptr};
+    KlToken kl{kMagicKl, nullptr};
+    bool nd_freed = false, kl_freed = false;
+    ndt::SessionState st;
+};
+
+std::mutex g_mutex;
+ndnet_b200_ctx *g_ctx = nullptr;
+
+ndnet_b200_ctx *default_ctx() {
+    if (!g_ctx) {
+        int dev = 0;
+        if (const char *e = getenv("NDNET_B200_DEVICE")) dev = atoi(e);
+        if (ndnet_b200_create(&g_ctx, dev) != 0) g_ctx = nullptr;
+    }
+    return g_ctx;
+}
+
+void maybe_delete(Session *s) {
+    if (s->nd_freed && s->kl_freed) { s->st.release(); delete s; }
+}
+
+}  // namespace
+
+extern "C" int ndt_downsample(double *point_cloud, unsigned short point_dim, unsigned long num_points,
+                              unsigned int *len_x, unsigned int *len_y, unsigned int *len_z, double *offset_x,
+                              double *offset_y, double *offset_z, double *voxel_size, unsigned short *classes,
+                              unsigned short num_classes, unsigned long num_desired_points,
+                              double *downsampled_point_cloud, unsigned long *num_downsampled_points,
+                              double *covariances, unsigned short *downsampled_classes,
+                              struct normal_distribution_t **nd_array, unsigned long *num_valid_nds,
+                              struct kl_divergence_t **kl_divergences, unsigned long *num_kl_divergences) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (nd_array) *nd_array = nullptr;
+    ndnet_b200_ctx *c = default_ctx();
+    if (!c) { fprintf(stderr, "ndt_downsample: no CUDA device available; libndnet_b200 has no CPU path\n"); return -201; }
+    if (!point_cloud || num_desired_points == 0) return -200;
+    const long N = (long)num_points, D = (long)num_desired_points;
+    // the reference reads 3 doubles per point with a hard-coded stride of 3 (normal_distributions.c:47)
+    // but takes the limits with stride point_dim (pointclouds.c:55-61); only point_dim == 3 is consistent.
+    if (point_dim != 3) { fprintf(stderr, "ndt_downsample: point_dim must be 3\n"); return -200; }
+    std::vector<double> feat((size_t)D * 12);
+    std::vector<uint16_t> lab((size_t)D);
+    ndnet_b200_cloud_info info;
+    int r = ndnet_b200_downsample_batch_host(c, point_cloud, NDNET_B200_F64, classes, 1, N, num_classes, D, 0, nullptr,
+                                             feat.data(), classes ? lab.data() : nullptr, nullptr, &info, nullptr);
+    if (r != 0) return r;
+    if (len_x) *len_x = info.len[0];
+    if (len_y) *len_y = info.len[1];
+    if (len_z) *len_z = info.len[2];
+    if (offset_x) *offset_x = info.offset[0];
+    if (offset_y) *offset_y = info.offset[1];
+    if (offset_z) *offset_z = info.offset[2];
+    if (voxel_size) *voxel_size = info.voxel_size;
+    if (info.status != 0) {
+        if (info.status == -3) fprintf(stderr, "Reached maximum number of iterations!\n");          // ndt.c:192
+        else fprintf(stderr, "Error allocating memory for normal distributions: grid too large\n");   // ndt.c:153
+        return info.status;
+    }
+    for (uint32_t i = 0; i < info.num_out; i++) {
+        if (downsampled_point_cloud) memcpy(downsampled_point_cloud + (size_t)i * 3, feat.data() + (size_t)i * 12, 3 * sizeof(double));
+        if (covariances) memcpy(covariances + (size_t)i * 9, feat.data() + (size_t)i * 12 + 3, 9 * sizeof(double));
+        if (downsampled_classes && classes) downsampled_classes[i] = lab[i];
+    }
+    if (num_downsampled_points) *num_downsampled_points = info.num_out;
+    if (num_valid_nds) *num_valid_nds = info.num_valid;
+    if (num_kl_divergences) *num_kl_divergences = info.num_kl_after;
+    if (info.prune_status == -2) fprintf(stderr, "Reached the end of the divergences array!\n");     // ndt.c:54
+    // retain the state for prune_nds / to_point_cloud
+    Session *s = new (std::nothrow) Session();
+    if (!s) return -202;
+    s->nd.owner = s; s->kl.owner = s;
+    cudaError_t e = s->st.capture(c->ws, 0, classes != nullptr);
+    if (e != cudaSuccess) { s->st.release(); delete s; return fail(c, e, "session capture"); }
+    if (nd_array) *nd_array = (struct normal_distribution_t *)&s->nd; else s->nd_freed = true;
+    if (kl_divergences) *kl_divergences = (struct kl_divergence_t *)&s->kl; else s->kl_freed = true;
+    if (s->nd_freed && s->kl_freed) maybe_delete(s);
+    return 0;
+}
+
+extern "C" int prune_nds(struct normal_distribution_t *nd_array, unsigned int len_x, unsigned int len_y, unsigned int len_z,
+                         unsigned long num_desired_nds, unsigned long *num_valid_nds,
+                         struct kl_divergence_t *kl_divergences, unsigned long *num_kl_divergences) {
+    (void)len_x; (void)len_y; (void)len_z;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    NdToken *t = (NdToken *)nd_array;
+    KlToken *k = (KlToken *)kl_divergences;
+    if (!t || t->magic != kMagicNd || !k || k->magic != kMagicKl || k->owner != t->owner) {
+        fprintf(stderr, "prune_nds: handles were not produced by this library's ndt_downsample\n");
+        return -200;
+    }
+    Session *s = t->owner;
+    if (num_valid_nds && num_desired_nds > *num_valid_nds) {
+        fprintf(stderr, "Number of desired normal distributions is greater than the number valid distributions!\n");  // ndt.c:37
+        return -1;
+    }
+    unsigned valid = 0, nkl = 0; int ret = 0;
+    cudaError_t e = s->st.prune((unsigned long)num_desired_nds, &valid, &nkl, &ret);
+    if (e != cudaSuccess) return fail(g_ctx, e, "session prune");
+    if (num_valid_nds) *num_valid_nds = valid;
+    if (num_kl_divergences) *num_kl_divergences = nkl;
+    if (ret == -2) fprintf(stderr, "Reached the end of the divergences array!\n");
+    return ret;
+}
+
+extern "C" int to_point_cloud(struct normal_distribution_t *nd_array, unsigned int len_x, unsigned int len_y, unsigned int len_z,
+                              double offset_x, double offset_y, double offset_z, double voxel_size, double *point_cloud,
+                              unsigned long *num_points, double *covariances, unsigned short *classes) {
+    (void)len_x; (void)len_y; (void)len_z; (void)offset_x; (void)offset_y; (void)offset_z; (void)voxel_size;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    NdToken *t = (NdToken *)nd_array;
+    if (!t || t->magic != kMagicNd) {
+        fprintf(stderr, "to_point_cloud: handle was not produced by this library's ndt_downsample\n");
+        return -200;
+    }
+    Session *s = t->owner;
+    std::vector<double> feat;
+    std::vector<uint16_t> lab;
+    unsigned rows = 0;
+    cudaError_t e = s->st.output(feat, lab, &rows);
+    if (e != cudaSuccess) return fail(g_ctx, e, "session output");
+    // The reference writes every surviving row; callers size buffers for the number they asked for,
+    // which equals the survivor count unless a walk stopped early (A15).
+    for (unsigned i = 0; i < rows; i++) {
+        if (point_cloud) memcpy(point_cloud + (size_t)i * 3, feat.data() + (size_t)i * 12, 3 * sizeof(double));
+        if (covariances) memcpy(covariances + (size_t)i * 9, feat.data() + (size_t)i * 12 + 3, 9 * sizeof(double));
+        if (classes && s->st.has_labels) classes[i] = lab[i];
+    }
+    if (num_points) *num_points = rows;
+    return 0;
+}
+
+extern "C" void free_nds(struct normal_distribution_t *nd_array, unsigned long num_nds) {
+    (void)num_nds;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    NdToken *t = (NdToken *)nd_array;
+    if (!t || t->magic != kMagicNd) return;     // NULL after a failed downsample (A16): never crash
+    Session *s = t->owner;
+    if (s->nd_freed) return;
+    s->nd_freed = true;
+    t->magic = 0;
+    maybe_delete(s);
+}
+
+extern "C" void free_kl_divergences(struct kl_divergence_t *kl_divergences) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    KlToken *t = (KlToken *)kl_divergences;
+    if (!t || t->magic != kMagicKl) return;
+    Session *s = t->owner;
+    if (s->kl_freed) return;
+    s->kl_freed = true;
+    t->magic = 0;
+    maybe_delete(s);
+}
+
+extern "C" void print_matrix(double *matrix, int rows, int cols) {
+    // core_legacy/src/matrix.c:28-35
+    for (int i = 0; i < rows; i++) {
+        for (int j = 0; j < cols; j++) printf("%f ", matrix[i * cols + j]);
+        printf("\n");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// model entry points: thin shims over mlp.cu
+// ------------------------------------------------------------------------------------------------
+struct ndnet_b200_model { mlp::Model m; };
+
+extern "C" int ndnet_b200_model_create(ndnet_b200_ctx *c, ndnet_b200_model **model, int kind, int n_tensors,
+                                       const char *const *names, const float *const *data,
+                                       const int64_t *const *shapes, const int *ndims) {
+    if (!c || !model || n_tensors <= 0 || !names || !data || !shapes || !ndims) return -200;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, e, "cudaSetDevice");
+    ndnet_b200_model *m = new (std::nothrow) ndnet_b200_model();
+    if (!m) return -202;
+    std::string err;
+    int r = m->m.build(kind, n_tensors, names, data, shapes, ndims, err);
+    if (r != 0) { c->err = err; fprintf(stderr, "ndnet_b200_model_create: %s\n", err.c_str()); m->m.release(); delete m; return r; }
+    *model = m;
+    return 0;
+}
+
+extern "C" void ndnet_b200_model_destroy(ndnet_b200_model *m) {
+    if (!m) return;
+    m->m.release();
+    delete m;
+}
+
+extern "C" int ndnet_b200_model_forward(ndnet_b200_ctx *c, ndnet_b200_model *m, const float *feat, int B, int D, float *out,
+                                        void *stream) {
+    if (!c || !m || !feat || !out || B <= 0 || D <= 0) return -200;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, e, "cudaSetDevice");
+    std::string err;
+    int r = m->m.forward(c->mlp_scratch, feat, B, D, out, (cudaStream_t)stream, err);
+    if (r != 0) { c->err = err; fprintf(stderr, "ndnet_b200_model_forward: %s\n", err.c_str()); }
+    return r;
+}

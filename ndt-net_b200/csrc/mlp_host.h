@@ -1,0 +1,25 @@
+// mlp_host.h — host-side interface of the PointNet / NDT-Net forward (mlp.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <string>
+
+namespace mlp {
+
+struct Scratch {
+    void *buf = nullptr; size_t bytes = 0;
+    cudaError_t reserve(size_t need);
+    void release();
+};
+
+struct ModelImpl;
+
+struct Model {
+    ModelImpl *impl = nullptr;
+    int build(int kind, int n_tensors, const char *const *names, const float *const *data, const int64_t *const *shapes,
+              const int *ndims, std::string &err);
+    int forward(Scratch &scratch, const float *feat, int B, int D, float *out, cudaStream_t st, std::string &err);
+    void release();
+};
+
+}  // namespace mlp

@@ -1,0 +1,76 @@
+// ndt_host.h — host-side declarations shared by the kernels and the C ABI.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <vector>
+
+namespace ndt {
+
+struct CloudState;
+
+// must match ndnet_b200_cloud_info in include/ndnet_b200.h
+struct NdtCloudInfo {
+    int32_t status, prune_status, evaluations;
+    uint32_t len[3];
+    uint32_t num_voxels, num_valid, num_kl, num_kl_after, num_out, num_survivors;
+    double voxel_size;
+    double offset[3];
+    double limits[6];
+};
+
+// Device workspace for a batch of up to B_cap clouds x N_cap points, D_cap desired distributions.
+struct Workspace {
+    int B_cap = 0; long N_cap = 0; long D_cap = 0; int bins_cap = 0;
+    unsigned vcap = 0;             // max occupied voxels per cloud = floor(1.2*D)+2
+    size_t bitmap_stride = 0;      // uint2 {bits, prefix} words per cloud
+    int ntiles_cap = 0;
+    CloudState *states = nullptr;
+    unsigned long long *lim_enc = nullptr;
+    uint2 *bitmap = nullptr;
+    unsigned *vox_cell = nullptr, *vox_n = nullptr, *vox_start = nullptr;
+    unsigned *slot_rank = nullptr, *tile_cnt = nullptr, *hist = nullptr;
+    int *point_voxel = nullptr;
+    void *sorted = nullptr;
+    double *mean = nullptr, *cov = nullptr, *cov_final = nullptr;
+    uint16_t *cls = nullptr;
+    double *kl_div = nullptr; unsigned char *kl_flag = nullptr;
+    unsigned long long *key = nullptr; unsigned *seq = nullptr;
+    unsigned *firstpos = nullptr; unsigned char *removed = nullptr;
+    double *list_div = nullptr; unsigned *list_seq = nullptr;
+    // of the last run
+    int last_B = 0; long last_N = 0; long last_D = 0;
+
+    cudaError_t reserve(int B, long N, long D, int bins);
+    void release();
+};
+
+cudaError_t run_batch(Workspace &w, const void *pts, int dtype, const uint16_t *labels, int B, long N, int num_classes,
+                      long D, unsigned flags, float *out_feat, double *out_feat64, uint16_t *out_labels, int *out_voxel,
+                      NdtCloudInfo *info, cudaStream_t st);
+
+size_t cloud_state_size();
+
+// host copy of the scalar results of one cloud of the last batch
+struct CloudSummary { int status; int len[3]; unsigned V, K, n_valid, walk; int prune_ret; };
+cudaError_t read_cloud_summary(const Workspace &w, int b, CloudSummary *out);
+
+// Device-resident state one legacy ndt_downsample call retains for prune_nds / to_point_cloud
+// (the reference keeps it in the nd_array / kl_divergences allocations, ndt.c:151,198).
+struct SessionState {
+    unsigned V = 0, K = 0, start = 0;      // start = first list entry still in the list
+    unsigned n_valid = 0, num_kl = 0;      // counters as the reference reports them
+    bool has_labels = false;
+    unsigned *vox_cell = nullptr; unsigned char *removed = nullptr;
+    double *mean = nullptr, *cov_final = nullptr; uint16_t *cls = nullptr;
+    unsigned *list_seq = nullptr; unsigned *firstpos = nullptr;
+    unsigned *d_result = nullptr;          // 4 words: n_removed, new start, ret flag, rows
+    double *d_feat = nullptr; uint16_t *d_lab = nullptr;
+
+    cudaError_t capture(const Workspace &w, int b, bool labels);
+    cudaError_t prune(unsigned long desired, unsigned *valid, unsigned *nkl, int *ret);
+    cudaError_t output(std::vector<double> &feat, std::vector<uint16_t> &lab, unsigned *rows);
+    void release();
+};
+
+}  // namespace ndt

@@ -1,0 +1,888 @@
+// ndt_kernels.cu — the batched NDT hot path for B200 (sm_100a): bounding box, voxel-size search,
+// stable voxel assignment, per-voxel sequential statistics, neighbour pseudo-KL with LU-history
+// emulation, descending stable sort with the NaN rule, head-first prune, ascending compaction.
+//
+// Compiled with -fmad=false (see ndt_device.cuh).  Replaces /root/reference/core_legacy/src/
+// {pointclouds,voxel,normal_distributions,kullback_leibler,ndt}.c for a whole batch of clouds per
+// launch sequence; nothing here synchronises with the host.
+#include "ndt_host.h"
+#include "ndt_device.cuh"
+
+#include <cstdio>
+
+namespace ndt {
+
+// ------------------------------------------------------------------------------------------------
+// K1  bounding box (pointclouds.c:40-66).  grid (chunks, B), block 256.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_limits(const T *__restrict__ pts, long N, unsigned long long *__restrict__ lim_enc) {
+    const int b = blockIdx.y;
+    const T *p = pts + (size_t)b * N * 3;
+    T mx[3], mn[3];
+    bool any = false;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
+        const T x = p[i * 3 + 0], y = p[i * 3 + 1], z = p[i * 3 + 2];
+        if (!any) { mx[0] = mn[0] = x; mx[1] = mn[1] = y; mx[2] = mn[2] = z; any = true; }
+        else {
+            mx[0] = x > mx[0] ? x : mx[0]; mn[0] = x < mn[0] ? x : mn[0];
+            mx[1] = y > mx[1] ? y : mx[1]; mn[1] = y < mn[1] ? y : mn[1];
+            mx[2] = z > mx[2] ? z : mx[2]; mn[2] = z < mn[2] ? z : mn[2];
+        }
+    }
+    // warp reduce through the order-preserving encoding, then one atomic per warp
+    unsigned long long e[6];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        e[a] = any ? enc_f64((double)mx[a]) : 0ull;
+        e[3 + a] = any ? enc_f64((double)mn[a]) : ~0ull;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            unsigned long long v = __shfl_xor_sync(0xffffffffu, e[a], o);
+            e[a] = v > e[a] ? v : e[a];
+            unsigned long long w = __shfl_xor_sync(0xffffffffu, e[3 + a], o);
+            e[3 + a] = w < e[3 + a] ? w : e[3 + a];
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            atomicMax(&lim_enc[b * 6 + a], e[a]);
+            atomicMin(&lim_enc[b * 6 + 3 + a], e[3 + a]);
+        }
+    }
+}
+
+// grid + risk flag for a guess (voxel.c:61-81); returns false when the grid cannot be held
+__device__ bool set_grid(CloudState &s) {
+    double q[3];
+    bool risky = false;
+    double cells = 1.0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const double dim = s.lim[a] - s.lim[3 + a];
+        q[a] = dim / s.guess;
+        const double c = ceil(q[a]);
+        if (!(c >= 0.0) || c > 2147483647.0) return false;
+        s.len[a] = (int)c;
+        s.off[a] = s.lim[3 + a];
+        if (c == q[a]) risky = true;   // floor(q) == len is reachable (A4); includes degenerate axes (len 0)
+        cells *= c;
+    }
+    if (cells > (double)kMaxGridCells) return false;
+    s.G = (unsigned)s.len[0] * (unsigned)s.len[1] * (unsigned)s.len[2];
+    s.nwords = (s.G + 31u) >> 5;
+    s.risky = risky ? 1 : 0;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  search bookkeeping (ndt.c:136-194).  grid B, block 256.  phase 0 = initialise from the limits,
+// phase 1 = count the bitmap of the pass that just ran and accept / bisect.
+// On acceptance it also builds the voxel directory: per word {bits, prefix popcount} and the list of
+// occupied cell ids in ascending order (slot -> cell).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_decide(CloudState *__restrict__ states, const unsigned long long *__restrict__ lim_enc,
+                                                uint2 *__restrict__ bitmap, size_t bitmap_stride,
+                                                unsigned *__restrict__ vox_cell, unsigned vcap, long num_desired, int phase) {
+    const int b = blockIdx.x;
+    CloudState &s = states[b];
+    uint2 *bm = bitmap + (size_t)b * bitmap_stride;
+    __shared__ unsigned s_part[8];
+    __shared__ unsigned s_total;
+    __shared__ int s_action;   // 0 nothing, 1 zero bitmap for next pass, 2 accepted -> build directory
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    if (phase == 0) {
+        if (tid == 0) {
+            for (int a = 0; a < 3; a++) {
+                const double m = dec_f64(lim_enc[b * 6 + a]);
+                s.lim[a] = m > DBL_MIN ? m : DBL_MIN;              // pointclouds.c:44-46,55-61 (A2)
+                const double n = dec_f64(lim_enc[b * 6 + 3 + a]);
+                s.lim[3 + a] = n < DBL_MAX ? n : DBL_MAX;
+            }
+            s.guess = (double)(kMaxVoxelGuess - kMinVoxelGuess) / 2.0;   // ndt.c:136
+            s.lo = kMinVoxelGuess; s.hi = kMaxVoxelGuess;
+            s.iter = 0; s.evals = 0; s.V = 0; s.K = 0; s.n_valid = 0; s.walk = 0; s.prune_ret = 0; s.n_out = 0;
+            s.n_survivors = 0;
+            for (int w = 0; w < kWorkers; w++) s.fail[w] = kDropped;
+            s.status = 1;
+            if (!set_grid(s)) { s.status = -1; s.G = 0; s.nwords = 0; }
+            s_action = s.status == 1 ? 1 : 0;
+        }
+        __syncthreads();
+    } else {
+        if (s.status != 1) return;
+        // count occupied cells of the pass
+        unsigned cnt = 0;
+        for (unsigned w = tid; w < s.nwords; w += blockDim.x) cnt += __popc(bm[w].x);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) s_part[wid] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned total = 0;
+            for (int w = 0; w < 8; w++) total += s_part[w];
+            s_total = total;
+            s.evals++;
+            const unsigned long num_nds = total;
+            const unsigned long D = (unsigned long)num_desired;
+            if ((double)num_nds > (double)D * (1 + kUpperThreshold)) { s.lo = s.guess; s_action = 1; }      // ndt.c:169
+            else if (num_nds < D) { s.hi = s.guess; s_action = 1; }                                            // ndt.c:171
+            else { s_action = 2; s.status = 0; s.V = total; }
+            if (s_action == 1) {
+                s.guess = s.lo + (s.hi - s.lo) / 2.0;                                                          // ndt.c:183
+                s.iter++;
+                if (s.iter >= kMaxGuessIterations) { s.status = -3; s_action = 0; }                            // ndt.c:187-194
+                else {
+                    for (int w = 0; w < kWorkers; w++) s.fail[w] = kDropped;
+                    if (!set_grid(s)) { s.status = -1; s_action = 0; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (s_action == 1) {
+        for (unsigned w = tid; w < s.nwords; w += blockDim.x) bm[w] = make_uint2(0u, 0u);
+    } else if (s_action == 2) {
+        // exclusive prefix popcount over the words + slot -> cell list
+        __shared__ unsigned s_carry;
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        for (unsigned base = 0; base < s.nwords; base += blockDim.x) {
+            const unsigned w = base + tid;
+            const unsigned bits = w < s.nwords ? bm[w].x : 0u;
+            const unsigned c = __popc(bits);
+            unsigned inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            if (lane == 31) s_part[wid] = inc;
+            __syncthreads();
+            unsigned woff = 0;
+            for (int k = 0; k < wid; k++) woff += s_part[k];
+            unsigned blk_total = 0;
+            for (int k = 0; k < 8; k++) blk_total += s_part[k];
+            const unsigned excl = s_carry + woff + inc - c;
+            if (w < s.nwords) {
+                bm[w].y = excl;
+                unsigned rest = bits, k = 0;
+                while (rest) {
+                    const int bit = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    if (excl + k < vcap) vox_cell[(size_t)b * vcap + excl + k] = w * 32u + (unsigned)bit;
+                    k++;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_carry += blk_total;
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  one estimate pass reduced to what the search needs: which cells are occupied
+// (normal_distributions.c:28-137 without the statistics).  grid (chunks, B), block 256, each CTA owns
+// kCountPointsPerCta consecutive points.  Small grids are marked in a shared-memory bitmap and merged
+// with one atomicOr per non-zero word; large grids go straight to the global bitmap.
+// A "risky" grid (A4) is handled by CTA 0 alone in two phases so that the worker-chunk early-return
+// semantics are exact.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void load_point(const T *p, long i, double &x, double &y, double &z) {
+    x = (double)p[i * 3 + 0]; y = (double)p[i * 3 + 1]; z = (double)p[i * 3 + 2];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N, CloudState *__restrict__ states,
+                                               uint2 *__restrict__ bitmap, size_t bitmap_stride) {
+    const int b = blockIdx.y;
+    CloudState &s = states[b];
+    if (s.status != 1) return;
+    __shared__ unsigned s_bits[kSmemBitmapBits / 32];
+    __shared__ unsigned s_fail[kWorkers];
+    const T *p = pts + (size_t)b * N * 3;
+    uint2 *bm = bitmap + (size_t)b * bitmap_stride;
+    const unsigned G = s.G, nwords = s.nwords;
+    if (G == 0) return;                                  // a degenerate axis: no voxel can be valid (A3)
+    const double vs = s.guess;
+    const double off[3] = {s.off[0], s.off[1], s.off[2]};
+    const int len[3] = {s.len[0], s.len[1], s.len[2]};
+    const long chunk = N / kWorkers;
+    const long n_used = chunk * kWorkers;               // the last N % 8 points are never voxelised (A5)
+    const bool use_smem = G <= kSmemBitmapBits;
+
+    if (s.risky) {
+        if (blockIdx.x != 0) return;
+        if (threadIdx.x < kWorkers) s_fail[threadIdx.x] = kDropped;
+        if (use_smem) for (unsigned w = threadIdx.x; w < nwords; w += blockDim.x) s_bits[w] = 0u;
+        __syncthreads();
+        for (long i = threadIdx.x; i < n_used; i += blockDim.x) {
+            double x, y, z; load_point(p, i, x, y, z);
+            unsigned id;
+            if (!voxel_of(x, y, z, off, vs, len, id)) atomicMin(&s_fail[i / chunk], (unsigned)i);
+        }
+        __syncthreads();
+        for (long i = threadIdx.x; i < n_used; i += blockDim.x) {
+            if ((unsigned)i >= s_fail[i / chunk]) continue;
+            double x, y, z; load_point(p, i, x, y, z);
+            unsigned id;
+            voxel_of(x, y, z, off, vs, len, id);
+            if (use_smem) atomicOr(&s_bits[id >> 5], 1u << (id & 31));
+            else atomicOr(&bm[id >> 5].x, 1u << (id & 31));
+        }
+        __syncthreads();
+        if (threadIdx.x < kWorkers) s.fail[threadIdx.x] = s_fail[threadIdx.x];
+        if (use_smem) for (unsigned w = threadIdx.x; w < nwords; w += blockDim.x) if (s_bits[w]) bm[w].x = s_bits[w];
+        return;
+    }
+
+    const long begin = (long)blockIdx.x * kCountPointsPerCta;
+    if (begin >= n_used) return;
+    const long end = begin + kCountPointsPerCta < n_used ? begin + kCountPointsPerCta : n_used;
+    if (use_smem) {
+        for (unsigned w = threadIdx.x; w < nwords; w += blockDim.x) s_bits[w] = 0u;
+        __syncthreads();
+        for (long i = begin + threadIdx.x; i < end; i += blockDim.x) {
+            double x, y, z; load_point(p, i, x, y, z);
+            unsigned id;
+            if (voxel_of(x, y, z, off, vs, len, id)) atomicOr(&s_bits[id >> 5], 1u << (id & 31));
+        }
+        __syncthreads();
+        for (unsigned w = threadIdx.x; w < nwords; w += blockDim.x) {
+            const unsigned v = s_bits[w];
+            if (v) atomicOr(&bm[w].x, v);
+        }
+    } else {
+        for (long i = begin + threadIdx.x; i < end; i += blockDim.x) {
+            double x, y, z; load_point(p, i, x, y, z);
+            unsigned id;
+            if (voxel_of(x, y, z, off, vs, len, id)) atomicOr(&bm[id >> 5].x, 1u << (id & 31));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4  stable voxel assignment, step 1: every warp walks one tile of kRankTile consecutive points in
+// order and gives each point (slot, rank among earlier points of the tile in the same slot).
+// grid (ceil(tiles/4), B), block 128 (4 warps = 4 tiles); dynamic smem 4 * vcap u16 counters.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N, const CloudState *__restrict__ states,
+                                              const uint2 *__restrict__ bitmap, size_t bitmap_stride, unsigned vcap,
+                                              int ntiles, unsigned *__restrict__ slot_rank, unsigned *__restrict__ tile_cnt,
+                                              int *__restrict__ point_voxel) {
+    extern __shared__ unsigned short s_cnt_all[];
+    const int b = blockIdx.y;
+    const CloudState &s = states[b];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tile = blockIdx.x * 4 + wid;
+    if (tile >= ntiles) return;
+    unsigned *sr = slot_rank + (size_t)b * N;
+    int *pv = point_voxel ? point_voxel + (size_t)b * N : nullptr;
+    const long begin = (long)tile * kRankTile;
+    const long tend = begin + kRankTile < N ? begin + kRankTile : N;
+    if (s.status != 0) {
+        for (long i = begin + lane; i < tend; i += 32) { sr[i] = kDropped; if (pv) pv[i] = -1; }
+        return;
+    }
+    unsigned short *cnt = s_cnt_all + (size_t)wid * vcap;
+    const unsigned V = s.V;
+    for (unsigned v = lane; v < V; v += 32) cnt[v] = 0;
+    __syncwarp();
+    const T *p = pts + (size_t)b * N * 3;
+    const uint2 *bm = bitmap + (size_t)b * bitmap_stride;
+    const double vs = s.guess;
+    const double off[3] = {s.off[0], s.off[1], s.off[2]};
+    const int len[3] = {s.len[0], s.len[1], s.len[2]};
+    const long chunk = N / kWorkers;
+    const long n_used = chunk * kWorkers;
+    for (long base = begin; base < tend; base += 32) {
+        const long i = base + lane;
+        unsigned slot = kDropped;
+        unsigned id = 0;
+        if (i < n_used && (unsigned)i < s.fail[i / chunk]) {
+            double x, y, z; load_point(p, i, x, y, z);
+            if (voxel_of(x, y, z, off, vs, len, id)) {
+                const uint2 w = bm[id >> 5];
+                slot = w.y + __popc(w.x & ((1u << (id & 31)) - 1u));
+            }
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, slot);
+        unsigned packed = kDropped;
+        if (slot != kDropped) {
+            const unsigned before = __popc(peers & ((1u << lane) - 1u));
+            const unsigned basec = cnt[slot];
+            packed = slot * (unsigned)kRankTile + basec + before;
+            __syncwarp(peers);
+            if (lane == 31 - __clz(peers)) cnt[slot] = (unsigned short)(basec + __popc(peers));
+        }
+        __syncwarp();
+        if (i < tend) { sr[i] = packed; if (pv) pv[i] = slot != kDropped ? (int)id : -1; }
+    }
+    __syncwarp();
+    unsigned *tc = tile_cnt + ((size_t)b * ntiles + tile) * vcap;
+    for (unsigned v = lane; v < V; v += 32) tc[v] = cnt[v];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5  stable voxel assignment, step 2: per slot, turn the per-tile counts into exclusive prefixes and
+// the slot totals into segment starts.  grid B, block 1024.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_offsets(const CloudState *__restrict__ states, unsigned vcap, int ntiles,
+                                                  unsigned *__restrict__ tile_cnt, unsigned *__restrict__ vox_n,
+                                                  unsigned *__restrict__ vox_start) {
+    const int b = blockIdx.x;
+    const CloudState &s = states[b];
+    if (s.status != 0) return;
+    const unsigned V = s.V;
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    unsigned *tc = tile_cnt + (size_t)b * ntiles * vcap;
+    for (unsigned base = 0; base < V; base += blockDim.x) {
+        const unsigned v = base + tid;
+        unsigned acc = 0;
+        if (v < V) {
+            for (int t = 0; t < ntiles; t++) {
+                const unsigned c = tc[(size_t)t * vcap + v];
+                tc[(size_t)t * vcap + v] = acc;
+                acc += c;
+            }
+            vox_n[(size_t)b * vcap + v] = acc;
+        }
+        unsigned inc = acc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        unsigned woff = 0, total = 0;
+        for (int k = 0; k < 32; k++) { const unsigned x = s_warp[k]; if (k < wid) woff += x; total += x; }
+        if (v < V) vox_start[(size_t)b * (vcap + 1) + v] = s_carry + woff + inc - acc;
+        __syncthreads();
+        if (tid == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (tid == 0) vox_start[(size_t)b * (vcap + 1) + V] = s_carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6  stable voxel assignment, step 3: scatter the points into voxel-major, ascending-index order;
+// vote labels into the per-voxel histogram.  grid (chunks, B), block 256.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_scatter(const T *__restrict__ pts, const uint16_t *__restrict__ labels, long N,
+                                                 const CloudState *__restrict__ states, unsigned vcap, int ntiles,
+                                                 const unsigned *__restrict__ slot_rank, const unsigned *__restrict__ tile_cnt,
+                                                 const unsigned *__restrict__ vox_start, T *__restrict__ sorted,
+                                                 unsigned *__restrict__ hist, int nbins) {
+    const int b = blockIdx.y;
+    if (states[b].status != 0) return;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const unsigned packed = slot_rank[(size_t)b * N + i];
+    if (packed == kDropped) return;
+    const unsigned slot = packed / (unsigned)kRankTile, rank = packed % (unsigned)kRankTile;
+    const int tile = (int)(i / kRankTile);
+    const unsigned pos = vox_start[(size_t)b * (vcap + 1) + slot] + tile_cnt[((size_t)b * ntiles + tile) * vcap + slot] + rank;
+    const T *p = pts + ((size_t)b * N + i) * 3;
+    T *q = sorted + ((size_t)b * N + pos) * 3;
+    q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
+    if (labels) {
+        const unsigned l = labels[(size_t)b * N + i];
+        if (l < (unsigned)nbins) atomicAdd(&hist[((size_t)b * vcap + slot) * nbins + l], 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7  per-voxel statistics: the literal sequential recurrence of normal_distributions.c:76-104 over
+// the voxel's points in ascending index order (bit-exact; the off-diagonal is order dependent, A6),
+// plus the label vote (:107-121).  One thread per voxel.  grid (ceil(vcap/128), B), block 128.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
+                                               const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
+                                               const unsigned *__restrict__ hist, int nbins,
+                                               double *__restrict__ mean, double *__restrict__ cov, uint16_t *__restrict__ cls) {
+    const int b = blockIdx.y;
+    const CloudState &s = states[b];
+    if (s.status != 0) return;
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= s.V) return;
+    const unsigned st = vox_start[(size_t)b * (vcap + 1) + v], en = vox_start[(size_t)b * (vcap + 1) + v + 1];
+    const T *p = sorted + ((size_t)b * N + st) * 3;
+    double mu0 = 0, mu1 = 0, mu2 = 0, m20 = 0, m21 = 0, m22 = 0, c01 = 0, c02 = 0, c12 = 0;
+    double cnt = 0.0;
+    for (unsigned k = 0; k < en - st; k++) {
+        const double x0 = (double)p[k * 3 + 0], x1 = (double)p[k * 3 + 1], x2 = (double)p[k * 3 + 2];
+        cnt += 1.0;                               // exact for counts < 2^53
+        // j = 0
+        const double o0 = mu0;
+        mu0 += (x0 - mu0) / cnt;
+        m20 += (x0 - o0) * (x0 - mu0);
+        c01 += (x0 - mu0) * (x1 - mu1) / cnt;     // mu1, mu2 still old here
+        if (isnan(c01)) c01 = 0.0;
+        c02 += (x0 - mu0) * (x2 - mu2) / cnt;
+        if (isnan(c02)) c02 = 0.0;
+        // j = 1
+        const double o1 = mu1;
+        mu1 += (x1 - mu1) / cnt;
+        m21 += (x1 - o1) * (x1 - mu1);
+        c12 += (x1 - mu1) * (x2 - mu2) / cnt;
+        if (isnan(c12)) c12 = 0.0;
+        // j = 2
+        const double o2 = mu2;
+        mu2 += (x2 - mu2) / cnt;
+        m22 += (x2 - o2) * (x2 - mu2);
+    }
+    double v0 = m20 / cnt, v1 = m21 / cnt, v2 = m22 / cnt;
+    if (isnan(v0)) v0 = 0.0;
+    if (isnan(v1)) v1 = 0.0;
+    if (isnan(v2)) v2 = 0.0;
+    double *mo = mean + ((size_t)b * vcap + v) * 3;
+    mo[0] = mu0; mo[1] = mu1; mo[2] = mu2;
+    double *co = cov + ((size_t)b * vcap + v) * 9;
+    co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
+    if (hist) {
+        const unsigned *h = hist + ((size_t)b * vcap + v) * nbins;
+        unsigned best = 0; uint16_t c = 0;
+        for (int j = 0; j < nbins; j++) { const unsigned x = h[j]; if (x > best) { best = x; c = (uint16_t)j; } }
+        cls[(size_t)b * vcap + v] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8  neighbour pseudo-KL (kullback_leibler.c:28-202) in closed "event index" form.
+//
+// The reference LU-factorises both covariances IN PLACE on every call where both voxels have more
+// than one sample (A10), while traversing voxels in ascending index and directions X+,X-,Y+,Y-,Z+,Z-.
+// So the matrix a voxel contributes to a given call is LU^k(Sigma), k = number of qualifying calls
+// that touched it earlier.  For voxel A the touch order is: as q of its Z-, Y-, X- neighbours, as p in
+// its own six directions, as q of its X+, Y+, Z+ neighbours.  One thread per voxel replays A's own
+// chain and, for each of its calls, the neighbour's chain up to the needed index.  It also emits the
+// final (mangled) covariance that to_point_cloud exports (ndt.c:107).
+// grid (ceil(vcap/64), B), block 64.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int neighbor_slot(const uint2 *bm, unsigned idx, int lx, int ly, int lz, int dir) {
+    // voxel.c:116-175 (unsigned wrap at 0 included)
+    unsigned z = idx / (unsigned)(lx * ly), y = (idx % (unsigned)(lx * ly)) / (unsigned)lx, x = idx % (unsigned)lx;
+    switch (dir) {
+        case 0: x += 1u; break;
+        case 1: x -= 1u; break;
+        case 2: y += 1u; break;
+        case 3: y -= 1u; break;
+        case 4: z += 1u; break;
+        default: z -= 1u; break;
+    }
+    if (x >= (unsigned)lx || y >= (unsigned)ly || z >= (unsigned)lz) return -1;
+    const unsigned n = z * (unsigned)lx * (unsigned)ly + y * (unsigned)lx + x;
+    const uint2 w = bm[n >> 5];
+    if (!((w.x >> (n & 31)) & 1u)) return -1;
+    return (int)(w.y + __popc(w.x & ((1u << (n & 31)) - 1u)));
+}
+
+__global__ void __launch_bounds__(64) k_kl(const CloudState *__restrict__ states, unsigned vcap,
+                                           const uint2 *__restrict__ bitmap, size_t bitmap_stride,
+                                           const unsigned *__restrict__ vox_cell, const unsigned *__restrict__ vox_n,
+                                           const double *__restrict__ cov, double *__restrict__ cov_final,
+                                           double *__restrict__ kl_div, unsigned char *__restrict__ kl_flag) {
+    const int b = blockIdx.y;
+    const CloudState &s = states[b];
+    if (s.status != 0) return;
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= s.V) return;
+    const uint2 *bm = bitmap + (size_t)b * bitmap_stride;
+    const unsigned *vn = vox_n + (size_t)b * vcap;
+    const unsigned *vc = vox_cell + (size_t)b * vcap;
+    const double *cv = cov + (size_t)b * vcap * 9;
+    const int lx = s.len[0], ly = s.len[1], lz = s.len[2];
+    const unsigned cell = vc[v];
+    const unsigned nA = vn[v];
+
+    int nb[kDirs]; unsigned nn[kDirs];
+#pragma unroll
+    for (int d = 0; d < kDirs; d++) {
+        nb[d] = neighbor_slot(bm, cell, lx, ly, lz, d);
+        nn[d] = nb[d] >= 0 ? vn[nb[d]] : 0u;
+    }
+    double A[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) A[i] = cv[(size_t)v * 9 + i];
+    double *out_div = kl_div + ((size_t)b * vcap + v) * kDirs;
+    unsigned char *out_flag = kl_flag + ((size_t)b * vcap + v) * kDirs;
+
+    if (nA > 1) {
+        // calls that reached A as q before its own turn: from Z- (dir 5), Y- (dir 3), X- (dir 1) neighbours
+        const int pre = (nn[5] > 1) + (nn[3] > 1) + (nn[1] > 1);
+        int perm, sgn;
+        for (int k = 0; k < pre; k++) lu3(A, perm, sgn);
+    }
+#pragma unroll 1
+    for (int d = 0; d < kDirs; d++) {
+        if (nb[d] < 0) { out_flag[d] = 0; continue; }
+        if (nA <= 1 || nn[d] <= 1) { out_div[d] = 0.0; out_flag[d] = 1; continue; }   // -1: div 0 still inserted (A11)
+        int pperm, psign;
+        lu3(A, pperm, psign);
+        // neighbour B's chain
+        const unsigned bslot = (unsigned)nb[d];
+        const unsigned bcell = vc[bslot];
+        int qual[kDirs];
+#pragma unroll
+        for (int e = 0; e < kDirs; e++) {
+            const int ns = neighbor_slot(bm, bcell, lx, ly, lz, e);
+            qual[e] = (ns >= 0 && vn[ns] > 1) ? 1 : 0;
+        }
+        const int all = qual[0] + qual[1] + qual[2] + qual[3] + qual[4] + qual[5];
+        const int early = qual[5] + qual[3] + qual[1];
+        int kB;
+        switch (d) {             // A lies in direction (d^1) from B
+            case 4: kB = 0; break;                          // A is B's Z- neighbour
+            case 2: kB = qual[5]; break;                    // A is B's Y- neighbour
+            case 0: kB = qual[5] + qual[3]; break;          // A is B's X- neighbour
+            case 1: kB = early + all; break;                // A is B's X+ neighbour
+            case 3: kB = early + all + qual[0]; break;      // A is B's Y+ neighbour
+            default: kB = early + all + qual[0] + qual[2]; break;   // A is B's Z+ neighbour
+        }
+        double Q[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) Q[i] = cv[(size_t)bslot * 9 + i];
+        int qperm, qsign;
+        for (int k = 0; k <= kB; k++) lu3(Q, qperm, qsign);
+        double div;
+        if (pseudo_kl(A, psign, Q, qperm, qsign, div)) { out_div[d] = div; out_flag[d] = 1; }
+        else out_flag[d] = 0;                                // -2: pair skipped, mutation kept (A11)
+    }
+    if (nA > 1) {
+        const int post = (nn[0] > 1) + (nn[2] > 1) + (nn[4] > 1);
+        int perm, sgn;
+        for (int k = 0; k < post; k++) lu3(A, perm, sgn);
+    }
+    double *cf = cov_final + ((size_t)b * vcap + v) * 9;
+#pragma unroll
+    for (int i = 0; i < 9; i++) cf[i] = A[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9  divergence list: compaction in insertion order, NaN rule (A14), stable descending sort
+// (kullback_leibler.c:181-195), prune walk (ndt.c:45-72) and ascending compaction (ndt.c:75-117).
+// One CTA per cloud, block 1024.  Sort keys live in shared memory when the padded list fits, else in
+// the global scratch.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long desc_key(double d) {
+    // larger divergence -> smaller key; -0.0 and +0.0 compare equal in the reference
+    if (d == 0.0) d = 0.0;
+    return ~enc_f64(d);
+}
+
+__device__ __forceinline__ unsigned block_scan_step(unsigned val, unsigned *s_warp, unsigned &total) {
+    // inclusive scan over a 1024-thread block; returns exclusive prefix of this thread, total of block
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned inc = val;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    __syncthreads();
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    unsigned woff = 0; total = 0;
+    for (int k = 0; k < 32; k++) { const unsigned x = s_warp[k]; if (k < wid) woff += x; total += x; }
+    return woff + inc - val;
+}
+
+__global__ void __launch_bounds__(1024) k_select(CloudState *__restrict__ states, unsigned vcap, long num_desired,
+                                                 const unsigned *__restrict__ vox_cell, const unsigned *__restrict__ vox_n,
+                                                 const double *__restrict__ mean, const double *__restrict__ cov_final,
+                                                 const uint16_t *__restrict__ cls, int has_labels,
+                                                 const double *__restrict__ kl_div, const unsigned char *__restrict__ kl_flag,
+                                                 unsigned long long *__restrict__ g_key, unsigned *__restrict__ g_seq,
+                                                 size_t kcap, int smem_cap, unsigned *__restrict__ g_firstpos,
+                                                 unsigned char *__restrict__ g_removed, unsigned flags,
+                                                 float *__restrict__ out_feat, double *__restrict__ out_feat64,
+                                                 uint16_t *__restrict__ out_labels, int *__restrict__ out_voxel,
+                                                 double *__restrict__ list_div, unsigned *__restrict__ list_seq,
+                                                 NdtCloudInfo *__restrict__ info) {
+    extern __shared__ unsigned long long s_dyn[];
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
+    __shared__ double s_wmin[32];
+    __shared__ double s_cmin;
+    const int b = blockIdx.x;
+    CloudState &s = states[b];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long D = num_desired;
+    float *of = out_feat ? out_feat + (size_t)b * D * 12 : nullptr;
+    double *of64 = out_feat64 ? out_feat64 + (size_t)b * D * 12 : nullptr;
+    uint16_t *ol = out_labels ? out_labels + (size_t)b * D : nullptr;
+    int *ov = out_voxel ? out_voxel + (size_t)b * D : nullptr;
+
+    if (s.status != 0) {
+        for (long i = tid; i < D * 12; i += blockDim.x) { if (of) of[i] = 0.f; if (of64) of64[i] = 0.0; }
+        for (long i = tid; i < D; i += blockDim.x) { if (ol) ol[i] = 0; if (ov) ov[i] = -1; }
+        if (tid == 0 && info) {
+            NdtCloudInfo &o = info[b];
+            o.status = s.status; o.prune_status = 0; o.evaluations = s.evals;
+            for (int a = 0; a < 3; a++) { o.len[a] = (unsigned)s.len[a]; o.offset[a] = s.off[a]; }
+            o.num_voxels = 0; o.num_valid = 0; o.num_kl = 0; o.num_kl_after = 0; o.num_out = 0; o.num_survivors = 0;
+            o.voxel_size = s.guess;
+            for (int a = 0; a < 6; a++) o.limits[a] = s.lim[a];
+        }
+        return;
+    }
+    const unsigned V = s.V;
+    const unsigned nslots = V * kDirs;
+    const double *kd = kl_div + (size_t)b * vcap * kDirs;
+    const unsigned char *kf = kl_flag + (size_t)b * vcap * kDirs;
+    unsigned long long *gk = g_key + (size_t)b * kcap;
+    unsigned *gs = g_seq + (size_t)b * kcap;
+
+    // ---- 1. compaction in insertion order + NaN rule: a NaN takes the exclusive prefix-minimum of
+    //         the finite (non-NaN) divergences inserted before it, +inf if none.
+    if (tid == 0) { s_carry = 0; s_cmin = __longlong_as_double(0x7FF0000000000000ll); }
+    __syncthreads();
+    for (unsigned base = 0; base < nslots; base += blockDim.x) {
+        const unsigned q = base + tid;
+        const bool present = q < nslots && kf[q];
+        const double d = present ? kd[q] : 0.0;
+        const bool isn = present && isnan(d);
+        // exclusive prefix min of non-NaN present values
+        double mval = (present && !isn) ? d : __longlong_as_double(0x7FF0000000000000ll);
+        double inc = mval;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = u < inc ? u : inc; }
+        double excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) excl = __longlong_as_double(0x7FF0000000000000ll);
+        unsigned total;
+        const unsigned pos_in = block_scan_step(present ? 1u : 0u, s_warp, total);   // contains __syncthreads
+        if (lane == 31) s_wmin[wid] = inc;
+        __syncthreads();
+        double wpre = s_cmin;
+        double blockmin = s_cmin;
+        for (int k = 0; k < 32; k++) { const double x = s_wmin[k]; if (k < wid) wpre = x < wpre ? x : wpre; blockmin = x < blockmin ? x : blockmin; }
+        excl = wpre < excl ? wpre : excl;
+        if (present) {
+            const unsigned pos = s_carry + pos_in;
+            if (pos < kcap) {
+                gk[pos] = desc_key(isn ? excl : d);
+                gs[pos] = q;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { s_carry += total; s_cmin = blockmin; }
+        __syncthreads();
+    }
+    const unsigned K = s_carry;
+    // ---- 2. stable sort (key ascending == divergence descending, then insertion sequence ascending)
+    unsigned P = 1; while (P < K) P <<= 1;
+    const bool in_smem = (int)P <= smem_cap;
+    unsigned long long *key = in_smem ? s_dyn : gk;
+    unsigned *seq = in_smem ? (unsigned *)(s_dyn + P) : gs;
+    if (in_smem) { for (unsigned i = tid; i < K; i += blockDim.x) { key[i] = gk[i]; seq[i] = gs[i]; } }
+    for (unsigned i = K + tid; i < P; i += blockDim.x) { key[i] = ~0ull; seq[i] = 0xFFFFFFFFu; }
+    __syncthreads();
+    for (unsigned k = 2; k <= P; k <<= 1) {
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = tid; i < P; i += blockDim.x) {
+                const unsigned l = i ^ j;
+                if (l > i) {
+                    const unsigned long long ka = key[i], kb = key[l];
+                    const unsigned sa = seq[i], sb = seq[l];
+                    const bool a_gt_b = ka > kb || (ka == kb && sa > sb);
+                    const bool up = (i & k) == 0;
+                    if (a_gt_b == up) { key[i] = kb; key[l] = ka; seq[i] = sb; seq[l] = sa; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // keep the sorted list (for the legacy handles / inspection)
+    if (list_div) {
+        double *ld = list_div + (size_t)b * kcap; unsigned *ls = list_seq + (size_t)b * kcap;
+        for (unsigned i = tid; i < K; i += blockDim.x) { const unsigned q = seq[i]; ld[i] = kd[q]; ls[i] = q; }
+    }
+    // ---- 3. prune walk: first occurrence of each p in list order, the first to_remove of them go,
+    //         subject to the shrinking-length stop (ndt.c:53)
+    unsigned *firstpos = g_firstpos + (size_t)b * vcap;
+    unsigned char *removed = g_removed + (size_t)b * vcap;
+    for (unsigned v = tid; v < V; v += blockDim.x) { firstpos[v] = 0xFFFFFFFFu; removed[v] = 0; }
+    __syncthreads();
+    for (unsigned i = tid; i < K; i += blockDim.x) atomicMin(&firstpos[seq[i] / kDirs], i);
+    __syncthreads();
+    const unsigned to_remove = (unsigned)((unsigned long)V - (unsigned long)D);   // V >= D on acceptance
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    unsigned walk_local = 0;       // max over threads of (pos+1) for removed entries
+    for (unsigned base = 0; base < K; base += blockDim.x) {
+        const unsigned i = base + tid;
+        const bool first = i < K && firstpos[seq[i] / kDirs] == i;
+        unsigned total;
+        const unsigned r = s_carry + block_scan_step(first ? 1u : 0u, s_warp, total);
+        if (first && r < to_remove && (unsigned long)i + r < (unsigned long)K) {
+            removed[seq[i] / kDirs] = 1;
+            walk_local = i + 1;
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += total;
+        __syncthreads();
+        if (s_carry >= to_remove) break;
+    }
+    // number removed and walk end
+    {
+        unsigned cnt = 0;
+        for (unsigned v = tid; v < V; v += blockDim.x) cnt += removed[v];
+        unsigned total;
+        __syncthreads();
+        block_scan_step(cnt, s_warp, total);
+        // reduce walk_local (max)
+        unsigned w = walk_local;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { unsigned u = __shfl_xor_sync(0xffffffffu, w, o); w = u > w ? u : w; }
+        __syncthreads();
+        if (lane == 0) s_warp[wid] = w;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned wm = 0;
+            for (int k = 0; k < 32; k++) wm = s_warp[k] > wm ? s_warp[k] : wm;
+            const unsigned n_removed = total;
+            s.K = K;
+            s.n_valid = V - n_removed;
+            if (n_removed < to_remove) { s.prune_ret = -2; s.walk = K - n_removed; }   // walk stopped at idx == K - removed
+            else { s.prune_ret = 0; s.walk = wm; }
+        }
+        __syncthreads();
+    }
+    // ---- 4. ascending compaction of the survivors (ndt.c:75-117), clamped to D rows (A15)
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    const double *mu = mean + (size_t)b * vcap * 3;
+    const double *cf = cov_final + (size_t)b * vcap * 9;
+    for (unsigned base = 0; base < V; base += blockDim.x) {
+        const unsigned v = base + tid;
+        const bool alive = v < V && !removed[v];
+        unsigned total;
+        const unsigned row = s_carry + block_scan_step(alive ? 1u : 0u, s_warp, total);
+        if (alive && (long)row < D) {
+            double f[12];
+            f[0] = mu[v * 3 + 0]; f[1] = mu[v * 3 + 1]; f[2] = mu[v * 3 + 2];
+#pragma unroll
+            for (int k = 0; k < 9; k++) f[3 + k] = cf[(size_t)v * 9 + k];
+            if (of64) {
+#pragma unroll
+                for (int k = 0; k < 12; k++) of64[(size_t)row * 12 + k] = f[k];
+            }
+            if (of) {
+#pragma unroll
+                for (int k = 0; k < 12; k++) {
+                    float x = (float)f[k];
+                    if ((flags & 1u) && !isfinite(x)) x = 0.f;
+                    of[(size_t)row * 12 + k] = x;
+                }
+            }
+            if (ol) ol[row] = has_labels ? cls[(size_t)b * vcap + v] : (uint16_t)0;
+            if (ov) ov[row] = (int)vox_cell[(size_t)b * vcap + v];
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += total;
+        __syncthreads();
+    }
+    const unsigned survivors = s_carry;
+    const unsigned rows = (long)survivors < D ? survivors : (unsigned)D;
+    for (long i = (long)rows * 12 + tid; i < D * 12; i += blockDim.x) { if (of) of[i] = 0.f; if (of64) of64[i] = 0.0; }
+    for (long i = (long)rows + tid; i < D; i += blockDim.x) { if (ol) ol[i] = 0; if (ov) ov[i] = -1; }
+    if (tid == 0) {
+        s.n_out = rows; s.n_survivors = survivors;
+        if (info) {
+            NdtCloudInfo &o = info[b];
+            o.status = 0; o.prune_status = s.prune_ret; o.evaluations = s.evals;
+            for (int a = 0; a < 3; a++) { o.len[a] = (unsigned)s.len[a]; o.offset[a] = s.off[a]; }
+            o.num_voxels = V; o.num_valid = s.n_valid; o.num_kl = K;
+            o.num_kl_after = K - (V - s.n_valid);   // what prune_nds leaves in *num_kl_divergences (ndt.c:65)
+            o.num_out = rows; o.num_survivors = survivors;
+            o.voxel_size = s.guess;
+            for (int a = 0; a < 6; a++) o.limits[a] = s.lim[a];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void k_init_limits(unsigned long long *lim_enc, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * 6) lim_enc[i] = (i % 6) < 3 ? 0ull : ~0ull;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+template <typename T>
+static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels, int B, long N, int num_classes,
+                             long D, unsigned flags, float *out_feat, double *out_feat64, uint16_t *out_labels,
+                             int *out_voxel, NdtCloudInfo *info, cudaStream_t st) {
+    const unsigned vcap = w.vcap;
+    const int ntiles = (int)((N + kRankTile - 1) / kRankTile);
+    const int nbins = num_classes + 1;
+    k_init_limits<<<(B * 6 + 127) / 128, 128, 0, st>>>(w.lim_enc, B);
+    {
+        int chunks = (int)((N + 256 * 16 - 1) / (256 * 16));
+        if (chunks < 1) chunks = 1;
+        k_limits<T><<<dim3(chunks, B), 256, 0, st>>>(pts, N, w.lim_enc);
+    }
+    k_decide<<<B, 256, 0, st>>>(w.states, w.lim_enc, w.bitmap, w.bitmap_stride, w.vox_cell, vcap, D, 0);
+    {
+        int chunks = (int)((N + kCountPointsPerCta - 1) / kCountPointsPerCta);
+        if (chunks < 1) chunks = 1;
+        for (int it = 0; it < kMaxGuessIterations; it++) {
+            k_count<T><<<dim3(chunks, B), 256, 0, st>>>(pts, N, w.states, w.bitmap, w.bitmap_stride);
+            k_decide<<<B, 256, 0, st>>>(w.states, w.lim_enc, w.bitmap, w.bitmap_stride, w.vox_cell, vcap, D, 1);
+        }
+    }
+    if (N > 0) {
+        const size_t rank_smem = 4 * (size_t)vcap * sizeof(unsigned short);
+        if (rank_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_rank<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
+        k_rank<T><<<dim3((ntiles + 3) / 4, B), 128, rank_smem, st>>>(
+            pts, N, w.states, w.bitmap, w.bitmap_stride, vcap, ntiles, w.slot_rank, w.tile_cnt, w.point_voxel);
+    }
+    k_offsets<<<B, 1024, 0, st>>>(w.states, vcap, ntiles, w.tile_cnt, w.vox_n, w.vox_start);
+    if (labels) CK(cudaMemsetAsync(w.hist, 0, (size_t)B * vcap * nbins * sizeof(unsigned), st));
+    if (N > 0) {
+        k_scatter<T><<<dim3((unsigned)((N + 255) / 256), B), 256, 0, st>>>(
+            pts, labels, N, w.states, vcap, ntiles, w.slot_rank, w.tile_cnt, w.vox_start, (T *)w.sorted,
+            labels ? w.hist : nullptr, nbins);
+    }
+    k_stats<T><<<dim3((vcap + 127) / 128, B), 128, 0, st>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start,
+                                                           labels ? w.hist : nullptr, nbins, w.mean, w.cov, w.cls);
+    k_kl<<<dim3((vcap + 63) / 64, B), 64, 0, st>>>(w.states, vcap, w.bitmap, w.bitmap_stride, w.vox_cell, w.vox_n, w.cov,
+                                                  w.cov_final, w.kl_div, w.kl_flag);
+    {
+        const size_t kcap = (size_t)vcap * kDirs;
+        size_t P = 1; while (P < kcap) P <<= 1;
+        int smem_cap = (int)P;
+        size_t bytes = P * 12;
+        const size_t max_dyn = 200 * 1024;
+        while (bytes > max_dyn) { smem_cap >>= 1; bytes = (size_t)smem_cap * 12; }
+        static bool attr_set = false;
+        if (!attr_set) { CK(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn)); attr_set = true; }
+        k_select<<<B, 1024, bytes, st>>>(w.states, vcap, D, w.vox_cell, w.vox_n, w.mean, w.cov_final, w.cls, labels ? 1 : 0,
+                                         w.kl_div, w.kl_flag, w.key, w.seq, kcap, smem_cap, w.firstpos, w.removed, flags,
+                                         out_feat, out_feat64, out_labels, out_voxel, w.list_div, w.list_seq, info);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t run_batch(Workspace &w, const void *pts, int dtype, const uint16_t *labels, int B, long N, int num_classes,
+                      long D, unsigned flags, float *out_feat, double *out_feat64, uint16_t *out_labels, int *out_voxel,
+                      NdtCloudInfo *info, cudaStream_t st) {
+    if (dtype == 0)
+        return run_typed<float>(w, (const float *)pts, labels, B, N, num_classes, D, flags, out_feat, out_feat64,
+                                out_labels, out_voxel, info, st);
+    return run_typed<double>(w, (const double *)pts, labels, B, N, num_classes, D, flags, out_feat, out_feat64, out_labels,
+                             out_voxel, info, st);
+}
+
+}  // namespace ndt

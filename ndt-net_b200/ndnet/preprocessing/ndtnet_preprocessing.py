@@ -1,0 +1,47 @@
+"""Drop-in for the reference's ndnet/preprocessing/ndtnet_preprocessing.py:6-73: same function name,
+arguments and return values, but the per-cloud Python loop (GPU->CPU->C->CPU->GPU per cloud) is one
+batched call into libndnet_b200.so on the current CUDA stream."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+from ndnet_b200.engine import default_engine
+
+
+def ndt_preprocessing(num_nds: int, points: torch.Tensor, classes: torch.Tensor = None, num_classes: int = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """points: (batch, num_points, 3) float tensor; classes: (batch, num_points, num_classes+1) one-hot or None.
+
+    Returns (points_new [B,num_nds,3], covs_new [B,num_nds,9], classes_new [B,num_nds,num_classes+1] or None),
+    float32 on points.device, NaN/inf replaced by 0 (ndtnet_preprocessing.py:66-69)."""
+    if points.dim() != 3 or points.shape[2] != 3:
+        raise ValueError("points must be shaped (batch, num_points, 3)")
+    out_device = points.device
+    if points.is_cuda:
+        dev = points.device
+    else:
+        if not torch.cuda.is_available():
+            raise RuntimeError("ndt_preprocessing needs a CUDA device: ndnet_b200 has no CPU path")
+        dev = torch.device("cuda", torch.cuda.current_device())
+    pts = points.to(device=dev)
+    if pts.dtype not in (torch.float32, torch.float64):
+        pts = pts.float()            # the reference widens whatever it gets to float64 (:30)
+    labels = None
+    ncls = 0
+    if classes is not None:
+        ncls = int(num_classes)
+        # one-hot -> tag (:34); torch.argmax returns the first maximal index like numpy
+        labels = torch.argmax(classes.to(dev), dim=2).to(torch.int16)
+    eng = default_engine(dev)
+    out = eng.downsample(pts, int(num_nds), labels, ncls, nan_to_num=True, want_info=False)
+    points_new = out.feat[:, :, 0:3].contiguous()
+    covs_new = out.feat[:, :, 3:12].contiguous()
+    classes_new = None
+    if classes is not None:
+        idx = out.labels.to(torch.int64) & 0xFFFF
+        classes_new = torch.zeros((pts.shape[0], int(num_nds), ncls + 1), dtype=torch.float32, device=dev)
+        classes_new.scatter_(2, idx.unsqueeze(-1), 1.0)   # (:55-57)
+        classes_new = classes_new.to(out_device)
+    return points_new.to(out_device), covs_new.to(out_device), classes_new

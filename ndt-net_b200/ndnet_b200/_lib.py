@@ -1,0 +1,72 @@
+"""Loader for libndnet_b200.so (the C ABI declared in include/ndnet_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or cannot be loaded the import of any
+product module fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("NDNET_B200_LIB", os.path.join(os.path.dirname(HERE), "lib", "libndnet_b200.so"))
+
+INFO_DTYPE = np.dtype([
+    ("status", "<i4"), ("prune_status", "<i4"), ("evaluations", "<i4"), ("len", "<u4", 3),
+    ("num_voxels", "<u4"), ("num_valid", "<u4"), ("num_kl", "<u4"), ("num_kl_after", "<u4"),
+    ("num_out", "<u4"), ("num_survivors", "<u4"),
+    ("voxel_size", "<f8"), ("offset", "<f8", 3), ("limits", "<f8", 6),
+])
+assert INFO_DTYPE.itemsize == 128
+
+F32, F64 = 0, 1
+NAN_TO_NUM = 1
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python __graft_entry__.py` (or make -C ndt-net_b200/csrc). "
+            "ndnet_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i, l, u = C.c_void_p, C.c_int, C.c_long, C.c_uint
+    L.ndnet_b200_version.restype = C.c_char_p
+    L.ndnet_b200_create.restype = i
+    L.ndnet_b200_create.argtypes = [C.POINTER(vp), i]
+    L.ndnet_b200_destroy.restype = None
+    L.ndnet_b200_destroy.argtypes = [vp]
+    L.ndnet_b200_last_error.restype = C.c_char_p
+    L.ndnet_b200_last_error.argtypes = [vp]
+    batch_args = [vp, vp, i, vp, i, l, i, l, u, vp, vp, vp, vp, vp, vp]
+    L.ndnet_b200_downsample_batch.restype = i
+    L.ndnet_b200_downsample_batch.argtypes = batch_args
+    L.ndnet_b200_downsample_batch_host.restype = i
+    L.ndnet_b200_downsample_batch_host.argtypes = batch_args
+    L.ndnet_b200_last_point_voxels.restype = i
+    L.ndnet_b200_last_point_voxels.argtypes = [vp, vp, vp]
+    L.ndnet_b200_last_kl_list.restype = l
+    L.ndnet_b200_last_kl_list.argtypes = [vp, i, vp, vp, vp, l]
+    L.ndnet_b200_model_create.restype = i
+    L.ndnet_b200_model_create.argtypes = [vp, C.POINTER(vp), i, i, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(vp),
+                                          C.POINTER(i)]
+    L.ndnet_b200_model_destroy.restype = None
+    L.ndnet_b200_model_destroy.argtypes = [vp]
+    L.ndnet_b200_model_forward.restype = i
+    L.ndnet_b200_model_forward.argtypes = [vp, vp, vp, i, i, vp, vp]
+    _lib = L
+    return L
+
+
+EXPORTED = [
+    "ndt_downsample", "prune_nds", "to_point_cloud", "free_nds", "free_kl_divergences", "print_matrix",
+    "ndnet_b200_create", "ndnet_b200_destroy", "ndnet_b200_last_error", "ndnet_b200_version",
+    "ndnet_b200_downsample_batch", "ndnet_b200_downsample_batch_host", "ndnet_b200_last_point_voxels",
+    "ndnet_b200_last_kl_list", "ndnet_b200_model_create", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
+]
