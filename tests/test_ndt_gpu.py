@@ -1,0 +1,221 @@
+"""GPU parity tests of the NDT hot path: the CUDA library, called through its C ABI (device-pointer batched
+entry, host-pointer batched entry and the legacy ndt_downsample symbols), against the CPU oracle and
+against the golden vectors the reference's own C sources produced.
+
+Bar (BASELINE.json north_star): voxel ids, per-voxel membership, the retained-distribution set, labels,
+means and the exported (LU-mangled) covariances are BIT-EXACT (any NaN == any NaN).  The pseudo-KL values
+may differ from the CPU in the last bits because CUDA's log() and glibc's log() round differently:
+tolerance |d_gpu - d_cpu| <= KL_TOL_ULPS ulps of max(|trace|-scale terms), checked below; the selection must
+still be identical unless two list entries at the cut are closer than that tolerance.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ndt_oracle
+from tests import cases
+from tests.helpers import same_bits
+
+pytestmark = pytest.mark.gpu
+
+KL_REL_TOL = 1e-13     # relative, on entries whose CPU and GPU values are finite and non-zero
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ndt_ref_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from ndnet_b200.engine import NdtEngine
+    return NdtEngine(0)
+
+
+def _run_gpu(engine, pts, labels, ncls, d):
+    t = torch.from_numpy(np.ascontiguousarray(pts)).cuda()[None]
+    lab = None if labels is None else torch.from_numpy(labels.astype(np.int16)).cuda()[None]
+    out = engine.downsample(t, d, lab, ncls, nan_to_num=False, want_f64=True, want_voxel=True)
+    torch.cuda.synchronize()
+    return out
+
+
+def _check_against_oracle(engine, name, pts, labels, ncls, d):
+    out = _run_gpu(engine, pts, labels, ncls, d)
+    o = ndt_oracle.run(pts, d, labels, ncls)
+    info = out.info[0]
+    assert info["status"] == o.ret, name
+    assert tuple(int(x) for x in info["len"]) == o.lens, name
+    assert info["voxel_size"] == o.voxel_size, name
+    assert info["evaluations"] == o.evaluations, name
+    assert np.array_equal(info["limits"], o.limits), name
+    n = pts.shape[0]
+    pv = engine.last_point_voxels(1, n).cpu().numpy()[0]
+    if o.ret != 0:
+        assert np.all(out.feat64.cpu().numpy() == 0) and info["num_out"] == 0, name
+        return
+    # voxel ids and membership: bit-exact
+    assert np.array_equal(pv, o.point_voxel), name
+    assert info["num_voxels"] == o.num_valid0 and info["num_valid"] == o.num_valid, name
+    assert info["prune_status"] == o.prune_ret, name
+    # divergence list: same (p, q) multiset in the same order unless values within tolerance swapped
+    div, p, q = engine.last_kl_list(0, int(info["num_kl"]) + 8)
+    assert len(div) == o.num_kl0, name
+    gpu_map = {(int(a), int(b)): v for a, b, v in zip(p, q, div)}
+    assert len(gpu_map) == len(div), name
+    for a, b, v in zip(o.kl_p0, o.kl_q0, o.kl_div0):
+        w = gpu_map[(int(a), int(b))]
+        if np.isnan(v) or np.isnan(w):
+            assert np.isnan(v) and np.isnan(w), name
+        elif v != w:
+            assert np.isfinite(v) and np.isfinite(w) and abs(v - w) <= KL_REL_TOL * max(abs(v), 1.0), (name, v, w)
+    # retained-distribution set, rows in ascending voxel index
+    rows = min(o.num_out, d)
+    assert info["num_out"] == rows and info["num_survivors"] == o.num_out, name
+    vox = out.voxel[0].cpu().numpy()
+    if not np.array_equal(vox[:rows], o.out_voxel[:rows]):
+        # only acceptable when the divergences at the cut are tied within tolerance
+        cpu_removed = set(np.flatnonzero((o.num_samples0 > 0) & (o.num_samples == 0)).tolist())
+        gpu_removed = set(np.flatnonzero(o.num_samples0 > 0).tolist()) - set(vox[:rows].tolist())
+        diff = cpu_removed ^ gpu_removed
+        best = {}
+        for a, v in zip(o.kl_p0, o.kl_div0):
+            best.setdefault(int(a), v)
+        vals = [best[x] for x in diff if x in best]
+        assert vals and (max(vals) - min(vals)) <= KL_REL_TOL * max(abs(max(vals)), 1.0), (name, sorted(diff))
+        return
+    assert np.all(vox[rows:] == -1), name
+    f = out.feat64[0].cpu().numpy()
+    assert same_bits(f[:rows, :3], o.out_pts[:rows]), name
+    assert same_bits(f[:rows, 3:], o.out_cov[:rows]), name
+    assert np.all(f[rows:] == 0), name
+    if labels is not None:
+        assert np.array_equal(out.labels[0].cpu().numpy().astype(np.uint16)[:rows], o.out_cls[:rows]), name
+
+
+@pytest.mark.parametrize("case", cases.small_cases(), ids=lambda c: c[0])
+def test_small_cases_match_oracle(engine, case):
+    _check_against_oracle(engine, *case)
+
+
+@pytest.mark.parametrize("case", cases.medium_cases(), ids=lambda c: c[0])
+def test_baseline_sized_clouds_match_oracle(engine, case):
+    _check_against_oracle(engine, *case)
+
+
+def test_golden_vectors_through_c_abi(engine):
+    """The reference's own outputs (tests/golden, made from core_legacy/src by make_golden.py)."""
+    g = np.load(GOLDEN)
+    by_name = {c[0]: c for c in cases.small_cases() + cases.medium_cases()[:3]}
+    for name in [str(n) for n in g["names"]]:
+        _, pts, labels, ncls, d = by_name[name]
+        out = _run_gpu(engine, pts, labels, ncls, d)
+        info = out.info[0]
+        hdr = g[name + "/hdr"]
+        assert info["status"] == hdr[0], name
+        assert tuple(int(x) for x in info["len"]) == tuple(int(x) for x in hdr[1:4]), name
+        assert info["voxel_size"] == g[name + "/vs"][0], name
+        if hdr[0] != 0:
+            continue
+        rows = min(int(hdr[4]), d)
+        f = out.feat64[0].cpu().numpy()
+        assert same_bits(f[:rows, :3], g[name + "/pts"][:rows]), name
+        assert same_bits(f[:rows, 3:], g[name + "/cov"][:rows]), name
+        if labels is not None:
+            assert np.array_equal(out.labels[0].cpu().numpy().astype(np.uint16)[:rows], g[name + "/cls"][:rows]), name
+        assert info["num_valid"] == hdr[5] and info["num_kl_after"] == hdr[6], name
+
+
+def test_batch_of_mixed_clouds_equals_single_cloud_runs(engine):
+    """Clouds in a batch are independent: a batch gives exactly what B single-cloud calls give, including
+    a cloud that fails (-3) in the middle of the batch."""
+    from ndnet_b200.synth import lidar_cloud
+    n, d = 20000, 500
+    pts = np.stack([lidar_cloud(n, 40 + b) for b in range(5)])
+    pts[2, :, 2] = 1.0      # degenerate axis -> -3
+    out = engine.downsample(torch.from_numpy(pts).cuda(), d, nan_to_num=False, want_f64=True, want_voxel=True)
+    for b in range(5):
+        single = engine.downsample(torch.from_numpy(pts[b:b + 1]).cuda(), d, nan_to_num=False, want_f64=True, want_voxel=True)
+        assert out.info[b]["status"] == single.info[0]["status"] == (-3 if b == 2 else 0)
+        assert same_bits(out.feat64[b].cpu().numpy(), single.feat64[0].cpu().numpy())
+        assert torch.equal(out.voxel[b], single.voxel[0])
+
+
+def test_f32_features_and_nan_to_num(engine):
+    """ndtnet_preprocessing.py:60-69: float32 cast then NaN/inf -> 0."""
+    name, pts, labels, ncls, d = cases.small_cases()[0]
+    t = torch.from_numpy(pts).cuda()[None]
+    raw = engine.downsample(t, d, nan_to_num=False, want_f64=True)
+    clean = engine.downsample(t, d, nan_to_num=True)
+    ref = torch.nan_to_num(raw.feat64.to(torch.float32), nan=0.0, posinf=0.0, neginf=0.0)
+    assert torch.equal(clean.feat, ref)
+    assert torch.isfinite(clean.feat).all()
+
+
+def test_full_size_batch_properties(engine):
+    """BASELINE.json config 4 shape (120k-point scans, D=1000), size-independent properties: every cloud
+    converges, D rows each, rows sorted by voxel index, idempotent across repeated calls, one cloud of the
+    batch equals the oracle."""
+    from ndnet_b200.synth import lidar_batch
+    B, n, d = 16, 120000, 1000
+    pts = lidar_batch(B, n, seed0=200)
+    t = torch.from_numpy(pts).cuda()
+    a = engine.downsample(t, d, nan_to_num=False, want_f64=True, want_voxel=True)
+    b = engine.downsample(t, d, nan_to_num=False, want_f64=True, want_voxel=True)
+    assert same_bits(a.feat64.cpu().numpy(), b.feat64.cpu().numpy()) and torch.equal(a.voxel, b.voxel)
+    assert np.all(a.info["status"] == 0) and np.all(a.info["num_out"] == d) and np.all(a.info["num_valid"] == d)
+    vox = a.voxel.cpu().numpy()
+    assert np.all(np.diff(vox, axis=1) > 0)
+    o = ndt_oracle.run(pts[5], d)
+    assert np.array_equal(vox[5], o.out_voxel) and same_bits(a.feat64[5, :, :3].cpu().numpy(), o.out_pts)
+    assert same_bits(a.feat64[5, :, 3:].cpu().numpy(), o.out_cov)
+
+
+def test_host_entry_matches_device_entry(engine):
+    from ndnet_b200.synth import lidar_batch
+    pts, lab = lidar_batch(3, 30000, seed0=300, with_labels=True)
+    feat_h, lab_h, info_h = engine.downsample_host(pts, 700, lab, 28)
+    dev = engine.downsample(torch.from_numpy(pts).cuda(), 700, torch.from_numpy(lab.astype(np.int16)).cuda(), 28)
+    assert torch.equal(feat_h, dev.feat.cpu())
+    assert np.array_equal(lab_h, dev.labels.cpu().numpy().astype(np.uint16))
+    assert np.array_equal(info_h["num_valid"], dev.info["num_valid"])
+
+
+def test_ndt_preprocessing_drop_in(engine):
+    """Same call as ndnet/preprocessing/ndtnet_preprocessing.py:6 (one-hot classes in, one-hot classes out)."""
+    from ndnet.preprocessing.ndtnet_preprocessing import ndt_preprocessing
+    from ndnet_b200.synth import lidar_batch
+    B, n, d, C = 2, 16000, 500, 28
+    pts, lab = lidar_batch(B, n, seed0=400, with_labels=True)
+    onehot = torch.zeros((B, n, C + 1)); onehot.scatter_(2, torch.from_numpy(lab.astype(np.int64))[..., None], 1.0)
+    p, c, k = ndt_preprocessing(d, torch.from_numpy(pts).cuda(), onehot.cuda(), C)
+    assert p.shape == (B, d, 3) and c.shape == (B, d, 9) and k.shape == (B, d, C + 1)
+    assert p.dtype == c.dtype == k.dtype == torch.float32 and p.is_cuda
+    for b in range(B):
+        o = ndt_oracle.run(pts[b], d, lab[b], C)
+        assert torch.equal(p[b].cpu(), torch.from_numpy(o.out_pts).float())
+        ref_c = torch.nan_to_num(torch.from_numpy(o.out_cov).float(), nan=0.0, posinf=0.0, neginf=0.0)
+        assert torch.equal(c[b].cpu(), ref_c)
+        assert torch.equal(k[b].argmax(1).cpu(), torch.from_numpy(o.out_cls.astype(np.int64)))
+        assert torch.all(k[b].sum(1) == 1)
+
+
+def test_legacy_sampler_drop_in():
+    """NDT_Sampler (ndt_legacy.py:45-240) bound to the legacy symbols of libndnet_b200.so."""
+    from ndnet.preprocessing.ndt_legacy import NDT_Sampler
+    name, pts, labels, ncls, d = cases.small_cases()[1]
+    s = NDT_Sampler(pts.astype(np.float64), labels, ncls)
+    p, c, k = s.downsample(d)
+    o = ndt_oracle.run(pts, d, labels, ncls)
+    assert s.status == 0 and same_bits(p, o.out_pts) and same_bits(c, o.out_cov) and np.array_equal(k, o.out_cls)
+    assert (s.len_x.value, s.len_y.value, s.len_z.value) == o.lens and s.voxel_size.value == o.voxel_size
+    assert s.num_valid_nds.value == o.num_valid and s.num_kl_divergences.value == o.num_kl
+    # continuation on the retained handles: same as asking for the smaller number on the same list
+    p2, c2, k2 = s.prune(d - 100)
+    assert p2.shape == (d - 100, 3) and s.num_valid_nds.value == d - 100
+    kept = {tuple(r) for r in p.tolist()}
+    assert all(tuple(r) in kept for r in p2.tolist())
+    s.cleanup()
+    # failure path never crashes (A16)
+    bad = NDT_Sampler(cases.small_cases()[11][1].astype(np.float64))
+    bad.downsample(64)
+    assert bad.status == -3
+    bad.cleanup()
