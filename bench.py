@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — clouds/sec of the ND-Net hot path (NDT voxelise + voxel-size search + pseudo-KL prune + NDT-Net
+segmentation forward) on synthetic 120k-point LiDAR-like scans, BASELINE.json config 4.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path on this box's host cores
+
+One "step" = one pass of the hot path over one batch of `--batch` scans per GPU.
+`value`  : clouds/s with the scans already resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same through the C ABI's host-buffer call (ndnet_b200_infer_host): pinned host scans -> H2D ->
+           kernels -> D2H of the per-distribution log-probabilities, every step.
+`roofline`: the dominant kernel, algorithmic bytes per launch / its CUDA-event duration, against the measured
+           HBM copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline`: the reference's own C core (oracle/_ref, compiled from /root/reference/core_legacy/src with the
+           GSL shim) + the fp32 torch network on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "ndt-net_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_POINTS, N_NDS, N_CLASSES, FEATURE_DIM = 120_000, 1000, 28, 1024
+WORKLOAD = "config4: segmentation head (seg_viz path), 120k-point synthetic LiDAR scans, n_desired_nds=1000, 29 classes, F=1024"
+STAGES = ["limits", "search", "rank", "offsets", "scatter", "stats", "kl", "select"]
+ALGO_BYTES_PER_CLOUD = N_POINTS * 12 + N_POINTS * 2 + N_NDS * 48 + N_NDS * 2     # SURVEY.md §8(d), with labels
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons of one GPU during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_scans(batch: int, seed0: int):
+    from ndnet_b200.synth import lidar_batch
+    pts, lab = lidar_batch(batch, N_POINTS, seed0=seed0, with_labels=True, num_classes=N_CLASSES)
+    return pts, lab
+
+
+def build_network(device):
+    from ndnet.models.ndtnet import NDTNetSegmentation
+    from ndnet_b200.model import deterministic_state_dict
+    net = NDTNetSegmentation(num_classes=N_CLASSES, feature_dim=FEATURE_DIM)
+    net.load_state_dict(deterministic_state_dict(net, 0))     # random-init weights of the named architecture
+    return net.to(device).eval()
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(n_clouds: int, seed0: int, threads: int):
+    """The reference path on the host: per-cloud ndt_downsample of the reference's own C core (8 pthreads inside,
+    oracle/_ref/libndnet_ref.so = unmodified core_legacy sources, -O0 as its CMake builds them) through the same
+    marshalling as ndnet/preprocessing/ndt_legacy.py, float32 + nan_to_num as ndtnet_preprocessing.py:60-69, then the
+    fp32 torch network on all host threads.  Returns (seconds, kind)."""
+    from oracle import ref_ctypes
+    torch.set_num_threads(threads)
+    if ref_ctypes.have_ref("threaded"):
+        lib, kind = ref_ctypes.load(ref_ctypes.ref_lib_path("threaded")), "reference"
+        run = lambda p, l: ref_ctypes.downsample(lib, p, N_NDS, l, N_CLASSES, out_rows=N_NDS + 256)   # noqa: E731
+        unpack = lambda r: (r.points[:N_NDS], r.covs[:N_NDS])                                         # noqa: E731
+    else:
+        from oracle import ndt_oracle
+        kind = "port"
+        run = lambda p, l: ndt_oracle.run(p, N_NDS, l, N_CLASSES)                                     # noqa: E731
+        unpack = lambda r: (r.out_pts[:N_NDS], r.out_cov[:N_NDS])                                     # noqa: E731
+    net = build_network("cpu")
+    pts, lab = make_scans(n_clouds, seed0)
+    t0 = time.perf_counter()
+    means = np.zeros((n_clouds, N_NDS, 3), np.float32)
+    covs = np.zeros((n_clouds, N_NDS, 9), np.float32)
+    for b in range(n_clouds):
+        r = run(pts[b].astype(np.float64), lab[b])
+        m, c = unpack(r)
+        means[b, : len(m)] = m
+        covs[b, : len(c)] = c
+    with torch.no_grad():
+        m = torch.nan_to_num(torch.from_numpy(means), nan=0.0, posinf=0.0, neginf=0.0)
+        c = torch.nan_to_num(torch.from_numpy(covs), nan=0.0, posinf=0.0, neginf=0.0)
+        out = net(m, c)
+    float(out.sum())
+    return time.perf_counter() - t0, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = args.ref_clouds
+    for _ in range(args.warmup):
+        cpu_reference(1, 9000, threads)
+    times = []
+    kind = "reference"
+    for s in range(args.steps):
+        dt, kind = cpu_reference(per_step, 10_000 + s * per_step, threads)
+        times.append(dt)
+    total = sum(times)
+    value = per_step * args.steps / total
+    line = {
+        "impl": "reference", "metric": "clouds/sec (NDT voxel+KL prune+PointNet fwd) @120k pts", "value": value, "unit": "clouds/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "clouds_per_step": per_step, "points": N_POINTS, "n_desired_nds": N_NDS},
+        "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": threads, "kind": kind,
+                         "sample": f"{per_step} scans per step x {args.steps} steps; NDT = reference C core (8 pthreads, -O0, GSL shim) "
+                                   f"serial over scans, network = torch fp32 on {threads} threads"},
+        "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from ndnet_b200 import _lib
+    from ndnet_b200.engine import NdtEngine
+    from ndnet_b200.model import B200Model, KIND_SEG
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    B = args.batch
+    n_sets = 3                                  # rotate inputs: 3 x B x 1.68 MB > 126 MB L2 for B >= 32
+    host_pts, host_lab, dev_pts, dev_lab = [], [], [], []
+    for s in range(n_sets):
+        p, l = make_scans(B, seed0=rank * 100_000 + s * B)
+        hp = torch.from_numpy(p).pin_memory()
+        hl = torch.from_numpy(l.astype(np.int16)).pin_memory()
+        host_pts.append(hp); host_lab.append(hl)
+        dev_pts.append(hp.to(dev)); dev_lab.append(hl.to(dev))
+    eng = NdtEngine(local)
+    net = build_network(dev)
+    model = B200Model(net, KIND_SEG, dev)
+    out_host = torch.empty((B, N_NDS, N_CLASSES + 1), dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device(i):
+        out = eng.downsample(dev_pts[i % n_sets], N_NDS, dev_lab[i % n_sets], N_CLASSES, nan_to_num=True, want_info=False)
+        return model(out.feat)
+
+    def step_host(i):
+        return model.infer_host(host_pts[i % n_sets], N_NDS, host_lab[i % n_sets], N_CLASSES, out_host)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def timed(step_fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(steps):
+            step_fn(i)
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # correctness guard of the measured configuration: every scan converged to N_NDS distributions
+    chk = eng.downsample(dev_pts[0], N_NDS, dev_lab[0], N_CLASSES)
+    assert np.all(chk.info["status"] == 0) and np.all(chk.info["num_out"] == N_NDS), "workload did not converge"
+
+    for i in range(args.warmup):
+        step_device(i); step_host(i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = L.ndnet_b200_launch_count()
+    ms = timed(step_device, args.steps)
+    launches = L.ndnet_b200_launch_count() - launches0
+    ms_e2e = timed(step_host, args.steps)
+    clocks = sampler.stop()
+
+    # per-stage CUDA-event times of the NDT kernels (same K steps, events on the launching stream) and of the network
+    L.ndnet_b200_stage_timing(eng.handle, 1)
+    barrier()
+    for i in range(args.steps):
+        eng.downsample(dev_pts[i % n_sets], N_NDS, dev_lab[i % n_sets], N_CLASSES, nan_to_num=True, want_info=False)
+    barrier()
+    st = (np.zeros(8, np.float64))
+    runs = np.zeros(1, np.int64)
+    L.ndnet_b200_stage_times(eng.handle, st.ctypes.data, 8, runs.ctypes.data)
+    L.ndnet_b200_stage_timing(eng.handle, 0)
+    stage_ms = {n: float(st[i]) / max(int(runs[0]), 1) for i, n in enumerate(STAGES)}
+    feat = eng.downsample(dev_pts[0], N_NDS, dev_lab[0], N_CLASSES, want_info=False).feat
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        model(feat)
+    e1.record(stream)
+    barrier()
+    stage_ms["network_forward"] = e0.elapsed_time(e1) / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    clouds = B * world * args.steps
+    value = clouds / (ms * 1e-3)
+    e2e_value = clouds / (ms_e2e * 1e-3)
+    peak, peak_src = peaks()
+    dom = max(STAGES, key=lambda n: stage_ms[n])
+    # the `search` stage is up to 15 k_count launches; each launch that does work reads every point once
+    launches_in_dom = {"search": 5}.get(dom, 1)
+    dom_ms = stage_ms[dom] / launches_in_dom
+    achieved = ALGO_BYTES_PER_CLOUD * B / (dom_ms * 1e-3) / 1e9
+    line = {
+        "metric": "clouds/sec (NDT voxel+KL prune+PointNet fwd) @120k pts", "value": value, "unit": "clouds/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 (NDT) + bf16/f32-accumulate (network)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "clouds_per_gpu_per_step": B, "points": N_POINTS, "n_desired_nds": N_NDS,
+                   "parallelism": f"scans sharded over {world} GPU(s), no forward collective",
+                   "l2": f"inputs rotate over {n_sets} resident batches ({n_sets * B * ALGO_BYTES_PER_CLOUD / 1e6:.0f} MB vs 126 MB L2)"},
+        "e2e": {"value": e2e_value, "unit": "clouds/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": B * N_POINTS * 14, "d2h_bytes_per_step": B * N_NDS * (N_CLASSES + 1) * 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": {"limits": "k_limits", "search": "k_count (x5 launches that do work, of 15)",
+                                                "rank": "k_rank", "offsets": "k_offsets", "scatter": "k_scatter", "stats": "k_stats",
+                                                "kl": "k_kl", "select": "k_select"}[dom],
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "stage_ms_per_step": stage_ms},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        n = args.cpu_clouds
+        dt, kind = cpu_reference(n, 500_000, os.cpu_count() or 1)
+        line["cpu_baseline"] = {"value": n / dt, "unit": "clouds/s", "cores": os.cpu_count() or 1, "kind": kind,
+                                "sample": f"{n} scans of the same workload; NDT = reference C core (8 pthreads, -O0, GSL shim) serial over "
+                                          f"scans, network = torch fp32 on all host threads"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="scans per GPU per step")
+    ap.add_argument("--cpu-clouds", type=int, default=48, help="scans in the cpu_baseline sample")
+    ap.add_argument("--ref-clouds", type=int, default=8, help="scans per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -131,6 +131,14 @@ int ndnet_b200_last_point_voxels(ndnet_b200_ctx *ctx, int32_t *out_dev, void *st
  * Host buffers of capacity `cap`; returns the number of entries or a negative error. */
 long ndnet_b200_last_kl_list(ndnet_b200_ctx *ctx, int b, double *div, int32_t *p_voxel, int32_t *q_voxel, long cap);
 
+/* Instrumentation for bench.py.  launch_count: kernels launched by this library since it was loaded.
+ * stage_timing(1) makes every ndnet_b200_downsample_batch record CUDA events between its stages on the
+ * launching stream (and synchronise at the end); stage_times returns the accumulated milliseconds for
+ * {limits, search, rank, offsets, scatter, stats, kl, select} and the number of batches measured. */
+long ndnet_b200_launch_count(void);
+int ndnet_b200_stage_timing(ndnet_b200_ctx *ctx, int enable);
+int ndnet_b200_stage_times(ndnet_b200_ctx *ctx, double *ms, int cap, long *runs);
+
 /* ---- PointNet / NDT-Net forward (ndnet/models/ndtnet.py:33-62,112-164,181-196,218-243) ------------ */
 
 typedef struct ndnet_b200_model ndnet_b200_model;
@@ -151,6 +159,14 @@ void ndnet_b200_model_destroy(ndnet_b200_model *model);
  * cls: out device [B, num_classes] f32 (softmax);  seg: out device [B, D, num_classes+1] f32 (log_softmax). */
 int ndnet_b200_model_forward(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const float *feat, int B, int D,
                              float *out, void *stream);
+
+/* The whole hot path in one call from HOST buffers (what bench.py times as `e2e`): H2D of points (+labels),
+ * NDT (NaN/inf -> 0 as ndtnet_preprocessing.py:66-69), network forward, D2H of the result
+ * (seg: [B, D, num_classes+1] log-probabilities; cls: [B, num_classes] probabilities), stream synchronise.
+ * out_elems_per_cloud = D*(num_classes+1) or num_classes of the MODEL. */
+int ndnet_b200_infer_host(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const void *points, int dtype,
+                          const uint16_t *labels, int B, long N, int num_classes, long num_desired, float *out_host,
+                          long out_elems_per_cloud, void *stream);
 
 #ifdef __cplusplus
 }

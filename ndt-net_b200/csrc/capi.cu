@@ -29,6 +29,7 @@ struct ndnet_b200_ctx {
     uint16_t *d_olab = nullptr; size_t d_olab_bytes = 0;
     int32_t *d_ovox = nullptr; size_t d_ovox_bytes = 0;
     NdtCloudInfo *d_info = nullptr; size_t d_info_bytes = 0;
+    float *d_logits = nullptr; size_t d_logits_bytes = 0;
     mlp::Scratch mlp_scratch;
 };
 
@@ -142,9 +143,26 @@ extern "C" void ndnet_b200_destroy(ndnet_b200_ctx *c) {
     cudaSetDevice(c->device);
     c->ws.release();
     c->mlp_scratch.release();
-    void *ptrs[] = {c->d_points, c->d_labels, c->d_feat, c->d_feat64, c->d_olab, c->d_ovox, c->d_info};
+    void *ptrs[] = {c->d_points, c->d_labels, c->d_feat, c->d_feat64, c->d_olab, c->d_ovox, c->d_info, c->d_logits};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete c;
+}
+
+extern "C" long ndnet_b200_launch_count(void) { return ndt::launches(); }
+
+extern "C" int ndnet_b200_stage_timing(ndnet_b200_ctx *c, int enable) {
+    if (!c) return -200;
+    c->ws.timer.enabled = enable != 0;
+    for (double &m : c->ws.timer.ms) m = 0;
+    c->ws.timer.runs = 0;
+    return 0;
+}
+
+extern "C" int ndnet_b200_stage_times(ndnet_b200_ctx *c, double *ms, int cap, long *runs) {
+    if (!c || !ms) return -200;
+    for (int i = 0; i < cap && i < (int)ndt::ST_COUNT; i++) ms[i] = c->ws.timer.ms[i];
+    if (runs) *runs = c->ws.timer.runs;
+    return (int)ndt::ST_COUNT;
 }
 
 extern "C" const char *ndnet_b200_last_error(const ndnet_b200_ctx *c) { return c ? c->err.c_str() : "null context"; }
@@ -152,6 +170,7 @@ extern "C" const char *ndnet_b200_last_error(const ndnet_b200_ctx *c) { return c
 // ------------------------------------------------------------------------------------------------
 // batched entry points
 // ------------------------------------------------------------------------------------------------
+struct ndnet_b200_model { mlp::Model m; };
 extern "C" int ndnet_b200_downsample_batch(ndnet_b200_ctx *c, const void *points, int dtype, const uint16_t *labels,
                                            int B, long N, int num_classes, long D, unsigned flags, float *out_feat,
                                            double *out_feat64, uint16_t *out_labels, int32_t *out_voxel,
@@ -202,6 +221,34 @@ extern "C" int ndnet_b200_downsample_batch_host(ndnet_b200_ctx *c, const void *p
     D2H(out_voxel, c->d_ovox, (size_t)B * D * 4);
     D2H(info, c->d_info, (size_t)B * sizeof(NdtCloudInfo));
 #undef D2H
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(c, e, "stream synchronise");
+    return 0;
+}
+
+// One call for the whole hot path from HOST buffers: H2D of the scans, NDT, network forward, D2H of the
+// per-distribution log-probabilities (segmentation) or class probabilities (classification), synchronise.
+extern "C" int ndnet_b200_infer_host(ndnet_b200_ctx *c, ndnet_b200_model *model, const void *points, int dtype,
+                                     const uint16_t *labels, int B, long N, int num_classes, long D, float *out_host,
+                                     long out_elems_per_cloud, void *stream) {
+    if (!c || !model || !points || !out_host || B <= 0 || N < 0 || D <= 0 || (dtype != 0 && dtype != 1)) return -200;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, e, "cudaSetDevice");
+    const size_t esz = dtype == 0 ? 4 : 8;
+    const size_t pbytes = (size_t)B * N * 3 * esz, obytes = (size_t)B * out_elems_per_cloud * 4;
+    if ((e = grow(c->d_points, c->d_points_bytes, pbytes)) != cudaSuccess) return fail(c, e, "staging allocation");
+    if (labels && (e = grow(c->d_labels, c->d_labels_bytes, (size_t)B * N * 2)) != cudaSuccess) return fail(c, e, "staging allocation");
+    if ((e = grow(c->d_feat, c->d_feat_bytes, (size_t)B * D * 12 * 4)) != cudaSuccess) return fail(c, e, "staging allocation");
+    if ((e = grow(c->d_logits, c->d_logits_bytes, obytes)) != cudaSuccess) return fail(c, e, "staging allocation");
+    if ((e = cudaMemcpyAsync(c->d_points, points, pbytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(c, e, "H2D points");
+    if (labels && (e = cudaMemcpyAsync(c->d_labels, labels, (size_t)B * N * 2, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return fail(c, e, "H2D labels");
+    int r = ndnet_b200_downsample_batch(c, c->d_points, dtype, labels ? c->d_labels : nullptr, B, N, num_classes, D,
+                                        NDNET_B200_NAN_TO_NUM, c->d_feat, nullptr, nullptr, nullptr, nullptr, stream);
+    if (r != 0) return r;
+    r = ndnet_b200_model_forward(c, model, c->d_feat, B, (int)D, c->d_logits, stream);
+    if (r != 0) return r;
+    if ((e = cudaMemcpyAsync(out_host, c->d_logits, obytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(c, e, "D2H");
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(c, e, "stream synchronise");
     return 0;
 }
@@ -424,8 +471,6 @@ extern "C" void print_matrix(double *matrix, int rows, int cols) {
 // ------------------------------------------------------------------------------------------------
 // model entry points: thin shims over mlp.cu
 // ------------------------------------------------------------------------------------------------
-struct ndnet_b200_model { mlp::Model m; };
-
 extern "C" int ndnet_b200_model_create(ndnet_b200_ctx *c, ndnet_b200_model **model, int kind, int n_tensors,
                                        const char *const *names, const float *const *data,
                                        const int64_t *const *shapes, const int *ndims) {

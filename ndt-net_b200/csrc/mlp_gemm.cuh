@@ -1,0 +1,275 @@
+// mlp_gemm.cuh — hand-written sm_100a GEMM for the PointNet / NDT-Net shared MLP:
+//   D[m, n] = sum_k A[m, k] * B[n, k]      (both operands K-major bf16, fp32 accumulation)
+// TMA (cp.async.bulk.tensor, 128B swizzle) stages the operand tiles in shared memory, one elected
+// thread issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN) into a TMEM accumulator, and four
+// epilogue warps read it back with tcgen05.ld and apply the fused epilogue:
+//   MODE_ROWS    rows = points of one cloud, columns = output channels:
+//                +bias (+per-cloud bias) (+ReLU) -> bf16 row-major activations for the next layer
+//   MODE_LOGSM   same orientation, final layer: +bias -> log_softmax over the valid columns -> fp32
+//   MODE_CHMAX   rows = output channels, columns = points of one cloud: the global max-pool over the
+//                points is a per-thread running max over TMEM columns, then +bias (+ReLU) and one
+//                atomicMax per channel: the [B, F, N] tensor of ndtnet.py:161 is never written.
+// Tiles never straddle clouds (3-D tensor maps {K, rows, cloud}; TMA zero-fills rows past the cloud).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mlp {
+
+enum { MODE_ROWS = 0, MODE_LOGSM = 1, MODE_CHMAX = 2 };
+
+struct GemmArgs {
+    int K;              // multiple of 64
+    int P;              // points per cloud
+    int a_batched;      // third TMA coordinate of the 128-row operand is the cloud index
+    int b_batched;      // ... of the BN-row operand
+    int mode;
+    int relu;
+    int n_valid;        // valid output channels
+    const float *bias;  // [n_valid] or null
+    const float *cbias; // per-cloud bias [B][ldcb] or null
+    int ldcb;
+    __nv_bfloat16 *out; // MODE_ROWS: [B][P][ldo]
+    int ldo;
+    float *outf;        // MODE_LOGSM: [B][P][n_valid]
+    unsigned *gmax;     // MODE_CHMAX: [B][ldg], order-preserving encoded floats (see enc_f32)
+    int ldg;
+};
+
+__device__ __forceinline__ unsigned enc_f32(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float dec_f32(unsigned u) {
+    u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace ptx
+
+// K-major, 128B-swizzled operand tile (rows x 64 bf16, 8-row groups 1024 B apart): UMMA shared-memory
+// descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
+// N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int kGemmThreads = 192;   // warps 0-3 epilogue, warp 4 TMA producer, warp 5 TMEM alloc + MMA issue
+
+template <int BN, int STAGES>
+constexpr size_t gemm_smem_bytes() { return (size_t)STAGES * (128 + BN) * 128 + 1024 /*align*/ + 256 /*barriers*/; }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads)
+k_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                               // STAGES x 16 KB
+    uint8_t *sB = smem + (size_t)STAGES * 128 * 128;  // STAGES x BN*128 B
+    uint64_t *bars = (uint64_t *)(sB + (size_t)STAGES * BN * 128);
+    uint64_t *full = bars, *empty = bars + STAGES, *tmem_full = bars + 2 * STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.z;
+    const int nkb = args.K / 64;
+    // operand tile origins
+    int a_row0, b_row0;
+    if (args.mode == MODE_CHMAX) { a_row0 = blockIdx.x * 128; b_row0 = blockIdx.y * BN; }
+    else { a_row0 = blockIdx.y * 128; b_row0 = blockIdx.x * BN; }
+    const int a_z = args.a_batched ? b : 0, b_z = args.b_batched ? b : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        ptx::mbar_init(tmem_full, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&mapA); ptx::prefetch_tmap(&mapB); }
+    if (warp == 5) ptx::tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                ptx::mbar_wait(&empty[s], ph ^ 1u);
+                ptx::mbar_expect_tx(&full[s], (128 + BN) * 128);
+                ptx::tma_load_3d(&mapA, &full[s], sA + (size_t)s * 128 * 128, kb * 64, a_row0, a_z);
+                ptx::tma_load_3d(&mapB, &full[s], sB + (size_t)s * BN * 128, kb * 64, b_row0, b_z);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                ptx::mbar_wait(&full[s], ph);
+                ptx::tc_fence_after();
+                const uint64_t da = make_kmajor_sw128_desc(ptx::smem_u32(sA + (size_t)s * 128 * 128));
+                const uint64_t db = make_kmajor_sw128_desc(ptx::smem_u32(sB + (size_t)s * BN * 128));
+#pragma unroll
+                for (int k4 = 0; k4 < 4; k4++)   // UMMA_K = 16 bf16 = 32 B = 2 descriptor units
+                    ptx::umma_bf16(tmem_base, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc, (kb | k4) ? 1u : 0u);
+                ptx::umma_commit(&empty[s]);     // frees the smem stage when these MMAs retire
+            }
+            ptx::umma_commit(tmem_full);         // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warp w owns TMEM lanes [32w, 32w+32)
+        ptx::mbar_wait(tmem_full, 0);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int m = warp * 32 + lane;          // accumulator row of this thread
+        if (args.mode == MODE_CHMAX) {
+            const int ch = a_row0 + m;
+            int valid = args.P - b_row0; if (valid > BN) valid = BN;
+            float best = -INFINITY;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (c0 >= valid) break;
+                uint32_t v[32];
+                ptx::tmem_ld32(taddr + (uint32_t)c0, v);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (c0 + j < valid) best = fmaxf(best, __uint_as_float(v[j]));
+            }
+            if (ch < args.n_valid) {
+                float r = best + (args.bias ? args.bias[ch] : 0.f);
+                if (args.relu) r = fmaxf(r, 0.f);
+                atomicMax(&args.gmax[(size_t)b * args.ldg + ch], enc_f32(r));
+            }
+        } else if (args.mode == MODE_ROWS) {
+            const int row = a_row0 + m;
+            const bool row_ok = row < args.P;
+            __nv_bfloat16 *orow = args.out + ((size_t)b * args.P + (row_ok ? row : 0)) * args.ldo + b_row0;
+            const float *cb = args.cbias ? args.cbias + (size_t)b * args.ldcb : nullptr;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld32(taddr + (uint32_t)c0, v);
+                ptx::tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const int n = b_row0 + c0 + j;
+                    float x0 = __uint_as_float(v[j]), x1 = __uint_as_float(v[j + 1]);
+                    if (n < args.n_valid) { if (args.bias) x0 += args.bias[n]; if (cb) x0 += cb[n]; } else x0 = 0.f;
+                    if (n + 1 < args.n_valid) { if (args.bias) x1 += args.bias[n + 1]; if (cb) x1 += cb[n + 1]; } else x1 = 0.f;
+                    if (args.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                    __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                    packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
+                }
+                if (row_ok) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) dst[q] = make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+                }
+            }
+        } else {   // MODE_LOGSM: BN == 32, the whole row is in this thread
+            const int row = a_row0 + m;
+            uint32_t v[32];
+            ptx::tmem_ld32(taddr, v);
+            ptx::tmem_ld_wait();
+            if (row < args.P) {
+                float x[32];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    x[j] = (j < args.n_valid) ? __uint_as_float(v[j]) + args.bias[j] : -INFINITY;
+                    mx = fmaxf(mx, x[j]);
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (j < args.n_valid) sum += __expf(x[j] - mx);
+                const float lse = mx + __logf(sum);
+                float *o = args.outf + ((size_t)b * args.P + row) * args.n_valid;
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (j < args.n_valid) o[j] = x[j] - lse;
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) ptx::tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+}
+
+}  // namespace mlp

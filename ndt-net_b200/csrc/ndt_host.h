@@ -9,6 +9,22 @@ namespace ndt {
 
 struct CloudState;
 
+// number of kernels this library launched since load (all contexts); bench.py reports the delta
+void count_launches(long n);
+long launches();
+
+// optional per-stage CUDA-event timing of run_batch (bench.py's roofline leg)
+enum Stage { ST_LIMITS = 0, ST_SEARCH, ST_RANK, ST_OFFSETS, ST_SCATTER, ST_STATS, ST_KL, ST_SELECT, ST_COUNT };
+struct StageTimer {
+    bool enabled = false;
+    cudaEvent_t ev[ST_COUNT + 1] = {};
+    bool created = false;
+    double ms[ST_COUNT] = {};
+    long runs = 0;
+    int search_launches = 0;
+    void mark(int i, cudaStream_t st) { if (enabled) cudaEventRecord(ev[i], st); }
+};
+
 // must match ndnet_b200_cloud_info in include/ndnet_b200.h
 struct NdtCloudInfo {
     int32_t status, prune_status, evaluations;
@@ -38,6 +54,7 @@ struct Workspace {
     unsigned long long *key = nullptr; unsigned *seq = nullptr;
     unsigned *firstpos = nullptr; unsigned char *removed = nullptr;
     double *list_div = nullptr; unsigned *list_seq = nullptr;
+    StageTimer timer;
     // of the last run
     int last_B = 0; long last_N = 0; long last_D = 0;
 

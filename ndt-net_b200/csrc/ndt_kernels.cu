@@ -827,6 +827,9 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     const unsigned vcap = w.vcap;
     const int ntiles = (int)((N + kRankTile - 1) / kRankTile);
     const int nbins = num_classes + 1;
+    StageTimer &tm = w.timer;
+    if (tm.enabled && !tm.created) { for (auto &e : tm.ev) cudaEventCreate(&e); tm.created = true; }
+    tm.mark(ST_LIMITS, st);
     k_init_limits<<<(B * 6 + 127) / 128, 128, 0, st>>>(w.lim_enc, B);
     {
         int chunks = (int)((N + 256 * 16 - 1) / (256 * 16));
@@ -834,6 +837,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         k_limits<T><<<dim3(chunks, B), 256, 0, st>>>(pts, N, w.lim_enc);
     }
     k_decide<<<B, 256, 0, st>>>(w.states, w.lim_enc, w.bitmap, w.bitmap_stride, w.vox_cell, vcap, D, 0);
+    tm.mark(ST_SEARCH, st);
     {
         int chunks = (int)((N + kCountPointsPerCta - 1) / kCountPointsPerCta);
         if (chunks < 1) chunks = 1;
@@ -842,23 +846,29 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
             k_decide<<<B, 256, 0, st>>>(w.states, w.lim_enc, w.bitmap, w.bitmap_stride, w.vox_cell, vcap, D, 1);
         }
     }
+    tm.mark(ST_RANK, st);
     if (N > 0) {
         const size_t rank_smem = 4 * (size_t)vcap * sizeof(unsigned short);
         if (rank_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_rank<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
         k_rank<T><<<dim3((ntiles + 3) / 4, B), 128, rank_smem, st>>>(
             pts, N, w.states, w.bitmap, w.bitmap_stride, vcap, ntiles, w.slot_rank, w.tile_cnt, w.point_voxel);
     }
+    tm.mark(ST_OFFSETS, st);
     k_offsets<<<B, 1024, 0, st>>>(w.states, vcap, ntiles, w.tile_cnt, w.vox_n, w.vox_start);
+    tm.mark(ST_SCATTER, st);
     if (labels) CK(cudaMemsetAsync(w.hist, 0, (size_t)B * vcap * nbins * sizeof(unsigned), st));
     if (N > 0) {
         k_scatter<T><<<dim3((unsigned)((N + 255) / 256), B), 256, 0, st>>>(
             pts, labels, N, w.states, vcap, ntiles, w.slot_rank, w.tile_cnt, w.vox_start, (T *)w.sorted,
             labels ? w.hist : nullptr, nbins);
     }
+    tm.mark(ST_STATS, st);
     k_stats<T><<<dim3((vcap + 127) / 128, B), 128, 0, st>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start,
                                                            labels ? w.hist : nullptr, nbins, w.mean, w.cov, w.cls);
+    tm.mark(ST_KL, st);
     k_kl<<<dim3((vcap + 63) / 64, B), 64, 0, st>>>(w.states, vcap, w.bitmap, w.bitmap_stride, w.vox_cell, w.vox_n, w.cov,
                                                   w.cov_final, w.kl_div, w.kl_flag);
+    tm.mark(ST_SELECT, st);
     {
         const size_t kcap = (size_t)vcap * kDirs;
         size_t P = 1; while (P < kcap) P <<= 1;
@@ -871,6 +881,13 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         k_select<<<B, 1024, bytes, st>>>(w.states, vcap, D, w.vox_cell, w.vox_n, w.mean, w.cov_final, w.cls, labels ? 1 : 0,
                                          w.kl_div, w.kl_flag, w.key, w.seq, kcap, smem_cap, w.firstpos, w.removed, flags,
                                          out_feat, out_feat64, out_labels, out_voxel, w.list_div, w.list_seq, info);
+    }
+    tm.mark(ST_COUNT, st);
+    count_launches(3 + 2 * kMaxGuessIterations + (N > 0 ? 2 : 0) + 4);
+    if (tm.enabled) {
+        CK(cudaEventSynchronize(tm.ev[ST_COUNT]));
+        for (int i = 0; i < ST_COUNT; i++) { float ms = 0; cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]); tm.ms[i] += ms; }
+        tm.runs++;
     }
     return cudaGetLastError();
 }

@@ -10,6 +10,10 @@ namespace ndt {
 
 size_t cloud_state_size() { return sizeof(CloudState); }
 
+static long g_launches = 0;
+void count_launches(long n) { __atomic_fetch_add(&g_launches, n, __ATOMIC_RELAXED); }
+long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 cudaError_t read_cloud_summary(const Workspace &w, int b, CloudSummary *out) {
     CloudState s;
     cudaError_t e = cudaMemcpy(&s, (const char *)w.states + (size_t)b * sizeof(CloudState), sizeof(s), cudaMemcpyDeviceToHost);

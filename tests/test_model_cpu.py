@@ -1,0 +1,39 @@
+"""CPU test: the drop-in torch modules (ndt-net_b200/ndnet/models/ndtnet.py) reproduce the outputs the
+reference's own modules gave (tests/golden/model_ref_golden.npz, made by make_model_golden.py) and keep the
+reference's state_dict key set."""
+import os
+
+import numpy as np
+import torch
+
+from ndnet.models.ndtnet import NDTNetClassification, NDTNetSegmentation
+from ndnet_b200.model import deterministic_state_dict
+from tests.golden.make_model_golden import inputs
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "model_ref_golden.npz")
+
+
+def test_drop_in_modules_match_reference_outputs():
+    g = np.load(GOLDEN)
+    with torch.no_grad():
+        seg = NDTNetSegmentation(num_classes=28, feature_dim=1024)
+        seg.load_state_dict(deterministic_state_dict(seg, 0)); seg.eval()
+        p, c = inputs(1, 2, 200)
+        out = seg(torch.from_numpy(p), torch.from_numpy(c)).numpy()
+        assert out.shape == g["seg_out"].shape == (2, 200, 29)
+        assert np.allclose(out, g["seg_out"], rtol=1e-4, atol=1e-4)
+        cls = NDTNetClassification()
+        cls.load_state_dict(deterministic_state_dict(cls, 1)); cls.eval()
+        p, c = inputs(2, 3, 130)
+        out = cls(torch.from_numpy(p), torch.from_numpy(c)).numpy()
+        assert out.shape == g["cls_out"].shape == (3, 512, 1)
+        assert np.allclose(out, g["cls_out"], rtol=1e-4, atol=1e-6)
+
+
+def test_state_dict_keys_follow_the_reference_layout():
+    keys = set(NDTNetSegmentation(num_classes=28).state_dict())
+    for k in ["feature_extractor.t1.conv1.weight", "feature_extractor.t2.fc3.bias", "feature_extractor.bn3.running_var",
+              "feature_extractor.conv3.weight", "conv4.weight", "bn3.running_mean", "feature_extractor.t1.bn5.weight"]:
+        assert k in keys, k
+    assert NDTNetSegmentation(num_classes=28).state_dict()["conv1.weight"].shape == (512, 1088, 1)
+    assert NDTNetClassification().state_dict()["conv3.weight"].shape == (512, 256, 1)

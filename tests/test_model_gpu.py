@@ -1,0 +1,84 @@
+"""GPU parity of the CUDA NDT-Net forward (tcgen05/TMA bf16 GEMM chain, ndt-net_b200/csrc/mlp*.cu) against
+the plain PyTorch fp32 forward of the same network (ndnet/models/ndtnet.py mirror, itself pinned to the
+reference modules by tests/test_model_cpu.py).
+
+Stated tolerance (bf16 operands, fp32 accumulation, 8 chained layers + two learned transforms):
+  segmentation log-probabilities: max |delta| <= SEG_ATOL, and >= SEG_AGREE of per-distribution argmax equal;
+  classification probabilities:   max |delta| <= CLS_ATOL.
+"""
+import numpy as np
+import pytest
+import torch
+
+from ndnet.models.ndtnet import NDTNetClassification, NDTNetSegmentation
+from ndnet_b200.model import deterministic_state_dict
+from tests.golden.make_model_golden import inputs
+
+pytestmark = pytest.mark.gpu
+
+SEG_ATOL, SEG_AGREE, CLS_ATOL = 0.15, 0.97, 2e-3
+
+
+def _seg(F=1024, C=28, seed=0):
+    net = NDTNetSegmentation(num_classes=C, feature_dim=F)
+    net.load_state_dict(deterministic_state_dict(net, seed))
+    return net.cuda().eval()
+
+
+@pytest.mark.parametrize("B,N", [(2, 200), (3, 128), (1, 1000), (5, 77)])
+def test_segmentation_forward_matches_torch_fp32(B, N):
+    net = _seg()
+    p, c = inputs(10 + N, B, N)
+    p, c = torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda()
+    with torch.no_grad():
+        ref = net(p, c)
+        got = net.forward_b200(p, c)
+    assert got.shape == ref.shape == (B, N, 29)
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    agree = (got.argmax(-1) == ref.argmax(-1)).float().mean().item()
+    assert err <= SEG_ATOL and agree >= SEG_AGREE, (err, agree)
+    assert torch.allclose(got.exp().sum(-1), torch.ones_like(got[..., 0]), atol=1e-3)
+
+
+def test_segmentation_feature_dim_768():
+    net = _seg(F=768, C=28, seed=3)
+    p, c = inputs(5, 2, 300)
+    p, c = torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda()
+    with torch.no_grad():
+        ref, got = net(p, c), net.forward_b200(p, c)
+    assert (got - ref).abs().max().item() <= SEG_ATOL
+
+
+@pytest.mark.parametrize("B,N", [(3, 130), (32, 512)])
+def test_classification_forward_matches_torch_fp32(B, N):
+    net = NDTNetClassification()
+    net.load_state_dict(deterministic_state_dict(net, 1))
+    net = net.cuda().eval()
+    p, c = inputs(20 + N, B, N)
+    p, c = torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda()
+    with torch.no_grad():
+        ref, got = net(p, c), net.forward_b200(p, c)
+    assert got.shape == ref.shape == (B, 512, 1)
+    assert (got - ref).abs().max().item() <= CLS_ATOL
+    assert torch.allclose(got.sum(1), torch.ones_like(got[:, 0]), atol=1e-4)
+
+
+def test_forward_b200_refuses_training_mode():
+    net = _seg().train()
+    p, c = inputs(1, 2, 64)
+    with pytest.raises(RuntimeError):
+        net.forward_b200(torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda())
+
+
+def test_end_to_end_ndt_then_network():
+    """The whole hot path: NDT features of synthetic scans -> segmentation log-probabilities."""
+    from ndnet.preprocessing.ndtnet_preprocessing import ndt_preprocessing
+    from ndnet_b200.synth import lidar_batch
+    net = _seg()
+    pts = torch.from_numpy(lidar_batch(2, 30000, seed0=77)).cuda()
+    means, covs, _ = ndt_preprocessing(500, pts)
+    with torch.no_grad():
+        ref, got = net(means, covs), net.forward_b200(means, covs)
+    agree = (got.argmax(-1) == ref.argmax(-1)).float().mean().item()
+    assert torch.isfinite(got).all() and agree >= 0.9, agree
