@@ -136,6 +136,9 @@ long ndnet_b200_last_kl_list(ndnet_b200_ctx *ctx, int b, double *div, int32_t *p
  * launching stream (and synchronise at the end); stage_times returns the accumulated milliseconds for
  * {limits, search, rank, offsets, scatter, stats, kl, select} and the number of batches measured. */
 long ndnet_b200_launch_count(void);
+/* Self test: compares the statistics kernel's reciprocal+FMA division by an integer count with the IEEE
+ * division on n pseudo-random operand pairs; returns the number of mismatching results (0 expected). */
+long ndnet_b200_selftest_div(long n, unsigned seed);
 int ndnet_b200_stage_timing(ndnet_b200_ctx *ctx, int enable);
 int ndnet_b200_stage_times(ndnet_b200_ctx *ctx, double *ms, int cap, long *runs);
 

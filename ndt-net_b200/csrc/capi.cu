@@ -64,7 +64,7 @@ static cudaError_t alloc(T *&p, size_t count) {
 }
 
 void Workspace::release() {
-    void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, slot_rank, tile_cnt, hist, point_voxel, sorted,
+    void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, vox_order, slot_rank, tile_cnt, hist, point_voxel, sorted,
                     mean, cov, cov_final, cls, kl_div, kl_flag, key, seq, firstpos, removed, list_div, list_seq};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = Workspace();
@@ -93,6 +93,7 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     A(vox_cell, (size_t)nB * vcap);
     A(vox_n, (size_t)nB * vcap);
     A(vox_start, (size_t)nB * (vcap + 1));
+    A(vox_order, (size_t)nB * vcap);
     A(slot_rank, (size_t)nB * nN);
     A(tile_cnt, (size_t)nB * ntiles_cap * vcap);
     A(hist, (size_t)nB * vcap * (nbins > 0 ? nbins : 1));
@@ -104,8 +105,9 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     A(cls, (size_t)nB * vcap);
     A(kl_div, (size_t)nB * kcap);
     A(kl_flag, (size_t)nB * kcap);
-    A(key, (size_t)nB * kcap);
-    A(seq, (size_t)nB * kcap);
+    size_t kpad = 1; while (kpad < kcap) kpad <<= 1;    // k_select pads its sort to a power of two
+    A(key, (size_t)nB * kpad);
+    A(seq, (size_t)nB * kpad);
     A(firstpos, (size_t)nB * vcap);
     A(removed, (size_t)nB * vcap);
     A(list_div, (size_t)nB * kcap);
@@ -146,6 +148,13 @@ extern "C" void ndnet_b200_destroy(ndnet_b200_ctx *c) {
     void *ptrs[] = {c->d_points, c->d_labels, c->d_feat, c->d_feat64, c->d_olab, c->d_ovox, c->d_info, c->d_logits};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete c;
+}
+
+extern "C" long ndnet_b200_selftest_div(long n, unsigned seed) {
+    unsigned long long bad = 0;
+    cudaError_t e = ndt::selftest_div(n, seed, &bad);
+    if (e != cudaSuccess) return fail(nullptr, e, "selftest_div");
+    return (long)bad;
 }
 
 extern "C" long ndnet_b200_launch_count(void) { return ndt::launches(); }

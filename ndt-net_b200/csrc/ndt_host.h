@@ -44,7 +44,7 @@ struct Workspace {
     CloudState *states = nullptr;
     unsigned long long *lim_enc = nullptr;
     uint2 *bitmap = nullptr;
-    unsigned *vox_cell = nullptr, *vox_n = nullptr, *vox_start = nullptr;
+    unsigned *vox_cell = nullptr, *vox_n = nullptr, *vox_start = nullptr, *vox_order = nullptr;
     unsigned *slot_rank = nullptr, *tile_cnt = nullptr, *hist = nullptr;
     int *point_voxel = nullptr;
     void *sorted = nullptr;
@@ -67,6 +67,7 @@ cudaError_t run_batch(Workspace &w, const void *pts, int dtype, const uint16_t *
                       NdtCloudInfo *info, cudaStream_t st);
 
 size_t cloud_state_size();
+cudaError_t selftest_div(long n, unsigned seed, unsigned long long *mismatches_host);
 
 // host copy of the scalar results of one cloud of the last batch
 struct CloudSummary { int status; int len[3]; unsigned V, K, n_valid, walk; int prune_ret; };

@@ -9,8 +9,16 @@
 #include "ndt_device.cuh"
 
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 namespace ndt {
+
+#ifdef NDT_CHECKS
+#define CHK(cond, id) do { if (!(cond)) { printf("NDT_CHECK %d failed: block %d thread %d\n", id, blockIdx.x, threadIdx.x); __trap(); } } while (0)
+#else
+#define CHK(cond, id) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // K1  bounding box (pointclouds.c:40-66).  grid (chunks, B), block 256.
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N,
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_offsets(const CloudState *__restrict__ states, unsigned vcap, int ntiles,
                                                   unsigned *__restrict__ tile_cnt, unsigned *__restrict__ vox_n,
-                                                  unsigned *__restrict__ vox_start) {
+                                                  unsigned *__restrict__ vox_start, unsigned *__restrict__ vox_order) {
     const int b = blockIdx.x;
     const CloudState &s = states[b];
     if (s.status != 0) return;
@@ -369,6 +377,19 @@ __global__ void __launch_bounds__(1024) k_offsets(const CloudState *__restrict__
         __syncthreads();
     }
     if (tid == 0) vox_start[(size_t)b * (vcap + 1) + V] = s_carry;
+    // processing order for k_stats: voxels bucketed by floor(log2(n)), heaviest bucket first, so the long
+    // sequential chains of the few huge voxels (up to ~25 % of a LiDAR scan in one cell) start first
+    __shared__ unsigned s_hist[32], s_cursor[32];
+    if (tid < 32) { s_hist[tid] = 0; s_cursor[tid] = 0; }
+    __syncthreads();
+    for (unsigned v = tid; v < V; v += blockDim.x) atomicAdd(&s_hist[__clz(vox_n[(size_t)b * vcap + v] | 1u)], 1u);
+    __syncthreads();
+    if (tid == 0) { unsigned run = 0; for (int k = 0; k < 32; k++) { const unsigned c = s_hist[k]; s_hist[k] = run; run += c; } }
+    __syncthreads();
+    for (unsigned v = tid; v < V; v += blockDim.x) {
+        const int key = __clz(vox_n[(size_t)b * vcap + v] | 1u);
+        vox_order[(size_t)b * vcap + s_hist[key] + atomicAdd(&s_cursor[key], 1u)] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -400,59 +421,145 @@ __global__ void __launch_bounds__(256) k_scatter(const T *__restrict__ pts, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// K7  per-voxel statistics: the literal sequential recurrence of normal_distributions.c:76-104 over
-// the voxel's points in ascending index order (bit-exact; the off-diagonal is order dependent, A6),
-// plus the label vote (:107-121).  One thread per voxel.  grid (ceil(vcap/128), B), block 128.
+// K7  per-voxel statistics: the sequential recurrence of normal_distributions.c:76-104 over the voxel's
+// points in ascending index order (bit-exact; the off-diagonal is order dependent, A6), plus the label
+// vote (:107-121).  One WARP per voxel, 32 points per round staged in shared memory:
+//   A. lanes 0-2 run the three mean chains  mu += (x - mu) / i  (the only loop-carried fp64 dependency);
+//      the division by the integer count uses a reciprocal computed off the chain and one FMA residual
+//      correction, which is correctly rounded for integer divisors < 2^26 (see div_by_count);
+//   B. all lanes compute, in parallel, the per-point terms that only need mu^{i-1} and mu^{i}:
+//      (x_j - old_j)(x_j - new_j) and (x_j - new_j)(x_k - old_k) / i;
+//   C. lanes 0-5 add the terms of the previous round to the six running sums in order (one DADD per step,
+//      issued in the shadow of the mean chain's latency).
+// grid (B, ceil(vcap/4)), block 128; voxels are visited heaviest-first (vox_order from k_offsets).
 // ------------------------------------------------------------------------------------------------
+
+// RN(d / cnt) for an integer-valued cnt in [1, 2^26) and its correctly rounded reciprocal r = RN(1/cnt).
+// q0 = RN(d r) is within 1.5 ulp of d/cnt, the FMA residual e = d - cnt q0 is exact, and q0 + e r differs
+// from d/cnt by < 2^-52 ulp, while d/cnt (53-bit numerator over an integer < 2^26) is either exactly
+// representable or at least 2^-27 ulp away from any rounding boundary; hence RN(q0 + e r) = RN(d/cnt).
+// Zeros, subnormal-range and huge operands take the true division.
+__device__ __forceinline__ double div_by_count(double d, double cnt, double r) {
+    const double ad = fabs(d);
+    if (ad > 1e-290 && ad < 1e290) {
+        const double q0 = d * r;
+        const double e = fma(-cnt, q0, d);
+        return fma(e, r, q0);
+    }
+    return d / cnt;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
                                                const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
+                                               const unsigned *__restrict__ vox_order,
                                                const unsigned *__restrict__ hist, int nbins,
                                                double *__restrict__ mean, double *__restrict__ cov, uint16_t *__restrict__ cls) {
-    const int b = blockIdx.y;
+    const int b = blockIdx.x;
     const CloudState &s = states[b];
     if (s.status != 0) return;
-    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= s.V) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned idx = blockIdx.y * 4 + warp;
+    if (idx >= s.V) return;
+    const unsigned v = vox_order[(size_t)b * vcap + idx];
     const unsigned st = vox_start[(size_t)b * (vcap + 1) + v], en = vox_start[(size_t)b * (vcap + 1) + v + 1];
     const T *p = sorted + ((size_t)b * N + st) * 3;
-    double mu0 = 0, mu1 = 0, mu2 = 0, m20 = 0, m21 = 0, m22 = 0, c01 = 0, c02 = 0, c12 = 0;
-    double cnt = 0.0;
-    for (unsigned k = 0; k < en - st; k++) {
-        const double x0 = (double)p[k * 3 + 0], x1 = (double)p[k * 3 + 1], x2 = (double)p[k * 3 + 2];
-        cnt += 1.0;                               // exact for counts < 2^53
-        // j = 0
-        const double o0 = mu0;
-        mu0 += (x0 - mu0) / cnt;
-        m20 += (x0 - o0) * (x0 - mu0);
-        c01 += (x0 - mu0) * (x1 - mu1) / cnt;     // mu1, mu2 still old here
-        if (isnan(c01)) c01 = 0.0;
-        c02 += (x0 - mu0) * (x2 - mu2) / cnt;
-        if (isnan(c02)) c02 = 0.0;
-        // j = 1
-        const double o1 = mu1;
-        mu1 += (x1 - mu1) / cnt;
-        m21 += (x1 - o1) * (x1 - mu1);
-        c12 += (x1 - mu1) * (x2 - mu2) / cnt;
-        if (isnan(c12)) c12 = 0.0;
-        // j = 2
-        const double o2 = mu2;
-        mu2 += (x2 - mu2) / cnt;
-        m22 += (x2 - o2) * (x2 - mu2);
+
+    __shared__ double s_x[4][3][32];       // coordinates of the round
+    __shared__ double s_r[4][32];          // 1 / count
+    __shared__ double s_mu[4][3][33];      // means: [.][0] before the round's first point, [.][k+1] after point k
+    __shared__ double s_t[4][2][6][32];    // terms of the round (double buffered): m2 x3, c01, c02, c12
+    double(*xs)[32] = s_x[warp];
+    double *rs = s_r[warp];
+    double(*mus)[33] = s_mu[warp];
+
+    const int cl = lane < 3 ? lane : 2;    // chain lane -> dimension
+    const int al = lane < 6 ? lane : 5;    // accumulator lane -> term
+    double mu = 0.0, acc = 0.0;
+    if (lane < 3) mus[lane][0] = 0.0;
+    const unsigned n = en - st;
+    int prev_m = 0, buf = 0;
+    for (unsigned base = 0; base < n; base += 32) {
+        const int m = (int)(n - base < 32u ? n - base : 32u);
+        double x0 = 0, x1 = 0, x2 = 0;
+        if (lane < m) {
+            x0 = (double)p[(size_t)(base + lane) * 3 + 0];
+            x1 = (double)p[(size_t)(base + lane) * 3 + 1];
+            x2 = (double)p[(size_t)(base + lane) * 3 + 2];
+            xs[0][lane] = x0; xs[1][lane] = x1; xs[2][lane] = x2;
+            rs[lane] = 1.0 / (double)(base + lane + 1);
+        }
+        __syncwarp();
+        // ---- A (this round's means) fused with C (previous round's running sums)
+        const double(*tp)[32] = s_t[warp][buf ^ 1];
+#pragma unroll 4
+        for (int k = 0; k < m; k++) {
+            const double x = xs[cl][k];
+            const double r = rs[k];
+            const double cnt = (double)(base + k + 1);
+            mu = mu + div_by_count(x - mu, cnt, r);
+            if (lane < 3) mus[lane][k + 1] = mu;
+            if (k < prev_m) {
+                acc += tp[al][k];
+                if (lane >= 3 && isnan(acc)) acc = 0.0;
+            }
+        }
+        for (int k = m; k < prev_m; k++) {           // only when the previous round was longer: never (rounds shrink last)
+            acc += tp[al][k];
+            if (lane >= 3 && isnan(acc)) acc = 0.0;
+        }
+        __syncwarp();
+        // ---- B: per-point terms
+        if (lane < m) {
+            const double o0 = mus[0][lane], o1 = mus[1][lane], o2 = mus[2][lane];
+            const double n0 = mus[0][lane + 1], n1 = mus[1][lane + 1], n2 = mus[2][lane + 1];
+            const double cnt = (double)(base + lane + 1);
+            double(*t)[32] = s_t[warp][buf];
+            t[0][lane] = (x0 - o0) * (x0 - n0);
+            t[1][lane] = (x1 - o1) * (x1 - n1);
+            t[2][lane] = (x2 - o2) * (x2 - n2);
+            t[3][lane] = (x0 - n0) * (x1 - o1) / cnt;   // mu_1, mu_2 not yet updated when j = 0 runs
+            t[4][lane] = (x0 - n0) * (x2 - o2) / cnt;
+            t[5][lane] = (x1 - n1) * (x2 - o2) / cnt;   // mu_2 not yet updated when j = 1 runs
+        }
+        __syncwarp();
+        if (lane < 3) mus[lane][0] = mus[lane][m];
+        prev_m = m; buf ^= 1;
+        __syncwarp();
     }
-    double v0 = m20 / cnt, v1 = m21 / cnt, v2 = m22 / cnt;
-    if (isnan(v0)) v0 = 0.0;
-    if (isnan(v1)) v1 = 0.0;
-    if (isnan(v2)) v2 = 0.0;
-    double *mo = mean + ((size_t)b * vcap + v) * 3;
-    mo[0] = mu0; mo[1] = mu1; mo[2] = mu2;
-    double *co = cov + ((size_t)b * vcap + v) * 9;
-    co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
+    {   // C for the last round
+        const double(*tp)[32] = s_t[warp][buf ^ 1];
+        for (int k = 0; k < prev_m; k++) {
+            acc += tp[al][k];
+            if (lane >= 3 && isnan(acc)) acc = 0.0;
+        }
+    }
+    // variances m2 / n (normal_distributions.c:86-89), NaN -> 0
+    const double cntn = (double)n;
+    double var = acc / cntn;
+    if (isnan(var)) var = 0.0;
+    const double out = lane < 3 ? var : acc;
+    const double v0 = __shfl_sync(0xffffffffu, out, 0), v1 = __shfl_sync(0xffffffffu, out, 1), v2 = __shfl_sync(0xffffffffu, out, 2);
+    const double c01 = __shfl_sync(0xffffffffu, out, 3), c02 = __shfl_sync(0xffffffffu, out, 4), c12 = __shfl_sync(0xffffffffu, out, 5);
+    const double m0 = __shfl_sync(0xffffffffu, mu, 0), m1 = __shfl_sync(0xffffffffu, mu, 1), m2 = __shfl_sync(0xffffffffu, mu, 2);
+    if (lane == 0) {
+        double *mo = mean + ((size_t)b * vcap + v) * 3;
+        mo[0] = m0; mo[1] = m1; mo[2] = m2;
+        double *co = cov + ((size_t)b * vcap + v) * 9;
+        co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
+    }
     if (hist) {
+        // lowest class index with the strictly largest count (normal_distributions.c:114-120)
         const unsigned *h = hist + ((size_t)b * vcap + v) * nbins;
-        unsigned best = 0; uint16_t c = 0;
-        for (int j = 0; j < nbins; j++) { const unsigned x = h[j]; if (x > best) { best = x; c = (uint16_t)j; } }
-        cls[(size_t)b * vcap + v] = c;
+        unsigned best = 0; int bc = 0x7fffffff;
+        for (int j = lane; j < nbins; j += 32) { const unsigned x = h[j]; if (x > best) { best = x; bc = j; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
+        }
+        if (lane == 0) cls[(size_t)b * vcap + v] = (uint16_t)(best > 0 ? bc : 0);
     }
 }
 
@@ -636,8 +743,11 @@ __global__ void __launch_bounds__(1024) k_select(CloudState *__restrict__ states
     const unsigned nslots = V * kDirs;
     const double *kd = kl_div + (size_t)b * vcap * kDirs;
     const unsigned char *kf = kl_flag + (size_t)b * vcap * kDirs;
-    unsigned long long *gk = g_key + (size_t)b * kcap;
-    unsigned *gs = g_seq + (size_t)b * kcap;
+    // the sort scratch is padded to a power of two per cloud (kpad >= kcap): the global-memory fallback
+    // pads the list up to the next power of two
+    size_t kpad = 1; while (kpad < kcap) kpad <<= 1;
+    unsigned long long *gk = g_key + (size_t)b * kpad;
+    unsigned *gs = g_seq + (size_t)b * kpad;
 
     // ---- 1. compaction in insertion order + NaN rule: a NaN takes the exclusive prefix-minimum of
     //         the finite (non-NaN) divergences inserted before it, +inf if none.
@@ -665,6 +775,7 @@ __global__ void __launch_bounds__(1024) k_select(CloudState *__restrict__ states
         excl = wpre < excl ? wpre : excl;
         if (present) {
             const unsigned pos = s_carry + pos_in;
+            CHK(pos < kcap, 1);
             if (pos < kcap) {
                 gk[pos] = desc_key(isn ? excl : d);
                 gs[pos] = q;
@@ -675,9 +786,11 @@ __global__ void __launch_bounds__(1024) k_select(CloudState *__restrict__ states
         __syncthreads();
     }
     const unsigned K = s_carry;
+    CHK(K <= kcap && V <= vcap, 2);
     // ---- 2. stable sort (key ascending == divergence descending, then insertion sequence ascending)
     unsigned P = 1; while (P < K) P <<= 1;
     const bool in_smem = (int)P <= smem_cap;
+    CHK(in_smem || P <= kpad, 3);
     unsigned long long *key = in_smem ? s_dyn : gk;
     unsigned *seq = in_smem ? (unsigned *)(s_dyn + P) : gs;
     if (in_smem) { for (unsigned i = tid; i < K; i += blockDim.x) { key[i] = gk[i]; seq[i] = gs[i]; } }
@@ -701,7 +814,7 @@ __global__ void __launch_bounds__(1024) k_select(CloudState *__restrict__ states
     // keep the sorted list (for the legacy handles / inspection)
     if (list_div) {
         double *ld = list_div + (size_t)b * kcap; unsigned *ls = list_seq + (size_t)b * kcap;
-        for (unsigned i = tid; i < K; i += blockDim.x) { const unsigned q = seq[i]; ld[i] = kd[q]; ls[i] = q; }
+        for (unsigned i = tid; i < K; i += blockDim.x) { const unsigned q = seq[i]; CHK(q < nslots, 4); ld[i] = kd[q]; ls[i] = q; }
     }
     // ---- 3. prune walk: first occurrence of each p in list order, the first to_remove of them go,
     //         subject to the shrinking-length stop (ndt.c:53)
@@ -709,7 +822,7 @@ __global__ void __launch_bounds__(1024) k_select(CloudState *__restrict__ states
     unsigned char *removed = g_removed + (size_t)b * vcap;
     for (unsigned v = tid; v < V; v += blockDim.x) { firstpos[v] = 0xFFFFFFFFu; removed[v] = 0; }
     __syncthreads();
-    for (unsigned i = tid; i < K; i += blockDim.x) atomicMin(&firstpos[seq[i] / kDirs], i);
+    for (unsigned i = tid; i < K; i += blockDim.x) { CHK(seq[i] / kDirs < V, 5); atomicMin(&firstpos[seq[i] / kDirs], i); }
     __syncthreads();
     const unsigned to_remove = (unsigned)((unsigned long)V - (unsigned long)D);   // V >= D on acceptance
     if (tid == 0) s_carry = 0;
@@ -808,6 +921,41 @@ __global__ void __launch_bounds__(1024) k_select(CloudState *__restrict__ states
 }
 
 // ------------------------------------------------------------------------------------------------
+// self test of div_by_count against the IEEE division, on pseudo-random operands (tests/ call this)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_selftest_div(long n, unsigned seed, unsigned long long *mismatches) {
+    unsigned long long bad = 0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        unsigned long long h = (unsigned long long)i * 0x9E3779B97F4A7C15ull + seed;
+        h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32; h *= 0x94D049BB133111EBull; h ^= h >> 29;
+        const unsigned mode = (unsigned)(i & 7);
+        // mantissa from the hash; exponent spread depends on the mode (typical coordinates .. extreme)
+        const int espan = mode < 4 ? 20 : (mode < 6 ? 200 : 1000);
+        const int e = 1023 + (int)((h >> 52) % (unsigned)(2 * espan + 1)) - espan;
+        unsigned long long bits = (h & 0x800FFFFFFFFFFFFFull) | ((unsigned long long)(e < 1 ? 1 : (e > 2046 ? 2046 : e)) << 52);
+        if (mode == 3) bits &= 0xFFFFFFFFE0000000ull;            // fp32-representable numerators
+        const double d = __longlong_as_double((long long)bits);
+        unsigned long long h2 = h * 0xD6E8FEB86659FD93ull; h2 ^= h2 >> 32;
+        const unsigned c = (mode & 1) ? (unsigned)(h2 % 120000u) + 1u : (unsigned)(h2 % 67000000u) + 1u;
+        const double cnt = (double)c;
+        const double want = d / cnt, got = div_by_count(d, cnt, 1.0 / cnt);
+        if (__double_as_longlong(want) != __double_as_longlong(got)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t selftest_div(long n, unsigned seed, unsigned long long *mismatches_host) {
+    unsigned long long *d = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d, 8);
+    if (e != cudaSuccess) return e;
+    cudaMemset(d, 0, 8);
+    k_selftest_div<<<592, 256>>>(n, seed, d);
+    e = cudaMemcpy(mismatches_host, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
 __global__ void k_init_limits(unsigned long long *lim_enc, int B) {
@@ -819,6 +967,13 @@ __global__ void k_init_limits(unsigned long long *lim_enc, int B) {
 // host driver
 // ------------------------------------------------------------------------------------------------
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+// NDNET_B200_DEBUG_SYNC=1: synchronise after every launch and name the kernel that faulted
+static bool debug_sync(const char *name) {
+    const char *e = getenv("NDNET_B200_DEBUG_SYNC");
+    return e && (*e == '1' || strcmp(e, name) == 0);
+}
+#define DBG(name) do { if (debug_sync(name)) { cudaError_t e_ = cudaStreamSynchronize(st); if (e_ == cudaSuccess) e_ = cudaGetLastError(); \
+    if (e_ != cudaSuccess) { fprintf(stderr, "ndnet_b200: kernel %s failed: %s\n", name, cudaGetErrorString(e_)); return e_; } } } while (0)
 
 template <typename T>
 static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels, int B, long N, int num_classes,
@@ -834,16 +989,16 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     {
         int chunks = (int)((N + 256 * 16 - 1) / (256 * 16));
         if (chunks < 1) chunks = 1;
-        k_limits<T><<<dim3(chunks, B), 256, 0, st>>>(pts, N, w.lim_enc);
+        k_limits<T><<<dim3(chunks, B), 256, 0, st>>>(pts, N, w.lim_enc); DBG("k_limits");
     }
-    k_decide<<<B, 256, 0, st>>>(w.states, w.lim_enc, w.bitmap, w.bitmap_stride, w.vox_cell, vcap, D, 0);
+    k_decide<<<B, 256, 0, st>>>(w.states, w.lim_enc, w.bitmap, w.bitmap_stride, w.vox_cell, vcap, D, 0); DBG("k_decide");
     tm.mark(ST_SEARCH, st);
     {
         int chunks = (int)((N + kCountPointsPerCta - 1) / kCountPointsPerCta);
         if (chunks < 1) chunks = 1;
         for (int it = 0; it < kMaxGuessIterations; it++) {
-            k_count<T><<<dim3(chunks, B), 256, 0, st>>>(pts, N, w.states, w.bitmap, w.bitmap_stride);
-            k_decide<<<B, 256, 0, st>>>(w.states, w.lim_enc, w.bitmap, w.bitmap_stride, w.vox_cell, vcap, D, 1);
+            k_count<T><<<dim3(chunks, B), 256, 0, st>>>(pts, N, w.states, w.bitmap, w.bitmap_stride); DBG("k_count");
+            k_decide<<<B, 256, 0, st>>>(w.states, w.lim_enc, w.bitmap, w.bitmap_stride, w.vox_cell, vcap, D, 1); DBG("k_decide");
         }
     }
     tm.mark(ST_RANK, st);
@@ -852,22 +1007,26 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         if (rank_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_rank<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
         k_rank<T><<<dim3((ntiles + 3) / 4, B), 128, rank_smem, st>>>(
             pts, N, w.states, w.bitmap, w.bitmap_stride, vcap, ntiles, w.slot_rank, w.tile_cnt, w.point_voxel);
+        DBG("k_rank");
     }
     tm.mark(ST_OFFSETS, st);
-    k_offsets<<<B, 1024, 0, st>>>(w.states, vcap, ntiles, w.tile_cnt, w.vox_n, w.vox_start);
+    k_offsets<<<B, 1024, 0, st>>>(w.states, vcap, ntiles, w.tile_cnt, w.vox_n, w.vox_start, w.vox_order); DBG("k_offsets");
     tm.mark(ST_SCATTER, st);
     if (labels) CK(cudaMemsetAsync(w.hist, 0, (size_t)B * vcap * nbins * sizeof(unsigned), st));
     if (N > 0) {
         k_scatter<T><<<dim3((unsigned)((N + 255) / 256), B), 256, 0, st>>>(
             pts, labels, N, w.states, vcap, ntiles, w.slot_rank, w.tile_cnt, w.vox_start, (T *)w.sorted,
             labels ? w.hist : nullptr, nbins);
+        DBG("k_scatter");
     }
     tm.mark(ST_STATS, st);
-    k_stats<T><<<dim3((vcap + 127) / 128, B), 128, 0, st>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start,
-                                                           labels ? w.hist : nullptr, nbins, w.mean, w.cov, w.cls);
+    k_stats<T><<<dim3(B, (vcap + 3) / 4), 128, 0, st>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order,
+                                                       labels ? w.hist : nullptr, nbins, w.mean, w.cov, w.cls);
+    DBG("k_stats");
     tm.mark(ST_KL, st);
     k_kl<<<dim3((vcap + 63) / 64, B), 64, 0, st>>>(w.states, vcap, w.bitmap, w.bitmap_stride, w.vox_cell, w.vox_n, w.cov,
                                                   w.cov_final, w.kl_div, w.kl_flag);
+    DBG("k_kl");
     tm.mark(ST_SELECT, st);
     {
         const size_t kcap = (size_t)vcap * kDirs;
@@ -881,7 +1040,9 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         k_select<<<B, 1024, bytes, st>>>(w.states, vcap, D, w.vox_cell, w.vox_n, w.mean, w.cov_final, w.cls, labels ? 1 : 0,
                                          w.kl_div, w.kl_flag, w.key, w.seq, kcap, smem_cap, w.firstpos, w.removed, flags,
                                          out_feat, out_feat64, out_labels, out_voxel, w.list_div, w.list_seq, info);
+        DBG("k_select");
     }
+    DBG("end");
     tm.mark(ST_COUNT, st);
     count_launches(3 + 2 * kMaxGuessIterations + (N > 0 ? 2 : 0) + 4);
     if (tm.enabled) {

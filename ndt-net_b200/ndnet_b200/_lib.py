@@ -53,6 +53,8 @@ def lib() -> C.CDLL:
     L.ndnet_b200_last_point_voxels.argtypes = [vp, vp, vp]
     L.ndnet_b200_last_kl_list.restype = l
     L.ndnet_b200_last_kl_list.argtypes = [vp, i, vp, vp, vp, l]
+    L.ndnet_b200_selftest_div.restype = l
+    L.ndnet_b200_selftest_div.argtypes = [l, u]
     L.ndnet_b200_launch_count.restype = l
     L.ndnet_b200_launch_count.argtypes = []
     L.ndnet_b200_stage_timing.restype = i
@@ -76,7 +78,7 @@ EXPORTED = [
     "ndt_downsample", "prune_nds", "to_point_cloud", "free_nds", "free_kl_divergences", "print_matrix",
     "ndnet_b200_create", "ndnet_b200_destroy", "ndnet_b200_last_error", "ndnet_b200_version",
     "ndnet_b200_downsample_batch", "ndnet_b200_downsample_batch_host", "ndnet_b200_last_point_voxels",
-    "ndnet_b200_last_kl_list", "ndnet_b200_launch_count", "ndnet_b200_stage_timing", "ndnet_b200_stage_times",
+    "ndnet_b200_last_kl_list", "ndnet_b200_selftest_div", "ndnet_b200_launch_count", "ndnet_b200_stage_timing", "ndnet_b200_stage_times",
     "ndnet_b200_model_create", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
     "ndnet_b200_infer_host",
 ]

@@ -198,6 +198,13 @@ def test_ndt_preprocessing_drop_in(engine):
         assert torch.all(k[b].sum(1) == 1)
 
 
+def test_count_division_is_ieee_exact():
+    """k_stats divides by the running count with a reciprocal + one FMA correction; it must equal the IEEE
+    quotient bit for bit (2e8 pseudo-random operand pairs, counts up to 6.7e7, exponents up to +-1000)."""
+    from ndnet_b200 import _lib
+    assert _lib.lib().ndnet_b200_selftest_div(200_000_000, 12345) == 0
+
+
 def test_legacy_sampler_drop_in():
     """NDT_Sampler (ndt_legacy.py:45-240) bound to the legacy symbols of libndnet_b200.so."""
     from ndnet.preprocessing.ndt_legacy import NDT_Sampler
