@@ -56,12 +56,26 @@ __device__ __forceinline__ double dec_f64(unsigned long long u) {
     return __longlong_as_double((long long)u);
 }
 
+// floor((p - off) / vs) exactly as voxel.c:89-91 computes it (IEEE subtraction, IEEE division, floor), but
+// without the division in the common case: with rv = RN(1/vs), q0 = RN(a * rv) is within 2 ulp of the
+// IEEE quotient, so whenever q0 is further than 2^-48 (relative) from an integer both have the same floor;
+// only the rare near-integer cases take the real division.
+__device__ __forceinline__ unsigned axis_cell(double p, double off, double vs, double rv) {
+    const double a = p - off;
+    const double q0 = a * rv;
+    const double f = floor(q0);
+    const double t = q0 - f;                                  // exact (Sterbenz / small integers)
+    const double eps = q0 * 3.5527136788005009e-15;           // 2^-48 * q0  (>= 16 ulp)
+    if (t > eps && (1.0 - t) > eps) return (unsigned)f;
+    return (unsigned)floor(a / vs);
+}
+
 // voxel.c:83-103 + :177-189.  Returns false when the point is outside the grid.
-__device__ __forceinline__ bool voxel_of(double x, double y, double z, const double off[3], double vs,
+__device__ __forceinline__ bool voxel_of(double x, double y, double z, const double off[3], double vs, double rv,
                                          const int len[3], unsigned &id) {
-    const unsigned vx = (unsigned)floor((x - off[0]) / vs);
-    const unsigned vy = (unsigned)floor((y - off[1]) / vs);
-    const unsigned vz = (unsigned)floor((z - off[2]) / vs);
+    const unsigned vx = axis_cell(x, off[0], vs, rv);
+    const unsigned vy = axis_cell(y, off[1], vs, rv);
+    const unsigned vz = axis_cell(z, off[2], vs, rv);
     if (vx >= (unsigned)len[0] || vy >= (unsigned)len[1] || vz >= (unsigned)len[2]) return false;
     id = vz * (unsigned)len[0] * (unsigned)len[1] + vy * (unsigned)len[0] + vx;
     return true;

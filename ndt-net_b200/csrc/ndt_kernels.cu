@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N
     const unsigned G = s.G, nwords = s.nwords;
     if (G == 0) return;                                  // a degenerate axis: no voxel can be valid (A3)
     const double vs = s.guess;
+    const double rv = 1.0 / vs;
     const double off[3] = {s.off[0], s.off[1], s.off[2]};
     const int len[3] = {s.len[0], s.len[1], s.len[2]};
     const long chunk = N / kWorkers;
@@ -231,14 +232,14 @@ __global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N
         for (long i = threadIdx.x; i < n_used; i += blockDim.x) {
             double x, y, z; load_point(p, i, x, y, z);
             unsigned id;
-            if (!voxel_of(x, y, z, off, vs, len, id)) atomicMin(&s_fail[i / chunk], (unsigned)i);
+            if (!voxel_of(x, y, z, off, vs, rv, len, id)) atomicMin(&s_fail[i / chunk], (unsigned)i);
         }
         __syncthreads();
         for (long i = threadIdx.x; i < n_used; i += blockDim.x) {
             if ((unsigned)i >= s_fail[i / chunk]) continue;
             double x, y, z; load_point(p, i, x, y, z);
             unsigned id;
-            voxel_of(x, y, z, off, vs, len, id);
+            voxel_of(x, y, z, off, vs, rv, len, id);
             if (use_smem) atomicOr(&s_bits[id >> 5], 1u << (id & 31));
             else atomicOr(&bm[id >> 5].x, 1u << (id & 31));
         }
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N
         for (long i = begin + threadIdx.x; i < end; i += blockDim.x) {
             double x, y, z; load_point(p, i, x, y, z);
             unsigned id;
-            if (voxel_of(x, y, z, off, vs, len, id)) atomicOr(&s_bits[id >> 5], 1u << (id & 31));
+            if (voxel_of(x, y, z, off, vs, rv, len, id)) atomicOr(&s_bits[id >> 5], 1u << (id & 31));
         }
         __syncthreads();
         for (unsigned w = threadIdx.x; w < nwords; w += blockDim.x) {
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N
         for (long i = begin + threadIdx.x; i < end; i += blockDim.x) {
             double x, y, z; load_point(p, i, x, y, z);
             unsigned id;
-            if (voxel_of(x, y, z, off, vs, len, id)) atomicOr(&bm[id >> 5].x, 1u << (id & 31));
+            if (voxel_of(x, y, z, off, vs, rv, len, id)) atomicOr(&bm[id >> 5].x, 1u << (id & 31));
         }
     }
 }
@@ -304,6 +305,7 @@ __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N,
     const T *p = pts + (size_t)b * N * 3;
     const uint2 *bm = bitmap + (size_t)b * bitmap_stride;
     const double vs = s.guess;
+    const double rv = 1.0 / vs;
     const double off[3] = {s.off[0], s.off[1], s.off[2]};
     const int len[3] = {s.len[0], s.len[1], s.len[2]};
     const long chunk = N / kWorkers;
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N,
         unsigned id = 0;
         if (i < n_used && (unsigned)i < s.fail[i / chunk]) {
             double x, y, z; load_point(p, i, x, y, z);
-            if (voxel_of(x, y, z, off, vs, len, id)) {
+            if (voxel_of(x, y, z, off, vs, rv, len, id)) {
                 const uint2 w = bm[id >> 5];
                 slot = w.y + __popc(w.x & ((1u << (id & 31)) - 1u));
             }
@@ -434,17 +436,18 @@ __global__ void __launch_bounds__(256) k_scatter(const T *__restrict__ pts, cons
 // grid (B, ceil(vcap/4)), block 128; voxels are visited heaviest-first (vox_order from k_offsets).
 // ------------------------------------------------------------------------------------------------
 
-// RN(d / cnt) for an integer-valued cnt in [1, 2^26) and its correctly rounded reciprocal r = RN(1/cnt).
-// q0 = RN(d r) is within 1.5 ulp of d/cnt, the FMA residual e = d - cnt q0 is exact, and q0 + e r differs
-// from d/cnt by < 2^-52 ulp, while d/cnt (53-bit numerator over an integer < 2^26) is either exactly
-// representable or at least 2^-27 ulp away from any rounding boundary; hence RN(q0 + e r) = RN(d/cnt).
-// Zeros, subnormal-range and huge operands take the true division.
-__device__ __forceinline__ double div_by_count(double d, double cnt, double r) {
+// RN(d / cnt) for an integer-valued cnt in [1, 2^26) without a division on the dependent chain:
+// rh = RN(1/cnt), rl = RN((1 - cnt rh) rh) give rh + rl = (1/cnt)(1 + e), |e| < 2^-104, so the single
+// rounding of fma(d, rh, RN(d rl)) rounds a value within 2^-103 (relative) of d/cnt.  d/cnt (53-bit
+// numerator over an integer < 2^26) is either exactly representable or at least 2^-80 (relative) away
+// from every rounding boundary, hence the result is the correctly rounded quotient.  Zeros, operands
+// whose low product could underflow and huge operands take the IEEE division.
+__device__ __forceinline__ double div_by_count(double d, double cnt) {
     const double ad = fabs(d);
-    if (ad > 1e-290 && ad < 1e290) {
-        const double q0 = d * r;
-        const double e = fma(-cnt, q0, d);
-        return fma(e, r, q0);
+    if (ad > 1e-250 && ad < 1e290) {
+        const double rh = 1.0 / cnt;
+        const double rl = fma(-cnt, rh, 1.0) * rh;
+        return fma(d, rh, d * rl);
     }
     return d / cnt;
 }
@@ -465,73 +468,174 @@ __global__ void __launch_bounds__(128) k_stats(const CloudState *__restrict__ st
     const unsigned st = vox_start[(size_t)b * (vcap + 1) + v], en = vox_start[(size_t)b * (vcap + 1) + v + 1];
     const T *p = sorted + ((size_t)b * N + st) * 3;
 
-    __shared__ double s_x[4][3][32];       // coordinates of the round
-    __shared__ double s_r[4][32];          // 1 / count
-    __shared__ double s_mu[4][3][33];      // means: [.][0] before the round's first point, [.][k+1] after point k
-    __shared__ double s_t[4][2][6][32];    // terms of the round (double buffered): m2 x3, c01, c02, c12
-    double(*xs)[32] = s_x[warp];
-    double *rs = s_r[warp];
-    double(*mus)[33] = s_mu[warp];
+    // point-major layouts: in phase A the chain lanes 0-2 (accumulator lanes 0-5) read consecutive banks and
+    // every other lane reads the same word as its neighbour (broadcast): no bank conflicts on the paced path
+    __shared__ double2 s_x[4][32][3];      // per point, per dimension: {x, x * rl}
+    __shared__ double2 s_r[4][32];         // 1 / count as an unevaluated sum {rh, rl} (~106 bits)
+    __shared__ double s_mu[4][33][3];      // means: [0][.] before the round's first point, [k+1][.] after point k
+    __shared__ double s_t[4][2][32][6];    // terms of the round (double buffered): m2 x3, c01, c02, c12
+    double2(*xs)[3] = s_x[warp];
+    double2 *rs = s_r[warp];
+    double(*mus)[3] = s_mu[warp];
 
     const int cl = lane < 3 ? lane : 2;    // chain lane -> dimension
     const int al = lane < 6 ? lane : 5;    // accumulator lane -> term
     double mu = 0.0, acc = 0.0;
-    if (lane < 3) mus[lane][0] = 0.0;
+    if (lane < 3) mus[0][lane] = 0.0;
     const unsigned n = en - st;
     int prev_m = 0, buf = 0;
+    bool prev_chk = false;                 // previous round produced a non-finite term: add with the NaN rule
+    T nx0 = 0, nx1 = 0, nx2 = 0;           // the next round's point of this lane, fetched one round ahead
+#ifdef NDT_PROFILE_STATS
+    long long tL = 0, tA = 0, tB = 0, tS = clock64();
+#endif
     for (unsigned base = 0; base < n; base += 32) {
+#ifdef NDT_PROFILE_STATS
+        long long c0 = clock64();
+#endif
         const int m = (int)(n - base < 32u ? n - base : 32u);
-        double x0 = 0, x1 = 0, x2 = 0;
+        double x0 = 0, x1 = 0, x2 = 0, c = 1.0, rh = 1.0, rl = 0.0;
+        if (base == 0 && lane < m) { nx0 = p[lane * 3 + 0]; nx1 = p[lane * 3 + 1]; nx2 = p[lane * 3 + 2]; }
         if (lane < m) {
-            x0 = (double)p[(size_t)(base + lane) * 3 + 0];
-            x1 = (double)p[(size_t)(base + lane) * 3 + 1];
-            x2 = (double)p[(size_t)(base + lane) * 3 + 2];
-            xs[0][lane] = x0; xs[1][lane] = x1; xs[2][lane] = x2;
-            rs[lane] = 1.0 / (double)(base + lane + 1);
+            x0 = (double)nx0; x1 = (double)nx1; x2 = (double)nx2;
+            c = (double)(base + lane + 1);
+            rh = 1.0 / c;
+            rl = fma(-c, rh, 1.0) * rh;
+            rs[lane] = make_double2(rh, rl);
+            xs[lane][0] = make_double2(x0, x0 * rl);
+            xs[lane][1] = make_double2(x1, x1 * rl);
+            xs[lane][2] = make_double2(x2, x2 * rl);
+        }
+        if (base + 32 + lane < n) {          // issue the next round's global loads now; they land during phase A
+            const T *pn = p + (size_t)(base + 32 + lane) * 3;
+            nx0 = pn[0]; nx1 = pn[1]; nx2 = pn[2];
         }
         __syncwarp();
-        // ---- A (this round's means) fused with C (previous round's running sums)
-        const double(*tp)[32] = s_t[warp][buf ^ 1];
-#pragma unroll 4
-        for (int k = 0; k < m; k++) {
-            const double x = xs[cl][k];
-            const double r = rs[k];
-            const double cnt = (double)(base + k + 1);
-            mu = mu + div_by_count(x - mu, cnt, r);
-            if (lane < 3) mus[lane][k + 1] = mu;
-            if (k < prev_m) {
-                acc += tp[al][k];
-                if (lane >= 3 && isnan(acc)) acc = 0.0;
+        // ---- A (this round's means) fused with C (previous round's running sums).  Per point the warp
+        //      issues only the dependency chain {d, t} -> q -> mu, one store and one add:
+        //      q = RN(d / count) is fma(d, rh, t) with t = (x - mu) * rl formed as fma(-mu, rl, x * rl) so that
+        //      it does not wait for d (see div_by_count for why the quotient is exact; the cancellation in t is
+        //      harmless while |d| >= 2^-22 |x|).  Whether every operand of the round was inside the proven
+        //      range is checked afterwards, in parallel, by phase B; if not, the round is redone with the IEEE
+        //      division.
+        const double(*tp)[6] = s_t[warp][buf ^ 1];
+        const double mu_start = mu;
+#ifdef NDT_PROFILE_STATS
+        long long c1 = clock64(); tL += c1 - c0;
+#endif
+        if (!prev_chk && m == 32 && prev_m == 32) {
+            // full rounds (all but the first and last of a voxel): straight-line, no per-step predicates,
+            // operands of the next four points are fetched while the current four are on the chain
+            double2 xv[4], rv[4], xn[4], rn[4];
+            double tv[4], tn[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { xv[j] = xs[j][cl]; rv[j] = rs[j]; tv[j] = tp[j][al]; }
+#pragma unroll
+            for (int k0 = 0; k0 < 32; k0 += 4) {
+                if (k0 + 4 < 32) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { xn[j] = xs[k0 + 4 + j][cl]; rn[j] = rs[k0 + 4 + j]; tn[j] = tp[k0 + 4 + j][al]; }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const double d = xv[j].x - mu;
+                    const double t = fma(-mu, rv[j].y, xv[j].y);
+                    mu = mu + fma(d, rv[j].x, t);
+                    if (lane < 3) mus[k0 + j + 1][lane] = mu;
+                    acc += tv[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) { xv[j] = xn[j]; rv[j] = rn[j]; tv[j] = tn[j]; }
+            }
+        } else if (!prev_chk) {
+            for (int k0 = 0; k0 < m; k0 += 4) {
+                double2 xv[4], rv[4];
+                double tv[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { const int k = (k0 + j) & 31; xv[j] = xs[k][cl]; rv[j] = rs[k]; tv[j] = tp[k][al]; }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int k = k0 + j;
+                    if (k < m) {
+                        const double d = xv[j].x - mu;
+                        const double t = fma(-mu, rv[j].y, xv[j].y);
+                        mu = mu + fma(d, rv[j].x, t);
+                        if (lane < 3) mus[k + 1][lane] = mu;
+                    }
+                    if (k < prev_m) acc += tv[j];
+                }
+            }
+            for (int k = (m + 3) & ~3; k < prev_m; k++) acc += tp[k][al];   // last round shorter than the one before
+        } else {
+            for (int k = 0; k < m; k++) {
+                const double d = xs[k][cl].x - mu;
+                mu = mu + fma(d, rs[k].x, fma(-mu, rs[k].y, xs[k][cl].y));
+                if (lane < 3) mus[k + 1][lane] = mu;
+            }
+            for (int k = 0; k < prev_m; k++) {
+                const double a2 = acc + tp[k][al];
+                acc = (lane >= 3 && a2 != a2) ? 0.0 : a2;                   // NaN -> 0 (normal_distributions.c:98-100)
             }
         }
-        for (int k = m; k < prev_m; k++) {           // only when the previous round was longer: never (rounds shrink last)
-            acc += tp[al][k];
-            if (lane >= 3 && isnan(acc)) acc = 0.0;
+        __syncwarp();
+#ifdef NDT_PROFILE_STATS
+        long long c2 = clock64(); tA += c2 - c1;
+#endif
+        // ---- B: per-point terms, all lanes in parallel; also validates the operands of the round
+        bool redone = false;
+        while (true) {
+            bool bad = false, nonfinite = false;
+            if (lane < m) {
+                const double o0 = mus[lane][0], o1 = mus[lane][1], o2 = mus[lane][2];
+                const double n0 = mus[lane + 1][0], n1 = mus[lane + 1][1], n2 = mus[lane + 1][2];
+                const double d0 = x0 - o0, d1 = x1 - o1, d2 = x2 - o2;          // the chain's d, bit for bit
+                const double a0 = fabs(d0), a1 = fabs(d1), a2 = fabs(d2);
+                bad = !(a0 > 1e-250 && a0 < 1e290 && a0 * 4194304.0 >= fabs(x0)) ||
+                      !(a1 > 1e-250 && a1 < 1e290 && a1 * 4194304.0 >= fabs(x1)) ||
+                      !(a2 > 1e-250 && a2 < 1e290 && a2 * 4194304.0 >= fabs(x2));
+                double(*t)[6] = s_t[warp][buf];
+                const double e0 = x0 - n0, e1 = x1 - n1;
+                const double t0 = d0 * e0, t1 = d1 * e1, t2 = d2 * (x2 - n2);
+                // (x_j - new_j)(x_k - old_k) / count: mu_k (k > j) is not yet updated when dimension j runs
+                const double p01 = e0 * d1, p02 = e0 * d2, p12 = e1 * d2;
+                double q01 = fma(p01, rh, p01 * rl), q02 = fma(p02, rh, p02 * rl), q12 = fma(p12, rh, p12 * rl);
+                {
+                    const double b0 = fabs(p01), b1 = fabs(p02), b2 = fabs(p12);
+                    const bool ok = b0 > 1e-250 && b0 < 1e290 && b1 > 1e-250 && b1 < 1e290 && b2 > 1e-250 && b2 < 1e290;
+                    if (!ok) { q01 = p01 / c; q02 = p02 / c; q12 = p12 / c; }     // zeros, tiny or huge products: IEEE division
+                }
+                t[lane][0] = t0; t[lane][1] = t1; t[lane][2] = t2; t[lane][3] = q01; t[lane][4] = q02; t[lane][5] = q12;
+                const double big = 1.7976931348623157e308;
+                nonfinite = !(fabs(t0) <= big && fabs(t1) <= big && fabs(t2) <= big && fabs(q01) <= big && fabs(q02) <= big && fabs(q12) <= big);
+            }
+            prev_chk = __any_sync(0xffffffffu, nonfinite);
+            if (redone || !__any_sync(0xffffffffu, bad)) break;
+            // rare: redo this round's means with the IEEE division, then its terms
+            mu = mu_start;
+            for (int k = 0; k < m; k++) {
+                const double cnt = (double)(base + k + 1);
+                mu = mu + (xs[k][cl].x - mu) / cnt;
+                if (lane < 3) mus[k + 1][lane] = mu;
+            }
+            redone = true;
+            __syncwarp();
         }
         __syncwarp();
-        // ---- B: per-point terms
-        if (lane < m) {
-            const double o0 = mus[0][lane], o1 = mus[1][lane], o2 = mus[2][lane];
-            const double n0 = mus[0][lane + 1], n1 = mus[1][lane + 1], n2 = mus[2][lane + 1];
-            const double cnt = (double)(base + lane + 1);
-            double(*t)[32] = s_t[warp][buf];
-            t[0][lane] = (x0 - o0) * (x0 - n0);
-            t[1][lane] = (x1 - o1) * (x1 - n1);
-            t[2][lane] = (x2 - o2) * (x2 - n2);
-            t[3][lane] = (x0 - n0) * (x1 - o1) / cnt;   // mu_1, mu_2 not yet updated when j = 0 runs
-            t[4][lane] = (x0 - n0) * (x2 - o2) / cnt;
-            t[5][lane] = (x1 - n1) * (x2 - o2) / cnt;   // mu_2 not yet updated when j = 1 runs
-        }
-        __syncwarp();
-        if (lane < 3) mus[lane][0] = mus[lane][m];
+        if (lane < 3) mus[0][lane] = mus[m][lane];
         prev_m = m; buf ^= 1;
         __syncwarp();
+#ifdef NDT_PROFILE_STATS
+        tB += clock64() - c2;
+#endif
     }
+#ifdef NDT_PROFILE_STATS
+    if (lane == 0 && n > 6000 && b < 2) printf("stats b %d idx %u n %u rounds %u: load %lld A %lld B %lld total %lld cycles (start %lld)\n", b, idx, n, (n + 31) / 32, tL, tA, tB, clock64() - tS, tS);
+#endif
     {   // C for the last round
-        const double(*tp)[32] = s_t[warp][buf ^ 1];
+        const double(*tp)[6] = s_t[warp][buf ^ 1];
         for (int k = 0; k < prev_m; k++) {
-            acc += tp[al][k];
-            if (lane >= 3 && isnan(acc)) acc = 0.0;
+            const double a2 = acc + tp[k][al];
+            acc = (lane >= 3 && a2 != a2) ? 0.0 : a2;
         }
     }
     // variances m2 / n (normal_distributions.c:86-89), NaN -> 0
@@ -938,7 +1042,7 @@ __global__ void k_selftest_div(long n, unsigned seed, unsigned long long *mismat
         unsigned long long h2 = h * 0xD6E8FEB86659FD93ull; h2 ^= h2 >> 32;
         const unsigned c = (mode & 1) ? (unsigned)(h2 % 120000u) + 1u : (unsigned)(h2 % 67000000u) + 1u;
         const double cnt = (double)c;
-        const double want = d / cnt, got = div_by_count(d, cnt, 1.0 / cnt);
+        const double want = d / cnt, got = div_by_count(d, cnt);
         if (__double_as_longlong(want) != __double_as_longlong(got)) bad++;
     }
     if (bad) atomicAdd(mismatches, bad);
