@@ -39,6 +39,20 @@ STAGES = ["limits", "search", "rank", "offsets", "scatter", "stats", "kl", "sele
 ALGO_BYTES_PER_CLOUD = N_POINTS * 12 + N_POINTS * 2 + N_NDS * 48 + N_NDS * 2     # SURVEY.md §8(d), with labels
 
 
+def ncu_traffic(kernel: str, batch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu capture
+    (profiles/traffic.json, written by tools/summarize_ncu.py); None when there is no capture for this batch."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    e = t.get(kernel)
+    if not e or e.get("batch") != batch:
+        return None
+    return e["dram_bytes_per_launch"]
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -175,7 +189,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     B = args.batch
-    n_sets = 3                                  # rotate inputs: 3 x B x 1.68 MB > 126 MB L2 for B >= 32
+    n_sets = 2 if B >= 128 else 3               # rotate inputs: n_sets x B x 1.68 MB > 126 MB L2 for B >= 32
     host_pts, host_lab, dev_pts, dev_lab = [], [], [], []
     for s in range(n_sets):
         p, l = make_scans(B, seed0=rank * 100_000 + s * B)
@@ -189,9 +203,10 @@ def run_ours(args):
     out_host = torch.empty((B, N_NDS, N_CLASSES + 1), dtype=torch.float32).pin_memory()
     stream = torch.cuda.current_stream(dev)
 
+    model.set_pipeline(args.lanes, args.chunk)
+
     def step_device(i):
-        out = eng.downsample(dev_pts[i % n_sets], N_NDS, dev_lab[i % n_sets], N_CLASSES, nan_to_num=True, want_info=False)
-        return model(out.feat)
+        return model.infer_device(dev_pts[i % n_sets], N_NDS, dev_lab[i % n_sets], N_CLASSES)
 
     def step_host(i):
         return model.infer_host(host_pts[i % n_sets], N_NDS, host_lab[i % n_sets], N_CLASSES, out_host)
@@ -273,6 +288,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64 (NDT) + bf16/f32-accumulate (network)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "clouds_per_gpu_per_step": B, "points": N_POINTS, "n_desired_nds": N_NDS,
                    "parallelism": f"scans sharded over {world} GPU(s), no forward collective",
+                   "pipeline": f"{args.lanes} lanes x chunks of {args.chunk} scans",
                    "l2": f"inputs rotate over {n_sets} resident batches ({n_sets * B * ALGO_BYTES_PER_CLOUD / 1e6:.0f} MB vs 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": "clouds/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": B * N_POINTS * 14, "d2h_bytes_per_step": B * N_NDS * (N_CLASSES + 1) * 4},
@@ -281,7 +297,8 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": {"limits": "k_limits", "search": "k_count (x5 launches that do work, of 15)",
                                                 "rank": "k_rank", "offsets": "k_offsets", "scatter": "k_scatter", "stats": "k_stats",
                                                 "kl": "k_kl", "select": "k_select"}[dom],
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic({"search": "k_count"}.get(dom, "k_" + dom), B),
                      "peak_source": peak_src, "stage_ms_per_step": stage_ms},
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -301,7 +318,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="scans per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="scans per GPU per step")
+    ap.add_argument("--lanes", type=int, default=4, help="pipeline lanes (internal streams) of the infer calls")
+    ap.add_argument("--chunk", type=int, default=32, help="scans per pipeline chunk")
     ap.add_argument("--cpu-clouds", type=int, default=48, help="scans in the cpu_baseline sample")
     ap.add_argument("--ref-clouds", type=int, default=8, help="scans per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -170,6 +170,15 @@ int ndnet_b200_model_forward(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const
 int ndnet_b200_infer_host(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const void *points, int dtype,
                           const uint16_t *labels, int B, long N, int num_classes, long num_desired, float *out_host,
                           long out_elems_per_cloud, void *stream);
+/* Same with DEVICE buffers in and out, asynchronous (the caller's stream waits for the result). */
+int ndnet_b200_infer_device(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const void *points, int dtype,
+                            const uint16_t *labels, int B, long N, int num_classes, long num_desired, float *out_dev,
+                            long out_elems_per_cloud, void *stream);
+/* Both infer calls cut the batch into chunks of at most `chunk` scans and run the chunks round-robin on `lanes`
+ * internal streams (each with its own workspace), so that host<->device copies overlap kernels and the
+ * latency-bound tail of one chunk (the sequential per-voxel statistics) overlaps the bulk work of another.
+ * Defaults: 2 lanes, 64 scans.  The lane count is fixed at the first infer call. */
+int ndnet_b200_set_pipeline(ndnet_b200_ctx *ctx, int lanes, int chunk);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,22 @@ struct ndnet_b200_ctx {
     NdtCloudInfo *d_info = nullptr; size_t d_info_bytes = 0;
     float *d_logits = nullptr; size_t d_logits_bytes = 0;
     mlp::Scratch mlp_scratch;
+    // pipeline lanes of ndnet_b200_infer_{host,device}: chunks of the batch run on separate streams so that
+    // copies overlap kernels and the latency-bound tail of one chunk overlaps the bulk work of another
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        Workspace ws;
+        mlp::Scratch scratch;
+        void *d_points = nullptr; size_t d_points_bytes = 0;
+        uint16_t *d_labels = nullptr; size_t d_labels_bytes = 0;
+        float *d_feat = nullptr; size_t d_feat_bytes = 0;
+        float *d_logits = nullptr; size_t d_logits_bytes = 0;
+    };
+    std::vector<Lane> lanes;
+    int n_lanes = 2;
+    int chunk = 64;
+    cudaEvent_t start_ev = nullptr;
 };
 
 namespace {
@@ -147,6 +163,14 @@ extern "C" void ndnet_b200_destroy(ndnet_b200_ctx *c) {
     c->mlp_scratch.release();
     void *ptrs[] = {c->d_points, c->d_labels, c->d_feat, c->d_feat64, c->d_olab, c->d_ovox, c->d_info, c->d_logits};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &l : c->lanes) {
+        l.ws.release(); l.scratch.release();
+        void *lp[] = {l.d_points, l.d_labels, l.d_feat, l.d_logits};
+        for (void *p : lp) if (p) cudaFree(p);
+        if (l.done) cudaEventDestroy(l.done);
+        if (l.stream) cudaStreamDestroy(l.stream);
+    }
+    if (c->start_ev) cudaEventDestroy(c->start_ev);
     delete c;
 }
 
@@ -234,32 +258,85 @@ extern "C" int ndnet_b200_downsample_batch_host(ndnet_b200_ctx *c, const void *p
     return 0;
 }
 
+// ---- pipelined whole-path inference ------------------------------------------------------------
+extern "C" int ndnet_b200_set_pipeline(ndnet_b200_ctx *c, int lanes, int chunk) {
+    if (!c || lanes < 1 || lanes > 8 || chunk < 1) return -200;
+    if (!c->lanes.empty() && (int)c->lanes.size() != lanes) return -203;   // lanes are fixed once created
+    c->n_lanes = lanes; c->chunk = chunk;
+    return 0;
+}
+
+static int infer_pipelined(ndnet_b200_ctx *c, ndnet_b200_model *model, const void *points, int dtype, const uint16_t *labels,
+                           int B, long N, int num_classes, long D, float *out, long out_elems_per_cloud, cudaStream_t user,
+                           bool host_io) {
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, e, "cudaSetDevice");
+    if (c->lanes.empty()) {
+        c->lanes.resize(c->n_lanes);
+        for (auto &l : c->lanes) {
+            if ((e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(c, e, "stream create");
+            if ((e = cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming)) != cudaSuccess) return fail(c, e, "event create");
+        }
+        if ((e = cudaEventCreateWithFlags(&c->start_ev, cudaEventDisableTiming)) != cudaSuccess) return fail(c, e, "event create");
+    }
+    const size_t esz = dtype == 0 ? 4 : 8;
+    // everything already enqueued on the caller's stream happens before the lanes start
+    if ((e = cudaEventRecord(c->start_ev, user)) != cudaSuccess) return fail(c, e, "event record");
+    const int L = (int)c->lanes.size();
+    // chunk size: at most c->chunk, but spread a small batch over all lanes
+    int chunk = c->chunk;
+    if ((B + L - 1) / L < chunk) chunk = (B + L - 1) / L;
+    int lane_i = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk, lane_i = (lane_i + 1) % L) {
+        const int nb = B - b0 < chunk ? B - b0 : chunk;
+        ndnet_b200_ctx::Lane &l = c->lanes[lane_i];
+        if ((e = cudaStreamWaitEvent(l.stream, c->start_ev, 0)) != cudaSuccess) return fail(c, e, "stream wait");
+        const char *psrc = (const char *)points + (size_t)b0 * N * 3 * esz;
+        const uint16_t *lsrc = labels ? labels + (size_t)b0 * N : nullptr;
+        float *odst = out + (size_t)b0 * out_elems_per_cloud;
+        const void *dp = psrc; const uint16_t *dl = lsrc; float *dout = odst;
+        if ((e = grow(l.d_feat, l.d_feat_bytes, (size_t)nb * D * 12 * 4)) != cudaSuccess) return fail(c, e, "lane allocation");
+        if (host_io) {
+            if ((e = grow(l.d_points, l.d_points_bytes, (size_t)nb * N * 3 * esz)) != cudaSuccess) return fail(c, e, "lane allocation");
+            if (labels && (e = grow(l.d_labels, l.d_labels_bytes, (size_t)nb * N * 2)) != cudaSuccess) return fail(c, e, "lane allocation");
+            if ((e = grow(l.d_logits, l.d_logits_bytes, (size_t)nb * out_elems_per_cloud * 4)) != cudaSuccess) return fail(c, e, "lane allocation");
+            if ((e = cudaMemcpyAsync(l.d_points, psrc, (size_t)nb * N * 3 * esz, cudaMemcpyHostToDevice, l.stream)) != cudaSuccess) return fail(c, e, "H2D points");
+            if (labels && (e = cudaMemcpyAsync(l.d_labels, lsrc, (size_t)nb * N * 2, cudaMemcpyHostToDevice, l.stream)) != cudaSuccess) return fail(c, e, "H2D labels");
+            dp = l.d_points; dl = labels ? l.d_labels : nullptr; dout = l.d_logits;
+        }
+        if ((e = l.ws.reserve(nb, N, D, num_classes + 1)) != cudaSuccess) return fail(c, e, "lane workspace allocation");
+        l.ws.last_B = nb; l.ws.last_N = N; l.ws.last_D = D;
+        if ((e = ndt::run_batch(l.ws, dp, dtype, dl, nb, N, num_classes, D, NDNET_B200_NAN_TO_NUM, l.d_feat, nullptr, nullptr, nullptr,
+                                nullptr, l.stream)) != cudaSuccess) return fail(c, e, "ndt::run_batch");
+        std::string err;
+        int r = model->m.forward(l.scratch, l.d_feat, nb, (int)D, dout, l.stream, err);
+        if (r != 0) { c->err = err; fprintf(stderr, "ndnet_b200_infer: %s\n", err.c_str()); return r; }
+        if (host_io && (e = cudaMemcpyAsync(odst, l.d_logits, (size_t)nb * out_elems_per_cloud * 4, cudaMemcpyDeviceToHost, l.stream)) != cudaSuccess)
+            return fail(c, e, "D2H");
+    }
+    for (auto &l : c->lanes) {
+        if ((e = cudaEventRecord(l.done, l.stream)) != cudaSuccess) return fail(c, e, "event record");
+        if ((e = cudaStreamWaitEvent(user, l.done, 0)) != cudaSuccess) return fail(c, e, "stream wait");
+    }
+    if (host_io && (e = cudaStreamSynchronize(user)) != cudaSuccess) return fail(c, e, "stream synchronise");
+    return 0;
+}
+
 // One call for the whole hot path from HOST buffers: H2D of the scans, NDT, network forward, D2H of the
 // per-distribution log-probabilities (segmentation) or class probabilities (classification), synchronise.
 extern "C" int ndnet_b200_infer_host(ndnet_b200_ctx *c, ndnet_b200_model *model, const void *points, int dtype,
                                      const uint16_t *labels, int B, long N, int num_classes, long D, float *out_host,
                                      long out_elems_per_cloud, void *stream) {
     if (!c || !model || !points || !out_host || B <= 0 || N < 0 || D <= 0 || (dtype != 0 && dtype != 1)) return -200;
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaSetDevice(c->device);
-    if (e != cudaSuccess) return fail(c, e, "cudaSetDevice");
-    const size_t esz = dtype == 0 ? 4 : 8;
-    const size_t pbytes = (size_t)B * N * 3 * esz, obytes = (size_t)B * out_elems_per_cloud * 4;
-    if ((e = grow(c->d_points, c->d_points_bytes, pbytes)) != cudaSuccess) return fail(c, e, "staging allocation");
-    if (labels && (e = grow(c->d_labels, c->d_labels_bytes, (size_t)B * N * 2)) != cudaSuccess) return fail(c, e, "staging allocation");
-    if ((e = grow(c->d_feat, c->d_feat_bytes, (size_t)B * D * 12 * 4)) != cudaSuccess) return fail(c, e, "staging allocation");
-    if ((e = grow(c->d_logits, c->d_logits_bytes, obytes)) != cudaSuccess) return fail(c, e, "staging allocation");
-    if ((e = cudaMemcpyAsync(c->d_points, points, pbytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(c, e, "H2D points");
-    if (labels && (e = cudaMemcpyAsync(c->d_labels, labels, (size_t)B * N * 2, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-        return fail(c, e, "H2D labels");
-    int r = ndnet_b200_downsample_batch(c, c->d_points, dtype, labels ? c->d_labels : nullptr, B, N, num_classes, D,
-                                        NDNET_B200_NAN_TO_NUM, c->d_feat, nullptr, nullptr, nullptr, nullptr, stream);
-    if (r != 0) return r;
-    r = ndnet_b200_model_forward(c, model, c->d_feat, B, (int)D, c->d_logits, stream);
-    if (r != 0) return r;
-    if ((e = cudaMemcpyAsync(out_host, c->d_logits, obytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(c, e, "D2H");
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(c, e, "stream synchronise");
-    return 0;
+    return infer_pipelined(c, model, points, dtype, labels, B, N, num_classes, D, out_host, out_elems_per_cloud, (cudaStream_t)stream, true);
+}
+
+// Same from/to DEVICE buffers; asynchronous: on return the caller's stream waits for the result.
+extern "C" int ndnet_b200_infer_device(ndnet_b200_ctx *c, ndnet_b200_model *model, const void *points, int dtype,
+                                       const uint16_t *labels, int B, long N, int num_classes, long D, float *out_dev,
+                                       long out_elems_per_cloud, void *stream) {
+    if (!c || !model || !points || !out_dev || B <= 0 || N < 0 || D <= 0 || (dtype != 0 && dtype != 1)) return -200;
+    return infer_pipelined(c, model, points, dtype, labels, B, N, num_classes, D, out_dev, out_elems_per_cloud, (cudaStream_t)stream, false);
 }
 
 extern "C" int ndnet_b200_last_point_voxels(ndnet_b200_ctx *c, int32_t *out_dev, void *stream) {

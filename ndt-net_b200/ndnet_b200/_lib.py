@@ -70,6 +70,10 @@ def lib() -> C.CDLL:
     L.ndnet_b200_model_forward.argtypes = [vp, vp, vp, i, i, vp, vp]
     L.ndnet_b200_infer_host.restype = i
     L.ndnet_b200_infer_host.argtypes = [vp, vp, vp, i, vp, i, l, i, l, vp, l, vp]
+    L.ndnet_b200_infer_device.restype = i
+    L.ndnet_b200_infer_device.argtypes = [vp, vp, vp, i, vp, i, l, i, l, vp, l, vp]
+    L.ndnet_b200_set_pipeline.restype = i
+    L.ndnet_b200_set_pipeline.argtypes = [vp, i, i]
     _lib = L
     return L
 
@@ -80,5 +84,5 @@ EXPORTED = [
     "ndnet_b200_downsample_batch", "ndnet_b200_downsample_batch_host", "ndnet_b200_last_point_voxels",
     "ndnet_b200_last_kl_list", "ndnet_b200_selftest_div", "ndnet_b200_launch_count", "ndnet_b200_stage_timing", "ndnet_b200_stage_times",
     "ndnet_b200_model_create", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
-    "ndnet_b200_infer_host",
+    "ndnet_b200_infer_host", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline",
 ]

@@ -111,6 +111,33 @@ class B200Model:
         return out
 
 
+    def infer_device(self, points: torch.Tensor, num_desired: int, labels: torch.Tensor | None = None,
+                     num_classes: int = 0) -> torch.Tensor:
+        """CUDA tensors in, CUDA tensor out, asynchronous on the current stream (chunks pipelined on internal lanes)."""
+        assert points.is_cuda and points.is_contiguous()
+        B, N, _ = points.shape
+        D = int(num_desired)
+        if self.kind == KIND_SEG:
+            out = torch.empty((B, D, self.n_out), dtype=torch.float32, device=points.device)
+        else:
+            out = torch.empty((B, self.n_out), dtype=torch.float32, device=points.device)
+        stream = torch.cuda.current_stream(points.device).cuda_stream
+        with torch.cuda.device(points.device):
+            rc = self._L.ndnet_b200_infer_device(
+                self.engine.handle, self._h, points.data_ptr(), _lib.F32 if points.dtype == torch.float32 else _lib.F64,
+                labels.data_ptr() if labels is not None else None, B, N, int(num_classes), D, out.data_ptr(),
+                out.numel() // B, stream)
+        if rc != 0:
+            raise RuntimeError(f"ndnet_b200_infer_device failed ({rc}): "
+                               f"{self._L.ndnet_b200_last_error(self.engine.handle).decode()}")
+        return out.unsqueeze(-1) if self.kind == KIND_CLS else out
+
+    def set_pipeline(self, lanes: int, chunk: int) -> None:
+        rc = self._L.ndnet_b200_set_pipeline(self.engine.handle, int(lanes), int(chunk))
+        if rc != 0:
+            raise RuntimeError(f"ndnet_b200_set_pipeline failed ({rc})")
+
+
 def smoke_forward(engine, feat: torch.Tensor) -> None:
     """Tiny forward of the segmentation network on the features smoke() just produced, vs torch fp32."""
     from ndnet.models.ndtnet import NDTNetSegmentation

@@ -91,3 +91,25 @@ def test_end_to_end_ndt_then_network():
         ref, got = net(means, covs), net.forward_b200(means, covs)
     agree = (got.argmax(-1) == ref.argmax(-1)).float().mean().item()
     assert torch.isfinite(got).all() and agree >= 0.9, agree
+
+
+def test_pipelined_inference_equals_single_stream_calls():
+    """ndnet_b200_infer_device / _host (chunks on internal lanes, copies overlapped) give exactly what the
+    single-stream downsample_batch + model_forward sequence gives."""
+    from ndnet_b200.engine import default_engine
+    from ndnet_b200.synth import lidar_batch
+    net = _seg()
+    pts, lab = lidar_batch(7, 20000, seed0=900, with_labels=True)
+    tp, tl = torch.from_numpy(pts).cuda(), torch.from_numpy(lab.astype(np.int16)).cuda()
+    with torch.no_grad():
+        net.forward_b200(torch.zeros(1, 8, 3).cuda(), torch.zeros(1, 8, 9).cuda())      # builds net._b200_model
+    m = net._b200_model
+    m.set_pipeline(2, 3)
+    eng = default_engine(0)
+    feat = eng.downsample(tp, 300, tl, 28, nan_to_num=True, want_info=False).feat
+    ref = m(feat)
+    got_dev = m.infer_device(tp, 300, tl, 28)
+    out_host = torch.empty((7, 300, 29), dtype=torch.float32).pin_memory()
+    got_host = m.infer_host(torch.from_numpy(pts).pin_memory(), 300, torch.from_numpy(lab.astype(np.int16)).pin_memory(), 28, out_host)
+    torch.cuda.synchronize()
+    assert torch.equal(ref, got_dev) and torch.equal(ref.cpu(), got_host)
