@@ -131,7 +131,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 constexpr int kGemmThreads = 192;   // warps 0-3 epilogue, warp 4 TMA producer, warp 5 TMEM alloc + MMA issue
 
 template <int BN, int STAGES>
-constexpr size_t gemm_smem_bytes() { return (size_t)STAGES * (128 + BN) * 128 + 1024 /*align*/ + 256 /*barriers*/; }
+constexpr size_t gemm_smem_bytes() { return (size_t)STAGES * (128 + BN) * 128 + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias tile*/; }
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads)
@@ -143,6 +143,7 @@ k_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtenso
     uint64_t *bars = (uint64_t *)(sB + (size_t)STAGES * BN * 128);
     uint64_t *full = bars, *empty = bars + STAGES, *tmem_full = bars + 2 * STAGES;
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 1);
+    float *s_bias = (float *)(bars + 2 * STAGES + 2);   // BN floats: bias (+ per-cloud bias) of this tile's columns
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.z;
@@ -159,6 +160,15 @@ k_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtenso
         ptx::fence_barrier_init();
     }
     if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&mapA); ptx::prefetch_tmap(&mapB); }
+    if (args.mode == MODE_ROWS && threadIdx.x < 128) {
+        const float *cb = args.cbias ? args.cbias + (size_t)b * args.ldcb : nullptr;
+        for (int i = threadIdx.x; i < BN; i += 128) {
+            const int n = b_row0 + i;
+            float v = 0.f;
+            if (n < args.n_valid) { if (args.bias) v += args.bias[n]; if (cb) v += cb[n]; }
+            s_bias[i] = v;
+        }
+    }
     if (warp == 5) ptx::tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
     ptx::tc_fence_before();
     __syncthreads();
@@ -221,7 +231,6 @@ k_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtenso
             const int row = a_row0 + m;
             const bool row_ok = row < args.P;
             __nv_bfloat16 *orow = args.out + ((size_t)b * args.P + (row_ok ? row : 0)) * args.ldo + b_row0;
-            const float *cb = args.cbias ? args.cbias + (size_t)b * args.ldcb : nullptr;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
@@ -231,9 +240,9 @@ k_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtenso
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     const int n = b_row0 + c0 + j;
-                    float x0 = __uint_as_float(v[j]), x1 = __uint_as_float(v[j + 1]);
-                    if (n < args.n_valid) { if (args.bias) x0 += args.bias[n]; if (cb) x0 += cb[n]; } else x0 = 0.f;
-                    if (n + 1 < args.n_valid) { if (args.bias) x1 += args.bias[n + 1]; if (cb) x1 += cb[n + 1]; } else x1 = 0.f;
+                    float x0 = __uint_as_float(v[j]) + s_bias[c0 + j], x1 = __uint_as_float(v[j + 1]) + s_bias[c0 + j + 1];
+                    if (n >= args.n_valid) x0 = 0.f;
+                    if (n + 1 >= args.n_valid) x1 = 0.f;
                     if (args.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
                     __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
                     packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
