@@ -99,6 +99,11 @@ def make_scans(batch: int, seed0: int):
     return pts, lab
 
 
+def ndist_seed(rank, batch, set_index):
+    from ndnet_b200.dist import scan_seeds
+    return scan_seeds(rank, batch, set_index)[0]
+
+
 def build_network(device):
     from ndnet.models.ndtnet import NDTNetSegmentation
     from ndnet_b200.model import deterministic_state_dict
@@ -192,7 +197,7 @@ def run_ours(args):
     n_sets = 2 if B >= 128 else 3               # rotate inputs: n_sets x B x 1.68 MB > 126 MB L2 for B >= 32
     host_pts, host_lab, dev_pts, dev_lab = [], [], [], []
     for s in range(n_sets):
-        p, l = make_scans(B, seed0=rank * 100_000 + s * B)
+        p, l = make_scans(B, seed0=ndist_seed(rank, B, s))
         hp = torch.from_numpy(p).pin_memory()
         hl = torch.from_numpy(l.astype(np.int16)).pin_memory()
         host_pts.append(hp); host_lab.append(hl)
@@ -211,18 +216,15 @@ def run_ours(args):
     def step_host(i):
         return model.infer_host(host_pts[i % n_sets], N_NDS, host_lab[i % n_sets], N_CLASSES, out_host)
 
+    from ndnet_b200 import dist as ndist
+
     def barrier():
         torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
+        ndist.barrier()
         torch.cuda.synchronize(dev)
 
     def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
+        return ndist.max_over_ranks(ms, dev)
 
     def timed(step_fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -238,6 +240,13 @@ def run_ours(args):
     chk = eng.downsample(dev_pts[0], N_NDS, dev_lab[0], N_CLASSES)
     assert np.all(chk.info["status"] == 0) and np.all(chk.info["num_out"] == N_NDS), "workload did not converge"
 
+    if args.profile_stage:
+        # for `ncu -k regex:<kernel>`: only full-batch single-stream launches of the NDT kernels and the network
+        for i in range(3):
+            f = eng.downsample(dev_pts[i % n_sets], N_NDS, dev_lab[i % n_sets], N_CLASSES, nan_to_num=True, want_info=False).feat
+            model(f)
+        torch.cuda.synchronize(dev)
+        return
     for i in range(args.warmup):
         step_device(i); step_host(i)
     sampler = ClockSampler(local)
@@ -324,6 +333,7 @@ def main():
     ap.add_argument("--cpu-clouds", type=int, default=48, help="scans in the cpu_baseline sample")
     ap.add_argument("--ref-clouds", type=int, default=8, help="scans per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-stage", action="store_true", help="only run 3 full-batch single-stream passes (ncu capture)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

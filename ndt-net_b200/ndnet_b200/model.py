@@ -151,5 +151,6 @@ def smoke_forward(engine, feat: torch.Tensor) -> None:
         got = net.forward_b200(f[:, :, :3], f[:, :, 3:])
     torch.cuda.synchronize()
     err = (got - ref).abs().max().item()
+    scale = max(1.0, ref.abs().max().item())
     agree = (got.argmax(-1) == ref.argmax(-1)).float().mean().item()
-    assert err < 0.25 and agree > 0.97, (err, agree)
+    assert err <= 2e-2 * scale and agree > 0.97, (err, scale, agree)   # bf16 operands: 2 % of the log-probability range
