@@ -126,6 +126,7 @@ int ndnet_b200_downsample_batch_host(ndnet_b200_ctx *ctx, const void *points, in
 
 /* Debug/inspection: copy per-point voxel ids of the last batch ([B,N] int32, -1 = never voxelised) to a
  * device buffer.  Used by the parity tests ("voxel ids and per-voxel membership bit-exact"). */
+int ndnet_b200_keep_point_voxels(ndnet_b200_ctx *ctx, int enable);   /* off by default (costs 4 B/point of HBM writes) */
 int ndnet_b200_last_point_voxels(ndnet_b200_ctx *ctx, int32_t *out_dev, void *stream);
 /* Debug/inspection: the pre-prune divergence list of cloud b of the last batch, in list order.
  * Host buffers of capacity `cap`; returns the number of entries or a negative error. */

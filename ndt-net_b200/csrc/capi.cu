@@ -80,10 +80,12 @@ static cudaError_t alloc(T *&p, size_t count) {
 }
 
 void Workspace::release() {
-    void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, vox_order, slot_rank, tile_cnt, hist, point_voxel, sorted,
+    const bool keep = keep_point_voxels;
+    void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, vox_order, slot_rank, tile_cnt, hist, point_voxel, sorted, sorted_labels,
                     mean, cov, cov_final, cls, kl_div, kl_flag, key, seq, firstpos, removed, list_div, list_seq};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = Workspace();
+    keep_point_voxels = keep;
 }
 
 cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
@@ -114,6 +116,7 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     A(tile_cnt, (size_t)nB * ntiles_cap * vcap);
     A(hist, (size_t)nB * vcap * (nbins > 0 ? nbins : 1));
     A(point_voxel, (size_t)nB * nN);
+    A(sorted_labels, (size_t)nB * nN);
     if ((e = cudaMalloc(&sorted, (size_t)nB * nN * 3 * sizeof(double) + 16)) != cudaSuccess) return e;
     A(mean, (size_t)nB * vcap * 3);
     A(cov, (size_t)nB * vcap * 9);
@@ -339,8 +342,15 @@ extern "C" int ndnet_b200_infer_device(ndnet_b200_ctx *c, ndnet_b200_model *mode
     return infer_pipelined(c, model, points, dtype, labels, B, N, num_classes, D, out_dev, out_elems_per_cloud, (cudaStream_t)stream, false);
 }
 
+extern "C" int ndnet_b200_keep_point_voxels(ndnet_b200_ctx *c, int enable) {
+    if (!c) return -200;
+    c->ws.keep_point_voxels = enable != 0;
+    return 0;
+}
+
 extern "C" int ndnet_b200_last_point_voxels(ndnet_b200_ctx *c, int32_t *out_dev, void *stream) {
     if (!c || !out_dev || c->ws.last_B == 0) return -200;
+    if (!c->ws.keep_point_voxels) { c->err = "enable ndnet_b200_keep_point_voxels before the batch"; return -204; }
     cudaError_t e = cudaMemcpyAsync(out_dev, c->ws.point_voxel, (size_t)c->ws.last_B * c->ws.last_N * 4,
                                     cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail(c, e, "last_point_voxels");

@@ -23,6 +23,7 @@ constexpr unsigned kSmemBitmapBits = 1u << 18; // grids up to this many cells ar
 constexpr int kCountPointsPerCta = 4096;
 constexpr int kRankTile = 2048;                // points per rank tile (one warp walks one tile in order)
 constexpr unsigned kDropped = 0xFFFFFFFFu;
+constexpr int kSmemLabelBins = 64;             // label sets up to this size are voted in shared memory by k_stats
 
 // Per-cloud search/grid state (device resident, one per cloud).
 struct CloudState {
@@ -79,6 +80,58 @@ __device__ __forceinline__ bool voxel_of(double x, double y, double z, const dou
     if (vx >= (unsigned)len[0] || vy >= (unsigned)len[1] || vz >= (unsigned)len[2]) return false;
     id = vz * (unsigned)len[0] * (unsigned)len[1] + vy * (unsigned)len[0] + vx;
     return true;
+}
+
+// Grid parameters of one pass, with fp32 copies for the prefilter below.
+struct GridCtx {
+    double off[3], vs, rv;
+    int len[3];
+    float off32[3], rv32;
+};
+
+__device__ __forceinline__ GridCtx make_grid_ctx(const CloudState &s) {
+    GridCtx g;
+    g.vs = s.guess; g.rv = 1.0 / s.guess; g.rv32 = (float)g.rv;
+#pragma unroll
+    for (int a = 0; a < 3; a++) { g.off[a] = s.off[a]; g.len[a] = s.len[a]; g.off32[a] = (float)s.off[a]; }
+    return g;
+}
+
+// fp32 prefilter for fp32 inputs: the offset is the minimum of fp32 values, hence itself an fp32 value, so
+// q32 = RN32(RN32(p - off) * RN32(1/vs)) differs from the reference's fp64 quotient by less than 2e-7 q.  When q32
+// is further than 4e-7 q from an integer the two have the same floor; otherwise (about 1e-5 of the points) the
+// exact fp64 path decides.  The floor itself is taken with the 2^23 magic-number add (FADD/integer pipes): the
+// conversion instructions (F2F/FRND/F2I) all issue on the quarter-rate XU pipe, which is what bounded k_count.
+__device__ __forceinline__ unsigned axis_cell32(float p, int a, const GridCtx &g) {
+    const float d = p - g.off32[a];
+    const float q = d * g.rv32;
+    if (q >= 0.0f && q < 4194304.0f) {
+        const float m = q + 8388608.0f;                       // RN(q) in the low mantissa bits
+        int ri = __float_as_int(m) - 0x4B000000;
+        float rf = m - 8388608.0f;
+        if (rf > q) { ri -= 1; rf -= 1.0f; }                  // nearest -> floor
+        const float t = q - rf;
+        const float eps = q * 4e-7f;
+        if (t > eps && (1.0f - t) > eps) return (unsigned)ri;
+    }
+    return axis_cell((double)p, g.off[a], g.vs, g.rv);
+}
+
+template <typename T>
+__device__ __forceinline__ bool point_cell(const T *__restrict__ p, long i, const GridCtx &g, unsigned &id);
+
+template <>
+__device__ __forceinline__ bool point_cell<float>(const float *__restrict__ p, long i, const GridCtx &g, unsigned &id) {
+    const float x = p[i * 3 + 0], y = p[i * 3 + 1], z = p[i * 3 + 2];
+    const unsigned vx = axis_cell32(x, 0, g), vy = axis_cell32(y, 1, g), vz = axis_cell32(z, 2, g);
+    if (vx >= (unsigned)g.len[0] || vy >= (unsigned)g.len[1] || vz >= (unsigned)g.len[2]) return false;
+    id = vz * (unsigned)g.len[0] * (unsigned)g.len[1] + vy * (unsigned)g.len[0] + vx;
+    return true;
+}
+
+template <>
+__device__ __forceinline__ bool point_cell<double>(const double *__restrict__ p, long i, const GridCtx &g, unsigned &id) {
+    return voxel_of(p[i * 3 + 0], p[i * 3 + 1], p[i * 3 + 2], g.off, g.vs, g.rv, g.len, id);
 }
 
 // ---------------------------------------------------------------------------------------------

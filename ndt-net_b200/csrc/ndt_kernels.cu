@@ -251,14 +251,16 @@ __global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N
 
     const long begin = (long)blockIdx.x * kCountPointsPerCta;
     if (begin >= n_used) return;
+    const GridCtx gc = make_grid_ctx(s);
     const long end = begin + kCountPointsPerCta < n_used ? begin + kCountPointsPerCta : n_used;
     if (use_smem) {
         for (unsigned w = threadIdx.x; w < nwords; w += blockDim.x) s_bits[w] = 0u;
         __syncthreads();
         for (long i = begin + threadIdx.x; i < end; i += blockDim.x) {
-            double x, y, z; load_point(p, i, x, y, z);
             unsigned id;
-            if (voxel_of(x, y, z, off, vs, rv, len, id)) atomicOr(&s_bits[id >> 5], 1u << (id & 31));
+            // test before set: only ~V of the G cells are occupied, so after the first few hundred points of the
+            // CTA nearly every bit is already there and the (serialising) shared-memory atomic is skipped
+            if (point_cell<T>(p, i, gc, id) && !((s_bits[id >> 5] >> (id & 31)) & 1u)) atomicOr(&s_bits[id >> 5], 1u << (id & 31));
         }
         __syncthreads();
         for (unsigned w = threadIdx.x; w < nwords; w += blockDim.x) {
@@ -267,9 +269,8 @@ __global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N
         }
     } else {
         for (long i = begin + threadIdx.x; i < end; i += blockDim.x) {
-            double x, y, z; load_point(p, i, x, y, z);
             unsigned id;
-            if (voxel_of(x, y, z, off, vs, rv, len, id)) atomicOr(&bm[id >> 5].x, 1u << (id & 31));
+            if (point_cell<T>(p, i, gc, id) && !((bm[id >> 5].x >> (id & 31)) & 1u)) atomicOr(&bm[id >> 5].x, 1u << (id & 31));
         }
     }
 }
@@ -310,13 +311,13 @@ __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N,
     const int len[3] = {s.len[0], s.len[1], s.len[2]};
     const long chunk = N / kWorkers;
     const long n_used = chunk * kWorkers;
+    const GridCtx gc = make_grid_ctx(s);
     for (long base = begin; base < tend; base += 32) {
         const long i = base + lane;
         unsigned slot = kDropped;
         unsigned id = 0;
         if (i < n_used && (unsigned)i < s.fail[i / chunk]) {
-            double x, y, z; load_point(p, i, x, y, z);
-            if (voxel_of(x, y, z, off, vs, rv, len, id)) {
+            if (point_cell<T>(p, i, gc, id)) {
                 const uint2 w = bm[id >> 5];
                 slot = w.y + __popc(w.x & ((1u << (id & 31)) - 1u));
             }
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(256) k_scatter(const T *__restrict__ pts, cons
                                                  const CloudState *__restrict__ states, unsigned vcap, int ntiles,
                                                  const unsigned *__restrict__ slot_rank, const unsigned *__restrict__ tile_cnt,
                                                  const unsigned *__restrict__ vox_start, T *__restrict__ sorted,
-                                                 unsigned *__restrict__ hist, int nbins) {
+                                                 uint16_t *__restrict__ sorted_labels, unsigned *__restrict__ hist, int nbins) {
     const int b = blockIdx.y;
     if (states[b].status != 0) return;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -418,7 +419,9 @@ __global__ void __launch_bounds__(256) k_scatter(const T *__restrict__ pts, cons
     q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
     if (labels) {
         const unsigned l = labels[(size_t)b * N + i];
-        if (l < (unsigned)nbins) atomicAdd(&hist[((size_t)b * vcap + slot) * nbins + l], 1u);
+        sorted_labels[(size_t)b * N + pos] = (uint16_t)l;
+        // wide label sets (> kSmemLabelBins classes) vote through global atomics; small ones are counted by k_stats
+        if (hist && l < (unsigned)nbins) atomicAdd(&hist[((size_t)b * vcap + slot) * nbins + l], 1u);
     }
 }
 
@@ -456,7 +459,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
                                                const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                                const unsigned *__restrict__ vox_order,
-                                               const unsigned *__restrict__ hist, int nbins,
+                                               const uint16_t *__restrict__ sorted_labels, const unsigned *__restrict__ hist, int nbins,
                                                double *__restrict__ mean, double *__restrict__ cov, uint16_t *__restrict__ cls) {
     const int b = blockIdx.x;
     const CloudState &s = states[b];
@@ -478,6 +481,10 @@ __global__ void __launch_bounds__(128) k_stats(const CloudState *__restrict__ st
     double2 *rs = s_r[warp];
     double(*mus)[3] = s_mu[warp];
 
+    __shared__ unsigned s_h[4][kSmemLabelBins];   // label votes of this voxel (normal_distributions.c:107-121)
+    const bool smem_votes = sorted_labels != nullptr && hist == nullptr;
+    const uint16_t *sl = sorted_labels ? sorted_labels + (size_t)b * N + st : nullptr;
+    if (smem_votes) { for (int j = lane; j < kSmemLabelBins; j += 32) s_h[warp][j] = 0; }
     const int cl = lane < 3 ? lane : 2;    // chain lane -> dimension
     const int al = lane < 6 ? lane : 5;    // accumulator lane -> term
     double mu = 0.0, acc = 0.0;
@@ -505,6 +512,10 @@ __global__ void __launch_bounds__(128) k_stats(const CloudState *__restrict__ st
             xs[lane][0] = make_double2(x0, x0 * rl);
             xs[lane][1] = make_double2(x1, x1 * rl);
             xs[lane][2] = make_double2(x2, x2 * rl);
+        }
+        if (smem_votes && lane < m) {
+            const unsigned l = sl[base + lane];
+            if (l < (unsigned)nbins) atomicAdd(&s_h[warp][l], 1u);
         }
         if (base + 32 + lane < n) {          // issue the next round's global loads now; they land during phase A
             const T *pn = p + (size_t)(base + 32 + lane) * 3;
@@ -652,9 +663,10 @@ __global__ void __launch_bounds__(128) k_stats(const CloudState *__restrict__ st
         double *co = cov + ((size_t)b * vcap + v) * 9;
         co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
     }
-    if (hist) {
+    if (hist || smem_votes) {
         // lowest class index with the strictly largest count (normal_distributions.c:114-120)
-        const unsigned *h = hist + ((size_t)b * vcap + v) * nbins;
+        __syncwarp();
+        const unsigned *h = smem_votes ? s_h[warp] : hist + ((size_t)b * vcap + v) * nbins;
         unsigned best = 0; int bc = 0x7fffffff;
         for (int j = lane; j < nbins; j += 32) { const unsigned x = h[j]; if (x > best) { best = x; bc = j; } }
 #pragma unroll
@@ -1110,22 +1122,24 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         const size_t rank_smem = 4 * (size_t)vcap * sizeof(unsigned short);
         if (rank_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_rank<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
         k_rank<T><<<dim3((ntiles + 3) / 4, B), 128, rank_smem, st>>>(
-            pts, N, w.states, w.bitmap, w.bitmap_stride, vcap, ntiles, w.slot_rank, w.tile_cnt, w.point_voxel);
+            pts, N, w.states, w.bitmap, w.bitmap_stride, vcap, ntiles, w.slot_rank, w.tile_cnt, w.keep_point_voxels ? w.point_voxel : nullptr);
         DBG("k_rank");
     }
     tm.mark(ST_OFFSETS, st);
     k_offsets<<<B, 1024, 0, st>>>(w.states, vcap, ntiles, w.tile_cnt, w.vox_n, w.vox_start, w.vox_order); DBG("k_offsets");
     tm.mark(ST_SCATTER, st);
-    if (labels) CK(cudaMemsetAsync(w.hist, 0, (size_t)B * vcap * nbins * sizeof(unsigned), st));
+    const bool wide_labels = labels && nbins > kSmemLabelBins;
+    if (wide_labels) CK(cudaMemsetAsync(w.hist, 0, (size_t)B * vcap * nbins * sizeof(unsigned), st));
     if (N > 0) {
         k_scatter<T><<<dim3((unsigned)((N + 255) / 256), B), 256, 0, st>>>(
             pts, labels, N, w.states, vcap, ntiles, w.slot_rank, w.tile_cnt, w.vox_start, (T *)w.sorted,
-            labels ? w.hist : nullptr, nbins);
+            w.sorted_labels, wide_labels ? w.hist : nullptr, nbins);
         DBG("k_scatter");
     }
     tm.mark(ST_STATS, st);
     k_stats<T><<<dim3(B, (vcap + 3) / 4), 128, 0, st>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order,
-                                                       labels ? w.hist : nullptr, nbins, w.mean, w.cov, w.cls);
+                                                       labels ? w.sorted_labels : nullptr, wide_labels ? w.hist : nullptr, nbins,
+                                                       w.mean, w.cov, w.cls);
     DBG("k_stats");
     tm.mark(ST_KL, st);
     k_kl<<<dim3((vcap + 63) / 64, B), 64, 0, st>>>(w.states, vcap, w.bitmap, w.bitmap_stride, w.vox_cell, w.vox_n, w.cov,

@@ -49,6 +49,8 @@ def lib() -> C.CDLL:
     L.ndnet_b200_downsample_batch.argtypes = batch_args
     L.ndnet_b200_downsample_batch_host.restype = i
     L.ndnet_b200_downsample_batch_host.argtypes = batch_args
+    L.ndnet_b200_keep_point_voxels.restype = i
+    L.ndnet_b200_keep_point_voxels.argtypes = [vp, i]
     L.ndnet_b200_last_point_voxels.restype = i
     L.ndnet_b200_last_point_voxels.argtypes = [vp, vp, vp]
     L.ndnet_b200_last_kl_list.restype = l
@@ -81,7 +83,7 @@ def lib() -> C.CDLL:
 EXPORTED = [
     "ndt_downsample", "prune_nds", "to_point_cloud", "free_nds", "free_kl_divergences", "print_matrix",
     "ndnet_b200_create", "ndnet_b200_destroy", "ndnet_b200_last_error", "ndnet_b200_version",
-    "ndnet_b200_downsample_batch", "ndnet_b200_downsample_batch_host", "ndnet_b200_last_point_voxels",
+    "ndnet_b200_downsample_batch", "ndnet_b200_downsample_batch_host", "ndnet_b200_keep_point_voxels", "ndnet_b200_last_point_voxels",
     "ndnet_b200_last_kl_list", "ndnet_b200_selftest_div", "ndnet_b200_launch_count", "ndnet_b200_stage_timing", "ndnet_b200_stage_times",
     "ndnet_b200_model_create", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
     "ndnet_b200_infer_host", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline",

@@ -122,6 +122,9 @@ class NdtEngine:
         return out_feat, out_lab, info
 
     # ---- inspection helpers used by the parity tests -------------------------------------------
+    def keep_point_voxels(self, enable: bool = True) -> None:
+        self._check(self._L.ndnet_b200_keep_point_voxels(self._h, 1 if enable else 0), "ndnet_b200_keep_point_voxels")
+
     def last_point_voxels(self, B: int, N: int) -> torch.Tensor:
         out = torch.empty((B, N), dtype=torch.int32, device=self.device)
         self._check(self._L.ndnet_b200_last_point_voxels(self._h, out.data_ptr(),

@@ -27,7 +27,9 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ndt_ref_golden.npz")
 @pytest.fixture(scope="module")
 def engine():
     from ndnet_b200.engine import NdtEngine
-    return NdtEngine(0)
+    e = NdtEngine(0)
+    e.keep_point_voxels(True)      # the parity tests compare every point's voxel id
+    return e
 
 
 def _run_gpu(engine, pts, labels, ncls, d):
