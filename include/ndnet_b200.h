@@ -148,8 +148,10 @@ int ndnet_b200_stage_times(ndnet_b200_ctx *ctx, double *ms, int cap, long *runs)
 typedef struct ndnet_b200_model ndnet_b200_model;
 
 /* kinds */
-#define NDNET_B200_NDTNET_CLS 0
-#define NDNET_B200_NDTNET_SEG 1
+#define NDNET_B200_NDTNET_CLS 0     /* ndnet/models/ndtnet.py:166-196  */
+#define NDNET_B200_NDTNET_SEG 1     /* ndnet/models/ndtnet.py:198-243  */
+#define NDNET_B200_POINTNET_CLS 2   /* ndnet/models/pointnet.py:137-167 */
+#define NDNET_B200_POINTNET_SEG 3   /* ndnet/models/pointnet.py:169-214 */
 
 /* Build a model from a flat list of named fp32 host tensors (the reference state_dict: names follow
  * ndtnet.py module attributes, e.g. "feature_extractor.t1.conv1.weight").  BatchNorm is folded with its
@@ -158,8 +160,10 @@ int ndnet_b200_model_create(ndnet_b200_ctx *ctx, ndnet_b200_model **model, int k
                             const char *const *names, const float *const *data, const int64_t *const *shapes,
                             const int *ndims);
 void ndnet_b200_model_destroy(ndnet_b200_model *model);
+/* floats per input row the model expects: 12 for NDT-Net (mean + covariance), point_dim for PointNet */
+int ndnet_b200_model_input_dim(const ndnet_b200_model *model);
 
-/* Forward over B clouds of D distributions.  feat: device [B, D, 12] f32.
+/* Forward over B clouds of D distributions.  feat: device [B, D, input_dim] f32.
  * cls: out device [B, num_classes] f32 (softmax);  seg: out device [B, D, num_classes+1] f32 (log_softmax). */
 int ndnet_b200_model_forward(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const float *feat, int B, int D,
                              float *out, void *stream);

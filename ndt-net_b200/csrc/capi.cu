@@ -582,6 +582,8 @@ extern "C" int ndnet_b200_model_create(ndnet_b200_ctx *c, ndnet_b200_model **mod
     return 0;
 }
 
+extern "C" int ndnet_b200_model_input_dim(const ndnet_b200_model *m) { return m ? m->m.input_dim() : -200; }
+
 extern "C" void ndnet_b200_model_destroy(ndnet_b200_model *m) {
     if (!m) return;
     m->m.release();

@@ -52,6 +52,77 @@ __global__ void __launch_bounds__(128) k_tnet3_l1(const float *__restrict__ feat
     }
 }
 
+// T-Net(d) first layer for a generic input width d <= 16 (PointNet with point_dim != 3, pointnet.py:45).
+__global__ void __launch_bounds__(128) k_tnet_l1(const float *__restrict__ x, int d, int total, const float *__restrict__ W /*[64][d]*/,
+                                                 const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out /*[total][64]*/) {
+    __shared__ float sW[64 * 16], sb[64];
+    for (int i = threadIdx.x; i < 64 * d; i += blockDim.x) sW[i] = W[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) sb[i] = bias[i];
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = k < d ? x[(size_t)p * d + k] : 0.f;
+    uint4 *o = reinterpret_cast<uint4 *>(out + (size_t)p * 64);
+#pragma unroll 1
+    for (int c8 = 0; c8 < 8; c8++) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int c = c8 * 8 + j * 2;
+            float a = sb[c], b = sb[c + 1];
+#pragma unroll
+            for (int k = 0; k < 16; k++) if (k < d) { a += sW[c * d + k] * v[k]; b += sW[(c + 1) * d + k] * v[k]; }
+            __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, 0.f), fmaxf(b, 0.f));
+            pk[j] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        o[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+// PointNet input transform + first trunk layer (pointnet.py:111-120): x' = T x, nan_to_num(nan=0), bn1(conv1(x')).
+__global__ void __launch_bounds__(128) k_trunk_l1_pn(const float *__restrict__ x, int d, int P, int total, const float *__restrict__ T1 /*[B][d*d]*/,
+                                                     const float *__restrict__ W /*[64][d]*/, const float *__restrict__ bias,
+                                                     __nv_bfloat16 *__restrict__ out /*[total][64]*/) {
+    __shared__ float sW[64 * 16], sb[64];
+    for (int i = threadIdx.x; i < 64 * d; i += blockDim.x) sW[i] = W[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) sb[i] = bias[i];
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const float *t = T1 + (size_t)(p / P) * d * d;
+    float v[16], y[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = k < d ? x[(size_t)p * d + k] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        float a = 0.f;
+        if (i < d) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) if (k < d) a += t[i * d + k] * v[k];
+            if (isnan(a)) a = 0.f;                                   // torch.nan_to_num(x, nan=0.0): inf -> +-FLT_MAX
+            else if (isinf(a)) a = a > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+        }
+        y[i] = a;
+    }
+    uint4 *o = reinterpret_cast<uint4 *>(out + (size_t)p * 64);
+#pragma unroll 1
+    for (int c8 = 0; c8 < 8; c8++) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int c = c8 * 8 + j * 2;
+            float a = sb[c], b = sb[c + 1];
+#pragma unroll
+            for (int k = 0; k < 16; k++) if (k < d) { a += sW[c * d + k] * y[k]; b += sW[(c + 1) * d + k] * y[k]; }
+            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            pk[j] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        o[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
 // Input transform + first trunk layer (ndtnet.py:132-149): p' = T1 p, Sigma' = T1 Sigma, bn1(conv1([p';Sigma'])).
 __global__ void __launch_bounds__(128) k_trunk_l1(const float *__restrict__ feat, int P, int total, const float *__restrict__ T1 /*[B][9]*/,
                                                   const float *__restrict__ W /*[64][12]*/, const float *__restrict__ bias,
@@ -221,6 +292,8 @@ struct TNetW {
 
 struct ModelImpl {
     int kind = 0, F = 0, ncls = 0;   // ncls = number of outputs of the last layer
+    bool pointnet = false;           // kinds 2/3: ndnet/models/pointnet.py (no covariance branch, generic point_dim)
+    int in_dim = 12;                 // floats per input row
     TNetW t1, t2;
     float *c1_w = nullptr, *c1_b = nullptr;                       // [64][12]
     __nv_bfloat16 *c2_w = nullptr, *c3_w = nullptr; float *c2_b = nullptr, *c3_b = nullptr;
@@ -287,7 +360,7 @@ bool build_tnet(ModelImpl &m, const TensorMapHost &t, const std::string &p, int 
         f2.out != 256 || f3.out != in * in) { err = "unexpected T-Net shapes under " + p; return false; }
     w.in = in;
     bool ok = true;
-    if (in == 3) ok = ok && up_f32(m, a.w, w.l1_w); else ok = ok && up_bf16(m, a.w.data(), a.w.size(), w.l1_wb);
+    if (in != 64) ok = ok && up_f32(m, a.w, w.l1_w); else ok = ok && up_bf16(m, a.w.data(), a.w.size(), w.l1_wb);
     ok = ok && up_f32(m, a.b, w.l1_b) && up_bf16(m, b.w.data(), b.w.size(), w.l2_w) && up_f32(m, b.b, w.l2_b) &&
          up_bf16(m, c.w.data(), c.w.size(), w.l3_w) && up_f32(m, c.b, w.l3_b) && up_f32(m, f1.w, w.fc1_w) && up_f32(m, f1.b, w.fc1_b) &&
          up_f32(m, f2.w, w.fc2_w) && up_f32(m, f2.b, w.fc2_b) && up_f32(m, f3.w, w.fc3_w) && up_f32(m, f3.b, w.fc3_b);
@@ -307,12 +380,16 @@ int Model::build(int kind, int n_tensors, const char *const *names, const float 
     }
     impl = new ModelImpl();
     ModelImpl &m = *impl;
-    m.kind = kind;
+    m.pointnet = kind >= 2;
+    m.kind = kind & 1;               // 0 classification head, 1 segmentation head
     const std::string fe = "feature_extractor";
-    if (!build_tnet(m, t, fe + ".t1", 3, m.t1, err) || !build_tnet(m, t, fe + ".t2", 64, m.t2, err)) return -301;
     Folded c1, c2, c3;
     if (!fold(t, fe + ".conv1", fe + ".bn1", c1, err) || !fold(t, fe + ".conv2", fe + ".bn2", c2, err) || !fold(t, fe + ".conv3", fe + ".bn3", c3, err)) return -301;
-    if (c1.in != 12 || c1.out != 64 || c2.in != 64 || c2.out != 128 || c3.in != 128) { err = "unexpected trunk shapes (point_dim 3 + covariances expected)"; return -302; }
+    m.in_dim = c1.in;
+    const int t1_dim = m.pointnet ? c1.in : 3;
+    if (m.pointnet ? (c1.in < 1 || c1.in > 16) : (c1.in != 12)) { err = "unsupported input width (NDT-Net: 3 + 9 covariances; PointNet: point_dim <= 16)"; return -302; }
+    if (c1.out != 64 || c2.in != 64 || c2.out != 128 || c3.in != 128) { err = "unexpected trunk shapes"; return -302; }
+    if (!build_tnet(m, t, fe + ".t1", t1_dim, m.t1, err) || !build_tnet(m, t, fe + ".t2", 64, m.t2, err)) return -301;
     m.F = c3.out;
     bool ok = up_f32(m, c1.w, m.c1_w) && up_f32(m, c1.b, m.c1_b) && up_bf16(m, c2.w.data(), c2.w.size(), m.c2_w) && up_f32(m, c2.b, m.c2_b) &&
               up_bf16(m, c3.w.data(), c3.w.size(), m.c3_w) && up_f32(m, c3.b, m.c3_b);
@@ -342,6 +419,8 @@ int Model::build(int kind, int n_tensors, const char *const *names, const float 
     if (!ok) { err = "device upload failed"; return -303; }
     return 0;
 }
+
+int Model::input_dim() const { return impl ? impl->in_dim : 0; }
 
 void Model::release() {
     if (!impl) return;
@@ -427,7 +506,7 @@ int Model::forward(Scratch &scratch, const float *feat, int B, int D, float *out
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_h64 = take(M * 64 * 2), o_h128 = take(M * 128 * 2), o_a1 = take(M * 64 * 2), o_xt2 = take(M * 64 * 2);
     const size_t o_gmax = take((size_t)B * (1024 + 1024 + m.F) * 4);
-    const size_t o_f512 = take((size_t)B * 512 * 4), o_f256 = take((size_t)B * 256 * 4), o_T1 = take((size_t)B * 9 * 4);
+    const size_t o_f512 = take((size_t)B * 512 * 4), o_f256 = take((size_t)B * 256 * 4), o_T1 = take((size_t)B * 256 * 4);
     const size_t o_T2 = take((size_t)B * 4096 * 4), o_T2t = take((size_t)B * 4096 * 2);
     const size_t o_cb = take((size_t)B * 512 * 4), o_logit = take((size_t)B * (m.ncls > 0 ? m.ncls : 1) * 4);
     const size_t o_s1 = take(m.kind == 1 ? M * 512 * 2 : 0), o_s2 = take(m.kind == 1 ? M * 256 * 2 : 0);
@@ -444,14 +523,17 @@ int Model::forward(Scratch &scratch, const float *feat, int B, int D, float *out
     if (cudaMemsetAsync(g1, 0, (size_t)B * (2048 + m.F) * 4, st) != cudaSuccess) { err = "memset failed"; return -305; }
     const int total = (int)M;
     // ---- input transform T-Net (ndtnet.py:132-133)
-    k_tnet3_l1<<<(total + 127) / 128, 128, 0, st>>>(feat, total, m.t1.l1_w, m.t1.l1_b, h64);
+    if (m.pointnet) k_tnet_l1<<<(total + 127) / 128, 128, 0, st>>>(feat, m.in_dim, total, m.t1.l1_w, m.t1.l1_b, h64);
+    else k_tnet3_l1<<<(total + 127) / 128, 128, 0, st>>>(feat, total, m.t1.l1_w, m.t1.l1_b, h64);
     f.rows(h64, 64, m.t1.l2_w, 128, false, m.t1.l2_b, nullptr, 0, true, h128);
     f.chmax(m.t1.l3_w, 1024, h128, 128, m.t1.l3_b, true, g1, 1024);
     f.fc(m.t1.fc1_w, m.t1.fc1_b, g1, 1024, true, f512, 512, 1024, 512, true);
     f.fc(m.t1.fc2_w, m.t1.fc2_b, f512, 512, false, f256, 256, 512, 256, true);
-    f.fc(m.t1.fc3_w, m.t1.fc3_b, f256, 256, false, T1, 9, 256, 9, false, 3);
+    const int td = m.t1.in;
+    f.fc(m.t1.fc3_w, m.t1.fc3_b, f256, 256, false, T1, td * td, 256, td * td, false, td);
     // ---- transform + conv1/bn1 (ndtnet.py:135-149)
-    k_trunk_l1<<<(total + 127) / 128, 128, 0, st>>>(feat, P, total, T1, m.c1_w, m.c1_b, a1);
+    if (m.pointnet) k_trunk_l1_pn<<<(total + 127) / 128, 128, 0, st>>>(feat, m.in_dim, P, total, T1, m.c1_w, m.c1_b, a1);
+    else k_trunk_l1<<<(total + 127) / 128, 128, 0, st>>>(feat, P, total, T1, m.c1_w, m.c1_b, a1);
     // ---- feature transform T-Net (ndtnet.py:152)
     f.rows(a1, 64, m.t2.l1_wb, 64, false, m.t2.l1_b, nullptr, 0, true, h64);
     f.rows(h64, 64, m.t2.l2_w, 128, false, m.t2.l2_b, nullptr, 0, true, h128);

@@ -20,6 +20,7 @@ struct Model {
               const int *ndims, std::string &err);
     int forward(Scratch &scratch, const float *feat, int B, int D, float *out, cudaStream_t st, std::string &err);
     void release();
+    int input_dim() const;
 };
 
 }  // namespace mlp

@@ -82,6 +82,9 @@ __device__ __forceinline__ bool voxel_of(double x, double y, double z, const dou
     return true;
 }
 
+// out-of-line copy for the fp32 prefilter's rare fallback, so that the compiler cannot speculate the fp64 path
+static __device__ __noinline__ unsigned axis_cell_rare(double p, double off, double vs, double rv) { return axis_cell(p, off, vs, rv); }
+
 // Grid parameters of one pass, with fp32 copies for the prefilter below.
 struct GridCtx {
     double off[3], vs, rv;
@@ -114,7 +117,7 @@ __device__ __forceinline__ unsigned axis_cell32(float p, int a, const GridCtx &g
         const float eps = q * 4e-7f;
         if (t > eps && (1.0f - t) > eps) return (unsigned)ri;
     }
-    return axis_cell((double)p, g.off[a], g.vs, g.rv);
+    return axis_cell_rare((double)p, g.off[a], g.vs, g.rv);
 }
 
 template <typename T>

@@ -66,6 +66,8 @@ def lib() -> C.CDLL:
     L.ndnet_b200_model_create.restype = i
     L.ndnet_b200_model_create.argtypes = [vp, C.POINTER(vp), i, i, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(vp),
                                           C.POINTER(i)]
+    L.ndnet_b200_model_input_dim.restype = i
+    L.ndnet_b200_model_input_dim.argtypes = [vp]
     L.ndnet_b200_model_destroy.restype = None
     L.ndnet_b200_model_destroy.argtypes = [vp]
     L.ndnet_b200_model_forward.restype = i
@@ -85,6 +87,6 @@ EXPORTED = [
     "ndnet_b200_create", "ndnet_b200_destroy", "ndnet_b200_last_error", "ndnet_b200_version",
     "ndnet_b200_downsample_batch", "ndnet_b200_downsample_batch_host", "ndnet_b200_keep_point_voxels", "ndnet_b200_last_point_voxels",
     "ndnet_b200_last_kl_list", "ndnet_b200_selftest_div", "ndnet_b200_launch_count", "ndnet_b200_stage_timing", "ndnet_b200_stage_times",
-    "ndnet_b200_model_create", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
+    "ndnet_b200_model_create", "ndnet_b200_model_input_dim", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
     "ndnet_b200_infer_host", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline",
 ]

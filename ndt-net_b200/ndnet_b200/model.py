@@ -9,7 +9,8 @@ import torch
 from . import _lib
 from .engine import default_engine
 
-KIND_CLS, KIND_SEG = 0, 1
+KIND_CLS, KIND_SEG = 0, 1                       # NDT-Net heads (ndtnet.py)
+KIND_POINTNET_CLS, KIND_POINTNET_SEG = 2, 3     # PointNet heads (pointnet.py)
 
 
 def deterministic_state_dict(module: torch.nn.Module, seed: int = 0) -> dict:
@@ -64,8 +65,9 @@ class B200Model:
             raise RuntimeError(f"ndnet_b200_model_create failed ({rc}): "
                                f"{self._L.ndnet_b200_last_error(self.engine.handle).decode()}")
         self._h = h
-        self.kind = kind
-        self.n_out = int(module.num_classes) + (1 if kind == KIND_SEG else 0)
+        self.kind = kind & 1                       # 0 classification, 1 segmentation
+        self.in_dim = int(self._L.ndnet_b200_model_input_dim(h))
+        self.n_out = int(module.num_classes) + (1 if self.kind == KIND_SEG else 0)
 
     def __del__(self):
         try:
@@ -76,8 +78,8 @@ class B200Model:
             pass
 
     def __call__(self, feat: torch.Tensor) -> torch.Tensor:
-        """feat: CUDA f32 [B, D, 12] -> cls: [B, n_out, 1] probabilities; seg: [B, D, n_out] log-probabilities."""
-        assert feat.is_cuda and feat.dtype == torch.float32 and feat.dim() == 3 and feat.shape[2] == 12
+        """feat: CUDA f32 [B, D, in_dim] -> cls: [B, n_out, 1] probabilities; seg: [B, D, n_out] log-probabilities."""
+        assert feat.is_cuda and feat.dtype == torch.float32 and feat.dim() == 3 and feat.shape[2] == self.in_dim
         feat = feat.contiguous()
         B, D, _ = feat.shape
         if self.kind == KIND_SEG:

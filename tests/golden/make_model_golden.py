@@ -28,6 +28,7 @@ def load_reference_models():
         import ndnet  # noqa: F401  (the reference package)
         sys.modules["ndnet.preprocessing.ndt_legacy"] = stub
         ref = importlib.import_module("ndnet.models.ndtnet")
+        ref.pointnet = importlib.import_module("ndnet.models.pointnet")
         assert ref.__file__.startswith("/root/reference"), ref.__file__
     finally:
         sys.path.remove("/root/reference")
@@ -56,6 +57,15 @@ def main():
         cls.load_state_dict(deterministic_state_dict(cls, 1)); cls.eval()
         p, c = inputs(2, 3, 130)
         out["cls_out"] = cls(torch.from_numpy(p), torch.from_numpy(c)).numpy()
+        # PointNet (ndnet/models/pointnet.py) on 12-D points and on plain xyz
+        pseg = ref.pointnet.PointNetSegmentation(point_dim=12, num_classes=28, feature_dim=768)
+        pseg.load_state_dict(deterministic_state_dict(pseg, 2)); pseg.eval()
+        p, c = inputs(3, 2, 150)
+        out["pn_seg_out"] = pseg(torch.from_numpy(np.concatenate([p, c], 2) * 0.3)).numpy()
+        pcls = ref.pointnet.PointNetClassification(point_dim=3, num_classes=40, feature_dim=768)
+        pcls.load_state_dict(deterministic_state_dict(pcls, 3)); pcls.eval()
+        p, c = inputs(4, 3, 140)
+        out["pn_cls_out"] = pcls(torch.from_numpy(p * 0.05)).numpy()
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model_ref_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items()})

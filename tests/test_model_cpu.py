@@ -30,6 +30,22 @@ def test_drop_in_modules_match_reference_outputs():
         assert np.allclose(out, g["cls_out"], rtol=1e-4, atol=1e-6)
 
 
+def test_pointnet_drop_in_modules_match_reference_outputs():
+    from ndnet.models.pointnet import PointNetClassification, PointNetSegmentation
+    g = np.load(GOLDEN)
+    with torch.no_grad():
+        pseg = PointNetSegmentation(point_dim=12, num_classes=28, feature_dim=768)
+        pseg.load_state_dict(deterministic_state_dict(pseg, 2)); pseg.eval()
+        p, c = inputs(3, 2, 150)
+        out = pseg(torch.from_numpy(np.concatenate([p, c], 2) * 0.3)).numpy()
+        assert np.allclose(out, g["pn_seg_out"], rtol=1e-4, atol=1e-4)
+        pcls = PointNetClassification(point_dim=3, num_classes=40, feature_dim=768)
+        pcls.load_state_dict(deterministic_state_dict(pcls, 3)); pcls.eval()
+        p, c = inputs(4, 3, 140)
+        out = pcls(torch.from_numpy(p * 0.05)).numpy()
+        assert np.allclose(out, g["pn_cls_out"], rtol=1e-4, atol=1e-6)
+
+
 def test_state_dict_keys_follow_the_reference_layout():
     keys = set(NDTNetSegmentation(num_classes=28).state_dict())
     for k in ["feature_extractor.t1.conv1.weight", "feature_extractor.t2.fc3.bias", "feature_extractor.bn3.running_var",

@@ -113,3 +113,22 @@ def test_pipelined_inference_equals_single_stream_calls():
     got_host = m.infer_host(torch.from_numpy(pts).pin_memory(), 300, torch.from_numpy(lab.astype(np.int16)).pin_memory(), 28, out_host)
     torch.cuda.synchronize()
     assert torch.equal(ref, got_dev) and torch.equal(ref.cpu(), got_host)
+
+
+def test_pointnet_forward_matches_torch_fp32():
+    """ndnet/models/pointnet.py: 12-D points (segmentation) and plain xyz (classification) through the CUDA path."""
+    from ndnet.models.pointnet import PointNetClassification, PointNetSegmentation
+    pseg = PointNetSegmentation(point_dim=12, num_classes=28, feature_dim=768)
+    pseg.load_state_dict(deterministic_state_dict(pseg, 2)); pseg = pseg.cuda().eval()
+    p, c = inputs(3, 4, 333)
+    x = torch.from_numpy(np.concatenate([p, c], 2) * 0.3).cuda()
+    with torch.no_grad():
+        ref, got = pseg(x), pseg.forward_b200(x)
+    ok, detail = _seg_ok(got, ref)
+    assert got.shape == (4, 333, 29) and ok, detail
+    pcls = PointNetClassification(point_dim=3, num_classes=40, feature_dim=768)
+    pcls.load_state_dict(deterministic_state_dict(pcls, 3)); pcls = pcls.cuda().eval()
+    x = torch.from_numpy(inputs(4, 6, 140)[0] * 0.05).cuda()
+    with torch.no_grad():
+        ref, got = pcls(x), pcls.forward_b200(x)
+    assert got.shape == ref.shape == (6, 40, 1) and (got - ref).abs().max().item() <= CLS_ATOL
