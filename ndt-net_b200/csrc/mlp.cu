@@ -393,7 +393,7 @@ int Model::build(int kind, int n_tensors, const char *const *names, const float 
     m.F = c3.out;
     bool ok = up_f32(m, c1.w, m.c1_w) && up_f32(m, c1.b, m.c1_b) && up_bf16(m, c2.w.data(), c2.w.size(), m.c2_w) && up_f32(m, c2.b, m.c2_b) &&
               up_bf16(m, c3.w.data(), c3.w.size(), m.c3_w) && up_f32(m, c3.b, m.c3_b);
-    if (kind == 1) {
+    if (m.kind == 1) {
         Folded h1, h2, h3, h4;
         if (!fold(t, "conv1", "bn1", h1, err) || !fold(t, "conv2", "bn2", h2, err) || !fold(t, "conv3", "bn3", h3, err) || !fold(t, "conv4", "", h4, err)) return -301;
         if (h1.in != m.F + 64 || h1.out != 512 || h2.in != 512 || h2.out != 256 || h3.in != 256 || h3.out != 128 || h4.in != 128 || h4.out > 32) {
