@@ -166,7 +166,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "clouds/sec (NDT voxel+KL prune+PointNet fwd) @120k pts", "value": value, "unit": "clouds/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clouds_per_step": per_step, "points": N_POINTS, "n_desired_nds": N_NDS},
+        "config": {"workload": WORKLOAD, "clouds_per_step": per_step, "points": N_POINTS, "n_desired_nds": N_NDS,
+                   "parallelism": "host CPU only (rank 0); NDT core uses its fixed 8 pthreads, torch all host threads"},
         "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": threads, "kind": kind,
                          "sample": f"{per_step} scans per step x {args.steps} steps; NDT = reference C core (8 pthreads, -O0, GSL shim) "
                                    f"serial over scans, network = torch fp32 on {threads} threads"},
@@ -269,6 +270,7 @@ def run_ours(args):
     L.ndnet_b200_stage_timing(eng.handle, 0)
     stage_ms = {n: float(st[i]) / max(int(runs[0]), 1) for i, n in enumerate(STAGES)}
     feat = eng.downsample(dev_pts[0], N_NDS, dev_lab[0], N_CLASSES, want_info=False).feat
+    model(feat)                               # sizes the single-stream scratch outside the timed loop
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)

@@ -12,6 +12,10 @@
 #include <cstdlib>
 #include <cstring>
 
+#ifndef NDT_STATS_MIN_BLOCKS
+#define NDT_STATS_MIN_BLOCKS 4
+#endif
+
 namespace ndt {
 
 #ifdef NDT_CHECKS
@@ -456,7 +460,7 @@ __device__ __forceinline__ double div_by_count(double d, double cnt) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
+__global__ void __launch_bounds__(128, NDT_STATS_MIN_BLOCKS) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
                                                const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                                const unsigned *__restrict__ vox_order,
                                                const uint16_t *__restrict__ sorted_labels, const unsigned *__restrict__ hist, int nbins,

@@ -103,6 +103,30 @@ def test_baseline_sized_clouds_match_oracle(engine, case):
     _check_against_oracle(engine, *case)
 
 
+def test_wide_label_set_uses_the_global_vote_path(engine):
+    """More than 64 classes: the label vote goes through global atomics instead of the shared-memory histogram."""
+    from ndnet_b200.synth import lidar_cloud
+    pts = lidar_cloud(30000, 61)
+    labels = np.random.default_rng(61).integers(0, 201, 30000).astype(np.uint16)
+    _check_against_oracle(engine, "wide_labels", pts, labels, 200, 700)
+
+
+def test_large_d_uses_the_global_memory_sort(engine):
+    """n_desired_nds = 8160 (tools/train_multiscale.py:33-36): ~30k list entries, beyond the shared-memory sort."""
+    from ndnet_b200.synth import lidar_cloud
+    pts = lidar_cloud(120000, 62)
+    _check_against_oracle(engine, "d8160", pts, None, 0, 8160)
+
+
+def test_fp64_batch_equals_fp32_batch_on_fp32_values(engine):
+    """The f64 entry (legacy ABI dtype) and the f32 entry agree on clouds whose coordinates are fp32 values."""
+    from ndnet_b200.synth import lidar_batch
+    pts = lidar_batch(3, 20000, seed0=63)
+    a = engine.downsample(torch.from_numpy(pts).cuda(), 400, nan_to_num=False, want_f64=True, want_voxel=True)
+    b = engine.downsample(torch.from_numpy(pts.astype(np.float64)).cuda(), 400, nan_to_num=False, want_f64=True, want_voxel=True)
+    assert torch.equal(a.voxel, b.voxel) and same_bits(a.feat64.cpu().numpy(), b.feat64.cpu().numpy())
+
+
 def test_golden_vectors_through_c_abi(engine):
     """The reference's own outputs (tests/golden, made from core_legacy/src by make_golden.py)."""
     g = np.load(GOLDEN)
