@@ -67,7 +67,8 @@ __device__ __forceinline__ unsigned axis_cell(double p, double off, double vs, d
     const double f = floor(q0);
     const double t = q0 - f;                                  // exact (Sterbenz / small integers)
     const double eps = q0 * 3.5527136788005009e-15;           // 2^-48 * q0  (>= 16 ulp)
-    if (t > eps && (1.0 - t) > eps) return (unsigned)f;
+    // a >= 0 (off is the minimum), so the quotient cannot fall below cell 0: no lower-boundary ambiguity there
+    if ((t > eps || f == 0.0) && (1.0 - t) > eps) return (unsigned)f;
     return (unsigned)floor(a / vs);
 }
 
@@ -115,7 +116,9 @@ __device__ __forceinline__ unsigned axis_cell32(float p, int a, const GridCtx &g
         if (rf > q) { ri -= 1; rf -= 1.0f; }                  // nearest -> floor
         const float t = q - rf;
         const float eps = q * 4e-7f;
-        if (t > eps && (1.0f - t) > eps) return (unsigned)ri;
+        // d >= 0 (off is the minimum, an fp32 value), so cell 0 has no lower-boundary ambiguity: flat ground at
+        // the minimum z puts most of a scan exactly there
+        if ((t > eps || ri == 0) && (1.0f - t) > eps) return (unsigned)ri;
     }
     return axis_cell_rare((double)p, g.off[a], g.vs, g.rv);
 }
