@@ -81,11 +81,13 @@ static cudaError_t alloc(T *&p, size_t count) {
 
 void Workspace::release() {
     const bool keep = keep_point_voxels;
+    cudaStream_t keep_side = side; cudaEvent_t keep_fork = ev_fork, keep_join = ev_join;
     void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, vox_order, slot_rank, tile_cnt, hist, point_voxel, sorted, sorted_labels,
                     mean, cov, cov_final, cls, kl_div, kl_flag, key, seq, firstpos, removed, list_div, list_seq};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = Workspace();
     keep_point_voxels = keep;
+    side = keep_side; ev_fork = keep_fork; ev_join = keep_join;
 }
 
 cudaError_t Workspace::reserve(int B, long N, long D, int bins) {

@@ -23,7 +23,8 @@ constexpr unsigned kSmemBitmapBits = 1u << 18; // grids up to this many cells ar
 constexpr int kCountPointsPerCta = 4096;
 constexpr int kRankTile = 2048;                // points per rank tile (one warp walks one tile in order)
 constexpr unsigned kDropped = 0xFFFFFFFFu;
-constexpr int kSmemLabelBins = 64;             // label sets up to this size are voted in shared memory by k_stats
+constexpr int kSmemLabelBins = 64;
+constexpr unsigned kHeavyVoxel = 512;         // voxels with at least this many points get a warp each in k_stats             // label sets up to this size are voted in shared memory by k_stats
 
 // Per-cloud search/grid state (device resident, one per cloud).
 struct CloudState {
@@ -45,6 +46,7 @@ struct CloudState {
     unsigned n_out;
     unsigned n_survivors;
     unsigned fail[kWorkers]; // first point of each worker chunk that left the grid (A4), else 0xFFFFFFFF
+    unsigned n_heavy;     // voxels with >= kHeavyVoxel points (first n_heavy entries of vox_order)
 };
 
 // Order-preserving map double <-> uint64 for atomicMin/atomicMax.

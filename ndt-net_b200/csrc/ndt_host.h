@@ -57,6 +57,8 @@ struct Workspace {
     unsigned *firstpos = nullptr; unsigned char *removed = nullptr;
     double *list_div = nullptr; unsigned *list_seq = nullptr;
     StageTimer timer;
+    cudaStream_t side = nullptr;       // side stream for kernels that are independent of the main chain
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // of the last run
     int last_B = 0; long last_N = 0; long last_D = 0;
 

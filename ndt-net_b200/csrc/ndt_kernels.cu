@@ -347,11 +347,11 @@ __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N,
 // K5  stable voxel assignment, step 2: per slot, turn the per-tile counts into exclusive prefixes and
 // the slot totals into segment starts.  grid B, block 1024.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_offsets(const CloudState *__restrict__ states, unsigned vcap, int ntiles,
+__global__ void __launch_bounds__(1024) k_offsets(CloudState *__restrict__ states, unsigned vcap, int ntiles,
                                                   unsigned *__restrict__ tile_cnt, unsigned *__restrict__ vox_n,
                                                   unsigned *__restrict__ vox_start, unsigned *__restrict__ vox_order) {
     const int b = blockIdx.x;
-    const CloudState &s = states[b];
+    CloudState &s = states[b];
     if (s.status != 0) return;
     const unsigned V = s.V;
     __shared__ unsigned s_warp[32];
@@ -391,7 +391,11 @@ __global__ void __launch_bounds__(1024) k_offsets(const CloudState *__restrict__
     __syncthreads();
     for (unsigned v = tid; v < V; v += blockDim.x) atomicAdd(&s_hist[__clz(vox_n[(size_t)b * vcap + v] | 1u)], 1u);
     __syncthreads();
-    if (tid == 0) { unsigned run = 0; for (int k = 0; k < 32; k++) { const unsigned c = s_hist[k]; s_hist[k] = run; run += c; } }
+    if (tid == 0) {
+        unsigned run = 0;
+        for (int k = 0; k < 32; k++) { const unsigned c = s_hist[k]; s_hist[k] = run; run += c; }
+        s.n_heavy = s_hist[__clz(kHeavyVoxel) + 1];      // keys 0..clz(kHeavyVoxel) hold the voxels with n >= kHeavyVoxel
+    }
     __syncthreads();
     for (unsigned v = tid; v < V; v += blockDim.x) {
         const int key = __clz(vox_n[(size_t)b * vcap + v] | 1u);
@@ -463,14 +467,13 @@ template <typename T>
 __global__ void __launch_bounds__(128, NDT_STATS_MIN_BLOCKS) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
                                                const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                                const unsigned *__restrict__ vox_order,
-                                               const uint16_t *__restrict__ sorted_labels, const unsigned *__restrict__ hist, int nbins,
-                                               double *__restrict__ mean, double *__restrict__ cov, uint16_t *__restrict__ cls) {
+                                               double *__restrict__ mean, double *__restrict__ cov) {
     const int b = blockIdx.x;
     const CloudState &s = states[b];
     if (s.status != 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned idx = blockIdx.y * 4 + warp;
-    if (idx >= s.V) return;
+    if (idx >= s.n_heavy) return;                 // lighter voxels: k_stats_light
     const unsigned v = vox_order[(size_t)b * vcap + idx];
     const unsigned st = vox_start[(size_t)b * (vcap + 1) + v], en = vox_start[(size_t)b * (vcap + 1) + v + 1];
     const T *p = sorted + ((size_t)b * N + st) * 3;
@@ -485,10 +488,6 @@ __global__ void __launch_bounds__(128, NDT_STATS_MIN_BLOCKS) k_stats(const Cloud
     double2 *rs = s_r[warp];
     double(*mus)[3] = s_mu[warp];
 
-    __shared__ unsigned s_h[4][kSmemLabelBins];   // label votes of this voxel (normal_distributions.c:107-121)
-    const bool smem_votes = sorted_labels != nullptr && hist == nullptr;
-    const uint16_t *sl = sorted_labels ? sorted_labels + (size_t)b * N + st : nullptr;
-    if (smem_votes) { for (int j = lane; j < kSmemLabelBins; j += 32) s_h[warp][j] = 0; }
     const int cl = lane < 3 ? lane : 2;    // chain lane -> dimension
     const int al = lane < 6 ? lane : 5;    // accumulator lane -> term
     double mu = 0.0, acc = 0.0;
@@ -516,10 +515,6 @@ __global__ void __launch_bounds__(128, NDT_STATS_MIN_BLOCKS) k_stats(const Cloud
             xs[lane][0] = make_double2(x0, x0 * rl);
             xs[lane][1] = make_double2(x1, x1 * rl);
             xs[lane][2] = make_double2(x2, x2 * rl);
-        }
-        if (smem_votes && lane < m) {
-            const unsigned l = sl[base + lane];
-            if (l < (unsigned)nbins) atomicAdd(&s_h[warp][l], 1u);
         }
         if (base + 32 + lane < n) {          // issue the next round's global loads now; they land during phase A
             const T *pn = p + (size_t)(base + 32 + lane) * 3;
@@ -667,20 +662,103 @@ __global__ void __launch_bounds__(128, NDT_STATS_MIN_BLOCKS) k_stats(const Cloud
         double *co = cov + ((size_t)b * vcap + v) * 9;
         co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
     }
-    if (hist || smem_votes) {
-        // lowest class index with the strictly largest count (normal_distributions.c:114-120)
-        __syncwarp();
-        const unsigned *h = smem_votes ? s_h[warp] : hist + ((size_t)b * vcap + v) * nbins;
-        unsigned best = 0; int bc = 0x7fffffff;
-        for (int j = lane; j < nbins; j += 32) { const unsigned x = h[j]; if (x > best) { best = x; bc = j; } }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-            if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
-        }
-        if (lane == 0) cls[(size_t)b * vcap + v] = (uint16_t)(best > 0 ? bc : 0);
+}
+
+// Statistics of the light voxels (fewer than kHeavyVoxel points: about 1040 of a scan's 1060 voxels, half of its
+// points): one THREAD per voxel runs the literal recurrence of normal_distributions.c:76-104, so a warp advances 32
+// voxels per instruction instead of one.  vox_order is bucketed by size, so the voxels of a warp have similar
+// lengths.  The divisions by the running count share one reciprocal per point (see div_by_count).
+// grid (ceil(vcap/128), B), block 128.
+template <typename T>
+__global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restrict__ states, unsigned vcap, long N,
+                                                     const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
+                                                     const unsigned *__restrict__ vox_order,
+                                                     double *__restrict__ mean, double *__restrict__ cov) {
+    const int b = blockIdx.y;
+    const CloudState &s = states[b];
+    if (s.status != 0) return;
+    const unsigned idx = s.n_heavy + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.V) return;
+    const unsigned v = vox_order[(size_t)b * vcap + idx];
+    const unsigned st = vox_start[(size_t)b * (vcap + 1) + v], en = vox_start[(size_t)b * (vcap + 1) + v + 1];
+    const T *p = sorted + ((size_t)b * N + st) * 3;
+    double mu0 = 0, mu1 = 0, mu2 = 0, m20 = 0, m21 = 0, m22 = 0, c01 = 0, c02 = 0, c12 = 0;
+    const unsigned n = en - st;
+    for (unsigned k = 0; k < n; k++) {
+        const double x0 = (double)p[(size_t)k * 3 + 0], x1 = (double)p[(size_t)k * 3 + 1], x2 = (double)p[(size_t)k * 3 + 2];
+        const double c = (double)(k + 1);
+        const double rh = 1.0 / c;
+        const double rl = fma(-c, rh, 1.0) * rh;
+        // RN(u / c): reciprocal form inside its proven range, IEEE division otherwise
+#define QDIV(u) ((fabs(u) > 1e-250 && fabs(u) < 1e290) ? fma((u), rh, (u) * rl) : (u) / c)
+        // j = 0
+        const double d0 = x0 - mu0;
+        const double o0 = mu0;
+        mu0 = mu0 + QDIV(d0);
+        m20 += (x0 - o0) * (x0 - mu0);
+        { const double u = (x0 - mu0) * (x1 - mu1); c01 += QDIV(u); if (c01 != c01) c01 = 0.0; }   // mu1, mu2 still old
+        { const double u = (x0 - mu0) * (x2 - mu2); c02 += QDIV(u); if (c02 != c02) c02 = 0.0; }
+        // j = 1
+        const double d1 = x1 - mu1;
+        const double o1 = mu1;
+        mu1 = mu1 + QDIV(d1);
+        m21 += (x1 - o1) * (x1 - mu1);
+        { const double u = (x1 - mu1) * (x2 - mu2); c12 += QDIV(u); if (c12 != c12) c12 = 0.0; }
+        // j = 2
+        const double d2 = x2 - mu2;
+        const double o2 = mu2;
+        mu2 = mu2 + QDIV(d2);
+        m22 += (x2 - o2) * (x2 - mu2);
+#undef QDIV
     }
+    const double cn = (double)n;
+    double v0 = m20 / cn, v1 = m21 / cn, v2 = m22 / cn;
+    if (v0 != v0) v0 = 0.0;
+    if (v1 != v1) v1 = 0.0;
+    if (v2 != v2) v2 = 0.0;
+    double *mo = mean + ((size_t)b * vcap + v) * 3;
+    mo[0] = mu0; mo[1] = mu1; mo[2] = mu2;
+    double *co = cov + ((size_t)b * vcap + v) * 9;
+    co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
+}
+
+// Label vote (normal_distributions.c:107-121): most frequent class of the voxel, lowest index on ties.  One warp
+// per voxel over its (sorted) labels, counts in shared memory; wide label sets were counted by k_scatter's global
+// atomics and only need the arg-max here.  grid (B, ceil(vcap/4)), block 128.
+__global__ void __launch_bounds__(128) k_votes(const CloudState *__restrict__ states, unsigned vcap, long N,
+                                               const uint16_t *__restrict__ sorted_labels, const unsigned *__restrict__ vox_start,
+                                               const unsigned *__restrict__ hist, int nbins, uint16_t *__restrict__ cls) {
+    const int b = blockIdx.x;
+    const CloudState &s = states[b];
+    if (s.status != 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned v = blockIdx.y * 4 + warp;
+    if (v >= s.V) return;
+    __shared__ unsigned s_h[4][kSmemLabelBins];
+    const unsigned *h;
+    if (hist) {
+        h = hist + ((size_t)b * vcap + v) * nbins;
+    } else {
+        for (int j = lane; j < kSmemLabelBins; j += 32) s_h[warp][j] = 0;
+        __syncwarp();
+        const unsigned st = vox_start[(size_t)b * (vcap + 1) + v], en = vox_start[(size_t)b * (vcap + 1) + v + 1];
+        const uint16_t *sl = sorted_labels + (size_t)b * N;
+        for (unsigned i = st + lane; i < en; i += 32) {
+            const unsigned l = sl[i];
+            if (l < (unsigned)nbins) atomicAdd(&s_h[warp][l], 1u);
+        }
+        __syncwarp();
+        h = s_h[warp];
+    }
+    unsigned best = 0; int bc = 0x7fffffff;
+    for (int j = lane; j < nbins; j += 32) { const unsigned x = h[j]; if (x > best) { best = x; bc = j; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+        if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
+    }
+    if (lane == 0) cls[(size_t)b * vcap + v] = (uint16_t)(best > 0 ? bc : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1141,10 +1219,28 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         DBG("k_scatter");
     }
     tm.mark(ST_STATS, st);
-    k_stats<T><<<dim3(B, (vcap + 3) / 4), 128, 0, st>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order,
-                                                       labels ? w.sorted_labels : nullptr, wide_labels ? w.hist : nullptr, nbins,
-                                                       w.mean, w.cov, w.cls);
-    DBG("k_stats");
+    // heavy voxels (a warp each; at most N / kHeavyVoxel of them per cloud), then the light ones (a thread each)
+    {
+        unsigned max_heavy = (unsigned)(N / kHeavyVoxel) + 1;
+        if (max_heavy > vcap) max_heavy = vcap;
+        // the light kernel and the votes are independent of the heavy one: fork them onto the side stream so the
+        // latency-bound tails overlap
+        if (!w.side) { CK(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&w.ev_join, cudaEventDisableTiming)); }
+        CK(cudaEventRecord(w.ev_fork, st));
+        CK(cudaStreamWaitEvent(w.side, w.ev_fork, 0));
+        k_stats<T><<<dim3(B, (max_heavy + 3) / 4), 128, 0, st>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order,
+                                                               w.mean, w.cov);
+        DBG("k_stats");
+        k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, 0, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start,
+                                                                         w.vox_order, w.mean, w.cov);
+        if (labels) {
+            k_votes<<<dim3(B, (vcap + 3) / 4), 128, 0, w.side>>>(w.states, vcap, N, w.sorted_labels, w.vox_start,
+                                                                wide_labels ? w.hist : nullptr, nbins, w.cls);
+        }
+        CK(cudaEventRecord(w.ev_join, w.side));
+        CK(cudaStreamWaitEvent(st, w.ev_join, 0));
+        DBG("k_stats_light/k_votes");
+    }
     tm.mark(ST_KL, st);
     k_kl<<<dim3((vcap + 63) / 64, B), 64, 0, st>>>(w.states, vcap, w.bitmap, w.bitmap_stride, w.vox_cell, w.vox_n, w.cov,
                                                   w.cov_final, w.kl_div, w.kl_flag);
@@ -1166,7 +1262,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     }
     DBG("end");
     tm.mark(ST_COUNT, st);
-    count_launches(3 + 2 * kMaxGuessIterations + (N > 0 ? 2 : 0) + 4);
+    count_launches(3 + 2 * kMaxGuessIterations + (N > 0 ? 2 : 0) + 5 + (labels ? 1 : 0));
     if (tm.enabled) {
         CK(cudaEventSynchronize(tm.ev[ST_COUNT]));
         for (int i = 0; i < ST_COUNT; i++) { float ms = 0; cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]); tm.ms[i] += ms; }
