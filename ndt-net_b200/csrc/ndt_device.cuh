@@ -24,7 +24,7 @@ constexpr int kCountPointsPerCta = 4096;
 constexpr int kRankTile = 2048;                // points per rank tile (one warp walks one tile in order)
 constexpr unsigned kDropped = 0xFFFFFFFFu;
 constexpr int kSmemLabelBins = 64;
-constexpr unsigned kHeavyVoxel = 512;         // voxels with at least this many points get a warp each in k_stats             // label sets up to this size are voted in shared memory by k_stats
+constexpr unsigned kHeavyVoxel = 512;           // voxels with at least this many points get a warp each in k_stats
 
 // Per-cloud search/grid state (device resident, one per cloud).
 struct CloudState {

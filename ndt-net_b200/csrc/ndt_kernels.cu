@@ -316,11 +316,14 @@ __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N,
     const long chunk = N / kWorkers;
     const long n_used = chunk * kWorkers;
     const GridCtx gc = make_grid_ctx(s);
+    const bool risky = s.risky != 0;
     for (long base = begin; base < tend; base += 32) {
         const long i = base + lane;
         unsigned slot = kDropped;
         unsigned id = 0;
-        if (i < n_used && (unsigned)i < s.fail[i / chunk]) {
+        bool live = i < n_used;
+        if (live && risky) live = (unsigned)i < s.fail[(unsigned long)i / (unsigned long)chunk];   // A4: only risky grids drop points
+        if (live) {
             if (point_cell<T>(p, i, gc, id)) {
                 const uint2 w = bm[id >> 5];
                 slot = w.y + __popc(w.x & ((1u << (id & 31)) - 1u));
@@ -364,10 +367,16 @@ __global__ void __launch_bounds__(1024) k_offsets(CloudState *__restrict__ state
         const unsigned v = base + tid;
         unsigned acc = 0;
         if (v < V) {
-            for (int t = 0; t < ntiles; t++) {
-                const unsigned c = tc[(size_t)t * vcap + v];
-                tc[(size_t)t * vcap + v] = acc;
-                acc += c;
+            // 8 independent loads in flight per thread (the running sum is the only dependency)
+            for (int t0 = 0; t0 < ntiles; t0 += 8) {
+                unsigned c[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) c[j] = t0 + j < ntiles ? tc[(size_t)(t0 + j) * vcap + v] : 0u;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (t0 + j < ntiles) tc[(size_t)(t0 + j) * vcap + v] = acc;
+                    acc += c[j];
+                }
             }
             vox_n[(size_t)b * vcap + v] = acc;
         }
