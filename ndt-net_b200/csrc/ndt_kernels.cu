@@ -12,9 +12,13 @@
 #include <cstdlib>
 #include <cstring>
 
+#ifndef NDT_STATS_WARPS
+#define NDT_STATS_WARPS 4
+#endif
 #ifndef NDT_STATS_MIN_BLOCKS
 #define NDT_STATS_MIN_BLOCKS 4
 #endif
+constexpr int kStatsWarps = NDT_STATS_WARPS;   // warps (= heavy voxels) per CTA of k_stats
 
 namespace ndt {
 
@@ -473,7 +477,7 @@ __device__ __forceinline__ double div_by_count(double d, double cnt) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128, NDT_STATS_MIN_BLOCKS) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
+__global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
                                                const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                                const unsigned *__restrict__ vox_order,
                                                double *__restrict__ mean, double *__restrict__ cov) {
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(128, NDT_STATS_MIN_BLOCKS) k_stats(const Cloud
     const CloudState &s = states[b];
     if (s.status != 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned idx = blockIdx.y * 4 + warp;
+    const unsigned idx = blockIdx.y * kStatsWarps + warp;
     if (idx >= s.n_heavy) return;                 // lighter voxels: k_stats_light
     const unsigned v = vox_order[(size_t)b * vcap + idx];
     const unsigned st = vox_start[(size_t)b * (vcap + 1) + v], en = vox_start[(size_t)b * (vcap + 1) + v + 1];
@@ -489,10 +493,10 @@ __global__ void __launch_bounds__(128, NDT_STATS_MIN_BLOCKS) k_stats(const Cloud
 
     // point-major layouts: in phase A the chain lanes 0-2 (accumulator lanes 0-5) read consecutive banks and
     // every other lane reads the same word as its neighbour (broadcast): no bank conflicts on the paced path
-    __shared__ double2 s_x[4][32][3];      // per point, per dimension: {x, x * rl}
-    __shared__ double2 s_r[4][32];         // 1 / count as an unevaluated sum {rh, rl} (~106 bits)
-    __shared__ double s_mu[4][33][3];      // means: [0][.] before the round's first point, [k+1][.] after point k
-    __shared__ double s_t[4][2][32][6];    // terms of the round (double buffered): m2 x3, c01, c02, c12
+    __shared__ double2 s_x[kStatsWarps][32][3];      // per point, per dimension: {x, x * rl}
+    __shared__ double2 s_r[kStatsWarps][32];         // 1 / count as an unevaluated sum {rh, rl} (~106 bits)
+    __shared__ double s_mu[kStatsWarps][33][3];      // means: [0][.] before the round's first point, [k+1][.] after point k
+    __shared__ double s_t[kStatsWarps][2][32][6];    // terms of the round (double buffered): m2 x3, c01, c02, c12
     double2(*xs)[3] = s_x[warp];
     double2 *rs = s_r[warp];
     double(*mus)[3] = s_mu[warp];
@@ -1237,8 +1241,8 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         if (!w.side) { CK(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&w.ev_join, cudaEventDisableTiming)); }
         CK(cudaEventRecord(w.ev_fork, st));
         CK(cudaStreamWaitEvent(w.side, w.ev_fork, 0));
-        k_stats<T><<<dim3(B, (max_heavy + 3) / 4), 128, 0, st>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order,
-                                                               w.mean, w.cov);
+        k_stats<T><<<dim3(B, (max_heavy + kStatsWarps - 1) / kStatsWarps), 32 * kStatsWarps, 0, st>>>(
+            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov);
         DBG("k_stats");
         k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, 0, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start,
                                                                          w.vox_order, w.mean, w.cov);
