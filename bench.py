@@ -75,6 +75,9 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 8.0:     # nvidia-smi takes a moment to print its first sample
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
@@ -82,9 +85,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """Samples from here on belong to the timed region."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc:
+            time.sleep(0.15)
             self.proc.terminate()
+        self.rows = self.rows[max(getattr(self, "first", 0) - 1, 0):]
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -252,6 +261,7 @@ def run_ours(args):
         step_device(i); step_host(i)
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.mark()
     launches0 = L.ndnet_b200_launch_count()
     ms = timed(step_device, args.steps)
     launches = L.ndnet_b200_launch_count() - launches0
