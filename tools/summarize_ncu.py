@@ -68,8 +68,50 @@ def kernel(rep, name, batch, out):
     print("wrote", out, "traffic", traffic)
 
 
-if __name__ == "__main__":
+def _main():
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
-    else:
+    elif sys.argv[1] == "kernel":
         kernel(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
+
+
+def table(rep, out, title):
+    """One row per captured launch of a multi-kernel report."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    H = rows[0]
+    ix = {h: i for i, h in enumerate(H)}
+    cols = [("gpu__time_duration.sum", "dur"), ("launch__grid_size", "grid"), ("launch__registers_per_thread", "regs"),
+            ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
+            ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+            ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
+            ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
+            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe %"),
+            ("sm__inst_executed.avg.per_cycle_elapsed", "IPC"), ("smsp__inst_executed.sum", "warp instr")]
+    with open(out, "w") as f:
+        f.write(f"# {title}\n\nfrom `{os.path.basename(rep)}` (`ncu --set full --clock-control none`, one row per captured launch; units as ncu "
+                "reports them, row 2 of the raw page).\n\n")
+        f.write("| kernel | " + " | ".join(c[1] for c in cols) + " |\n|---|" + "---:|" * len(cols) + "\n")
+        units = rows[1]
+        for r in rows[2:]:
+            name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "")
+            vals = []
+            for k, _ in cols:
+                if k in ix:
+                    v, u = r[ix[k]], units[ix[k]]
+                    try:
+                        v = f"{float(v.replace(',', '')):.4g}"
+                    except ValueError:
+                        pass
+                    vals.append(f"{v} {u}".strip() if u not in ("%", "") else v)
+                else:
+                    vals.append("-")
+            f.write(f"| `{name}` | " + " | ".join(vals) + " |\n")
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "table":
+        table(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        _main()
