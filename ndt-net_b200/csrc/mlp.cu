@@ -160,55 +160,54 @@ __global__ void __launch_bounds__(128) k_trunk_l1(const float *__restrict__ feat
 }
 
 // y[b][o] = act(W[o] . x[b] + bias[o]) for B rows (the per-cloud FC stacks, ndtnet.py:54-60,189-191): a small
-// fp32 GEMM tiled through shared memory.  Block = 32 outputs x 32 batch rows; lane = batch row, each warp owns 4
-// outputs; the x tile is stored transposed so both operands are read conflict-free (w is a broadcast).
-// grid (ceil(out/32), ceil(B/32)), block 256.
+// fp32 GEMM tiled through shared memory.  Block = 8 outputs x 32 batch rows (one output per warp, lane = batch
+// row) so that even a 32-scan chunk spreads a 512-wide layer over 64 CTAs; the x tile is stored transposed so both
+// operands are read conflict-free (w is a broadcast).  grid (ceil(out/8), ceil(B/32)), block 256.
 __global__ void __launch_bounds__(256) k_fc(const float *__restrict__ W, const float *__restrict__ bias, const void *__restrict__ xin,
                                             int ldx, int decode, float *__restrict__ y, int ldy, int B, int in, int out, int relu,
                                             int identity_dim, __nv_bfloat16 *__restrict__ y_t /*[B][dim][dim] transposed bf16*/) {
     __shared__ float sx[128][33];
-    __shared__ float sw[32][129];
+    __shared__ float sw[8][129];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int o0 = blockIdx.x * 8, r0 = blockIdx.y * 32;
+    float acc = 0.f;
     for (int k0 = 0; k0 < in; k0 += 128) {
 #pragma unroll 4
         for (int i = threadIdx.x; i < 32 * 128; i += 256) {
             const int r = i >> 7, k = i & 127;
-            float xv = 0.f, wv = 0.f;
-            if (k0 + k < in) {
-                if (r0 + r < B) {
-                    if (decode) xv = dec_f32(((const unsigned *)xin)[(size_t)(r0 + r) * ldx + k0 + k]);
-                    else xv = ((const float *)xin)[(size_t)(r0 + r) * ldx + k0 + k];
-                }
-                if (o0 + r < out) wv = W[(size_t)(o0 + r) * in + k0 + k];
+            float xv = 0.f;
+            if (k0 + k < in && r0 + r < B) {
+                if (decode) xv = dec_f32(((const unsigned *)xin)[(size_t)(r0 + r) * ldx + k0 + k]);
+                else xv = ((const float *)xin)[(size_t)(r0 + r) * ldx + k0 + k];
             }
             sx[k][r] = xv;
-            sw[r][k] = wv;
+        }
+#pragma unroll
+        for (int i = threadIdx.x; i < 8 * 128; i += 256) {
+            const int r = i >> 7, k = i & 127;
+            sw[r][k] = (k0 + k < in && o0 + r < out) ? W[(size_t)(o0 + r) * in + k0 + k] : 0.f;
         }
         __syncthreads();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
-        for (int k = 0; k < 128; k++) {
-            const float xv = sx[k][lane];
-#pragma unroll
-            for (int j = 0; j < 4; j++) acc[j] += sw[warp * 4 + j][k] * xv;
+        for (int k = 0; k < 128; k += 4) {
+            a0 += sw[warp][k] * sx[k][lane];
+            a1 += sw[warp][k + 1] * sx[k + 1][lane];
+            a2 += sw[warp][k + 2] * sx[k + 2][lane];
+            a3 += sw[warp][k + 3] * sx[k + 3][lane];
         }
+        acc += (a0 + a1) + (a2 + a3);
         __syncthreads();
     }
-    const int row = r0 + lane;
-    if (row >= B) return;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int o = o0 + warp * 4 + j;
-        if (o >= out) continue;
-        float v = acc[j] + (bias ? bias[o] : 0.f);
-        if (identity_dim > 0 && (o / identity_dim) == (o % identity_dim)) v += 1.f;   // + eye (ndtnet.py:59)
-        if (relu) v = fmaxf(v, 0.f);
-        y[(size_t)row * ldy + o] = v;
-        if (y_t) {
-            const int i = o / identity_dim, jj = o % identity_dim;
-            y_t[(size_t)row * identity_dim * identity_dim + (size_t)jj * identity_dim + i] = __float2bfloat16(v);
-        }
+    const int row = r0 + lane, o = o0 + warp;
+    if (row >= B || o >= out) return;
+    float v = acc + (bias ? bias[o] : 0.f);
+    if (identity_dim > 0 && (o / identity_dim) == (o % identity_dim)) v += 1.f;   // + eye (ndtnet.py:59)
+    if (relu) v = fmaxf(v, 0.f);
+    y[(size_t)row * ldy + o] = v;
+    if (y_t) {
+        const int i = o / identity_dim, jj = o % identity_dim;
+        y_t[(size_t)row * identity_dim * identity_dim + (size_t)jj * identity_dim + i] = __float2bfloat16(v);
     }
 }
 
@@ -489,7 +488,7 @@ struct Fwd {
     void fc(const float *W, const float *bias, const void *x, int ldx, bool decode, float *y, int ldy, int in, int out, bool relu,
             int identity_dim = 0, __nv_bfloat16 *y_t = nullptr) {
         if (!ok) return;
-        dim3 grid((out + 31) / 32, (B + 31) / 32);
+        dim3 grid((out + 7) / 8, (B + 31) / 32);
         k_fc<<<grid, 256, 0, st>>>(W, bias, x, ldx, decode ? 1 : 0, y, ldy, B, in, out, relu ? 1 : 0, identity_dim, y_t);
     }
 };
