@@ -340,8 +340,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="scans per GPU per step")
-    ap.add_argument("--lanes", type=int, default=4, help="pipeline lanes (internal streams) of the infer calls")
-    ap.add_argument("--chunk", type=int, default=32, help="scans per pipeline chunk")
+    ap.add_argument("--lanes", type=int, default=8, help="pipeline lanes (internal streams) of the infer calls")
+    ap.add_argument("--chunk", type=int, default=64, help="scans per pipeline chunk")
     ap.add_argument("--cpu-clouds", type=int, default=48, help="scans in the cpu_baseline sample")
     ap.add_argument("--ref-clouds", type=int, default=8, help="scans per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -265,7 +265,7 @@ extern "C" int ndnet_b200_downsample_batch_host(ndnet_b200_ctx *c, const void *p
 
 // ---- pipelined whole-path inference ------------------------------------------------------------
 extern "C" int ndnet_b200_set_pipeline(ndnet_b200_ctx *c, int lanes, int chunk) {
-    if (!c || lanes < 1 || lanes > 8 || chunk < 1) return -200;
+    if (!c || lanes < 1 || lanes > 32 || chunk < 1) return -200;
     if (!c->lanes.empty() && (int)c->lanes.size() != lanes) return -203;   // lanes are fixed once created
     c->n_lanes = lanes; c->chunk = chunk;
     return 0;

@@ -463,15 +463,21 @@ struct Fwd {
         if (!ok) *err = "gemm launch failed";
         gemm_launches++;
     }
-    // weights [C][K] x activations [B][P][K] -> max over points per cloud, encoded [B][ldg]
+    // weights [C][K=128] x activations [B][P][128] -> max over points per cloud, encoded [B][ldg]
     void chmax(const __nv_bfloat16 *w, int C, const __nv_bfloat16 *act, int K, const float *bias, bool relu, unsigned *gmax, int ldg) {
         if (!ok) return;
-        CUtensorMap ma, mb;
-        if (!make_map(&ma, w, K, C, 1, 128) || !make_map(&mb, act, K, P, B, 128)) { ok = false; *err = "cuTensorMapEncodeTiled failed"; return; }
-        GemmArgs g{}; g.K = K; g.P = P; g.a_batched = 0; g.b_batched = 1; g.mode = MODE_CHMAX; g.relu = relu ? 1 : 0; g.n_valid = C;
-        g.bias = bias; g.gmax = gmax; g.ldg = ldg;
-        dim3 grid((C + 127) / 128, (P + 127) / 128, B);
-        ok = launch_gemm<128, 2>(ma, mb, g, grid, st);
+        if (K != 128) { ok = false; *err = "k_gemm_chmax expects K = 128"; return; }
+        CUtensorMap mw, mx;
+        if (!make_map(&mw, w, K, C, 1, 128) || !make_map(&mx, act, K, P, B, 64)) { ok = false; *err = "cuTensorMapEncodeTiled failed"; return; }
+        GemmArgs g{}; g.K = K; g.P = P; g.mode = MODE_CHMAX; g.relu = relu ? 1 : 0; g.n_valid = C; g.bias = bias; g.gmax = gmax; g.ldg = ldg;
+        static bool attr = false;
+        if (!attr) {
+            if (cudaFuncSetAttribute(k_gemm_chmax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChmaxSmemBytes) != cudaSuccess) { ok = false; *err = "smem attribute"; return; }
+            attr = true;
+        }
+        dim3 grid((C + 511) / 512, B);
+        k_gemm_chmax<<<grid, kGemmThreads, kChmaxSmemBytes, st>>>(mw, mx, g);
+        ok = cudaGetLastError() == cudaSuccess;
         if (!ok) *err = "gemm launch failed";
         gemm_launches++;
     }

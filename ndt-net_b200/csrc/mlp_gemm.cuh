@@ -281,4 +281,138 @@ k_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtenso
     if (warp == 5) ptx::tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_gemm_chmax: the max-pooled layers (conv 128 -> 1024 / F followed by max over the points of a cloud,
+// ndtnet.py:47-50,161,186,224).  D[channel, point] = W[channel, :] . act[point, :], K = 128.
+//
+// One CTA owns one cloud and a group of up to 4 channel tiles (512 channels).  The group's weights (4 x 128 x 128
+// bf16 = 128 KB) are loaded ONCE and stay in shared memory; the cloud's activations stream through a 3-stage TMA
+// ring in tiles of 64 points (16 KB), so every activation byte is read C/512 times instead of C/128 times and the
+// loop is paced by the tensor pipe, not by L2.  The accumulators (4 x 64 columns) are double buffered in TMEM:
+// while tcgen05.mma fills one buffer the four epilogue warps drain the other with tcgen05.ld into a per-thread
+// running max (thread = channel).  Each (cloud, channel) maximum is produced by exactly one thread: plain store,
+// no atomics.  grid (ceil(C/512), B), block 192.
+// ------------------------------------------------------------------------------------------------
+constexpr int kChmaxStages = 3;
+constexpr size_t kChmaxSmemBytes = 4 * 32768 + kChmaxStages * 16384 + 1024 + 256;
+
+__global__ void __launch_bounds__(kGemmThreads)
+k_gemm_chmax(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const GemmArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sW = smem;                                   // [tile 4][kb 2][128 rows x 128 B]
+    uint8_t *sX = smem + 4 * 32768;                       // [stage][kb 2][64 rows x 128 B]
+    uint64_t *bars = (uint64_t *)(sX + kChmaxStages * 16384);
+    uint64_t *w_full = bars, *x_full = bars + 1, *x_empty = x_full + kChmaxStages;
+    uint64_t *t_full = x_empty + kChmaxStages, *t_empty = t_full + 2;
+    uint32_t *tmem_slot = (uint32_t *)(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int ch0 = blockIdx.x * 512;
+    int ntile = (args.n_valid - ch0 + 127) / 128; if (ntile > 4) ntile = 4;
+    const int npt = (args.P + 63) / 64;
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(w_full, 1);
+        for (int s = 0; s < kChmaxStages; s++) { ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], 1); }
+        for (int i = 0; i < 2; i++) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&mapW); ptx::prefetch_tmap(&mapX); }
+    if (warp == 5) ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            ptx::mbar_expect_tx(w_full, (uint32_t)ntile * 32768u);
+            for (int ct = 0; ct < ntile; ct++)
+                for (int kb = 0; kb < 2; kb++)
+                    ptx::tma_load_3d(&mapW, w_full, sW + (size_t)(ct * 2 + kb) * 16384, kb * 64, ch0 + ct * 128, 0);
+            for (int t = 0; t < npt; t++) {
+                const int s = t % kChmaxStages;
+                const uint32_t ph = (uint32_t)(t / kChmaxStages) & 1u;
+                ptx::mbar_wait(&x_empty[s], ph ^ 1u);
+                ptx::mbar_expect_tx(&x_full[s], 16384u);
+                ptx::tma_load_3d(&mapX, &x_full[s], sX + (size_t)s * 16384, 0, t * 64, b);
+                ptx::tma_load_3d(&mapX, &x_full[s], sX + (size_t)s * 16384 + 8192, 64, t * 64, b);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+            ptx::mbar_wait(w_full, 0);
+            for (int t = 0; t < npt; t++) {
+                const int s = t % kChmaxStages, buf = t & 1;
+                ptx::mbar_wait(&x_full[s], (uint32_t)(t / kChmaxStages) & 1u);
+                ptx::mbar_wait(&t_empty[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);     // the epilogue drained this buffer
+                ptx::tc_fence_after();
+                for (int ct = 0; ct < ntile; ct++) {
+                    const uint32_t d = tmem_base + (uint32_t)(buf * 256 + ct * 64);
+#pragma unroll
+                    for (int kb = 0; kb < 2; kb++) {
+                        const uint64_t da = make_kmajor_sw128_desc(ptx::smem_u32(sW + (size_t)(ct * 2 + kb) * 16384));
+                        const uint64_t db = make_kmajor_sw128_desc(ptx::smem_u32(sX + (size_t)s * 16384 + (size_t)kb * 8192));
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; k4++)
+                            ptx::umma_bf16(d, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc, (kb | k4) ? 1u : 0u);
+                    }
+                }
+                ptx::umma_commit(&x_empty[s]);
+                ptx::umma_commit(&t_full[buf]);
+            }
+        }
+    } else {
+        // ---- epilogue: thread = channel (TMEM lane); running max over the cloud's points per channel tile
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int t = 0; t < npt; t++) {
+            const int buf = t & 1;
+            int valid = args.P - t * 64; if (valid > 64) valid = 64;
+            ptx::mbar_wait(&t_full[buf], (uint32_t)(t >> 1) & 1u);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 256);
+#pragma unroll
+            for (int ct = 0; ct < 4; ct++) {
+                if (ct < ntile) {
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        if (c0 < valid) {
+                            uint32_t v[32];
+                            ptx::tmem_ld32(taddr + (uint32_t)(ct * 64 + c0), v);
+                            ptx::tmem_ld_wait();
+                            if (c0 + 32 <= valid) {
+#pragma unroll
+                                for (int j = 0; j < 32; j++) best[ct] = fmaxf(best[ct], __uint_as_float(v[j]));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; j++) if (c0 + j < valid) best[ct] = fmaxf(best[ct], __uint_as_float(v[j]));
+                            }
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(&t_empty[buf])) : "memory");
+            }
+        }
+#pragma unroll
+        for (int ct = 0; ct < 4; ct++) {
+            const int ch = ch0 + ct * 128 + warp * 32 + lane;
+            if (ct < ntile && ch < args.n_valid) {
+                float r = best[ct] + (args.bias ? args.bias[ch] : 0.f);
+                if (args.relu) r = fmaxf(r, 0.f);
+                args.gmax[(size_t)b * args.ldg + ch] = enc_f32(r);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace mlp
