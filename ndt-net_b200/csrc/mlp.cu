@@ -457,9 +457,17 @@ struct Fwd {
         GemmArgs g{}; g.K = K; g.P = P; g.a_batched = 1; g.b_batched = w_batched ? 1 : 0; g.mode = MODE_ROWS; g.relu = relu ? 1 : 0; g.n_valid = N;
         g.bias = bias; g.cbias = cbias; g.ldcb = ldcb; g.out = out; g.ldo = N;
         dim3 grid((N + BN - 1) / BN, (P + 127) / 128, B);
-        if (BN == 256) ok = launch_gemm<256, 3>(ma, mb, g, grid, st);
-        else if (BN == 128) ok = launch_gemm<128, 2>(ma, mb, g, grid, st);
-        else ok = launch_gemm<64, 2>(ma, mb, g, grid, st);
+        // one k-block (K = 64): a single stage keeps the CTA at 24-48 KB of shared memory so several CTAs share an SM
+        // and one CTA's epilogue overlaps another's load/MMA; deeper K: two stages (still 2 CTAs per SM at BN = 256)
+        if (K <= 64) {
+            if (BN == 256) ok = launch_gemm<256, 1>(ma, mb, g, grid, st);
+            else if (BN == 128) ok = launch_gemm<128, 1>(ma, mb, g, grid, st);
+            else ok = launch_gemm<64, 1>(ma, mb, g, grid, st);
+        } else {
+            if (BN == 256) ok = launch_gemm<256, 2>(ma, mb, g, grid, st);
+            else if (BN == 128) ok = launch_gemm<128, 2>(ma, mb, g, grid, st);
+            else ok = launch_gemm<64, 2>(ma, mb, g, grid, st);
+        }
         if (!ok) *err = "gemm launch failed";
         gemm_launches++;
     }
