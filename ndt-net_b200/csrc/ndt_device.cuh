@@ -237,7 +237,7 @@ __device__ __forceinline__ void lu3_invert(const double lu[9], int perm, double 
         t[6] *= t[8];
         t[7] *= t[8];
     }
-    const int q0 = perm & 3, q1 = (perm >> 2) & 3, q2 = (perm >> 4) & 3;
+    const int q0 = perm & 3, q1 = (perm >> 2) & 3;          // the third entry is whatever is left
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         // inv[i][perm[k]] = t[i][k]

@@ -313,10 +313,6 @@ __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N,
     __syncwarp();
     const T *p = pts + (size_t)b * N * 3;
     const uint2 *bm = bitmap + (size_t)b * bitmap_stride;
-    const double vs = s.guess;
-    const double rv = 1.0 / vs;
-    const double off[3] = {s.off[0], s.off[1], s.off[2]};
-    const int len[3] = {s.len[0], s.len[1], s.len[2]};
     const long chunk = N / kWorkers;
     const long n_used = chunk * kWorkers;
     const GridCtx gc = make_grid_ctx(s);

@@ -88,6 +88,13 @@ class NdtEngine:
             info = np.frombuffer(info_dev.cpu().numpy().tobytes(), dtype=_lib.INFO_DTYPE).copy()
         return NdtBatch(feat, out_lab, voxel, feat64, info)
 
+    def downsample_multiscale(self, points: torch.Tensor, num_desired_list, labels: torch.Tensor | None = None,
+                              num_classes: int = 0, **kw) -> list:
+        """Several n_desired_nds for the same clouds (the multiscale use of tools/train_multiscale.py:33-43,
+        BASELINE config 5: 4096 / 1024 / 256 per cloud).  Each resolution is an independent ndt_downsample, exactly as
+        the reference's dataset would run it; returns one NdtBatch per entry of `num_desired_list`."""
+        return [self.downsample(points, int(d), labels, num_classes, **kw) for d in num_desired_list]
+
     def downsample_host(self, points: np.ndarray | torch.Tensor, num_desired: int, labels=None, num_classes: int = 0,
                         nan_to_num: bool = True, out_feat: torch.Tensor | None = None):
         """HOST buffers in, HOST buffers out (H2D + kernels + D2H + sync inside the C call)."""

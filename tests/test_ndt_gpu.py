@@ -127,6 +127,19 @@ def test_fp64_batch_equals_fp32_batch_on_fp32_values(engine):
     assert torch.equal(a.voxel, b.voxel) and same_bits(a.feat64.cpu().numpy(), b.feat64.cpu().numpy())
 
 
+def test_multiscale_resolutions_match_oracle(engine):
+    """BASELINE config 5: n_desired_nds 4096 / 1024 / 256 for the same scan."""
+    from ndnet_b200.synth import lidar_cloud
+    pts = lidar_cloud(120000, 71)
+    outs = engine.downsample_multiscale(torch.from_numpy(pts).cuda()[None], [4096, 1024, 256], nan_to_num=False,
+                                        want_f64=True, want_voxel=True)
+    for d, out in zip([4096, 1024, 256], outs):
+        o = ndt_oracle.run(pts, d)
+        assert out.info[0]["status"] == o.ret == 0 and out.info[0]["num_out"] == d
+        assert np.array_equal(out.voxel[0].cpu().numpy(), o.out_voxel)
+        assert same_bits(out.feat64[0, :, :3].cpu().numpy(), o.out_pts) and same_bits(out.feat64[0, :, 3:].cpu().numpy(), o.out_cov)
+
+
 def test_golden_vectors_through_c_abi(engine):
     """The reference's own outputs (tests/golden, made from core_legacy/src by make_golden.py)."""
     g = np.load(GOLDEN)
