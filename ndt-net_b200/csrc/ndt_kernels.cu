@@ -477,199 +477,208 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
                                                const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                                const unsigned *__restrict__ vox_order,
                                                double *__restrict__ mean, double *__restrict__ cov) {
+    // Each warp runs TWO heavy voxels (neighbours in the size-ordered list, so of similar length) in lockstep: the
+    // three mean chains of voxel 0 sit on lanes 0-2, those of voxel 1 on lanes 3-5, the six running sums on lanes
+    // 0-5 / 6-11, so the paced instruction stream (phase A) is shared by both voxels.
     const int b = blockIdx.x;
     const CloudState &s = states[b];
     if (s.status != 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned idx = blockIdx.y * kStatsWarps + warp;
-    if (idx >= s.n_heavy) return;                 // lighter voxels: k_stats_light
-    const unsigned v = vox_order[(size_t)b * vcap + idx];
-    const unsigned st = vox_start[(size_t)b * (vcap + 1) + v], en = vox_start[(size_t)b * (vcap + 1) + v + 1];
-    const T *p = sorted + ((size_t)b * N + st) * 3;
+    const unsigned pair = blockIdx.y * kStatsWarps + warp;
+    if (pair * 2 >= s.n_heavy) return;            // lighter voxels: k_stats_light
+    unsigned vv[2], nn[2];
+    const T *pp[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const unsigned idx = pair * 2 + q;
+        if (idx < s.n_heavy) {
+            vv[q] = vox_order[(size_t)b * vcap + idx];
+            const unsigned st = vox_start[(size_t)b * (vcap + 1) + vv[q]], en = vox_start[(size_t)b * (vcap + 1) + vv[q] + 1];
+            nn[q] = en - st;
+            pp[q] = sorted + ((size_t)b * N + st) * 3;
+        } else { vv[q] = 0; nn[q] = 0; pp[q] = sorted; }
+    }
 
-    // point-major layouts: in phase A the chain lanes 0-2 (accumulator lanes 0-5) read consecutive banks and
-    // every other lane reads the same word as its neighbour (broadcast): no bank conflicts on the paced path
-    __shared__ double2 s_x[kStatsWarps][32][3];      // per point, per dimension: {x, x * rl}
-    __shared__ double2 s_r[kStatsWarps][32];         // 1 / count as an unevaluated sum {rh, rl} (~106 bits)
-    __shared__ double s_mu[kStatsWarps][33][3];      // means: [0][.] before the round's first point, [k+1][.] after point k
-    __shared__ double s_t[kStatsWarps][2][32][6];    // terms of the round (double buffered): m2 x3, c01, c02, c12
-    double2(*xs)[3] = s_x[warp];
+    // point-major layouts: in phase A the chain lanes (accumulator lanes) read consecutive banks and every other
+    // lane reads the same word as a neighbour (broadcast): no bank conflicts on the paced path
+    __shared__ double2 s_x[kStatsWarps][2][32][3];      // per voxel, point, dimension: {x, x * rl}
+    __shared__ double2 s_r[kStatsWarps][32];            // 1 / count as an unevaluated sum {rh, rl} (~106 bits), shared by both voxels
+    __shared__ double s_mu[kStatsWarps][2][33][3];      // means: [0][.] before the round's first point, [k+1][.] after point k
+    __shared__ double s_t[kStatsWarps][2][2][32][6];    // [buffer][voxel] terms of the round: m2 x3, c01, c02, c12
     double2 *rs = s_r[warp];
-    double(*mus)[3] = s_mu[warp];
 
-    const int cl = lane < 3 ? lane : 2;    // chain lane -> dimension
-    const int al = lane < 6 ? lane : 5;    // accumulator lane -> term
+    const int cq = lane < 6 ? lane / 3 : 1, cj = lane < 6 ? lane % 3 : 2;     // chain lane -> (voxel, dimension)
+    const int aq = lane < 12 ? lane / 6 : 1, at = lane < 12 ? lane % 6 : 5;   // accumulator lane -> (voxel, term)
+    const bool chain_lane = lane < 6, cov_lane = lane < 12 && at >= 3;
     double mu = 0.0, acc = 0.0;
-    if (lane < 3) mus[0][lane] = 0.0;
-    const unsigned n = en - st;
-    int prev_m = 0, buf = 0;
+    if (chain_lane) s_mu[warp][cq][0][cj] = 0.0;
+    const unsigned nmax = nn[0] > nn[1] ? nn[0] : nn[1];
+    int prev_m[2] = {0, 0};
+    int buf = 0;
     bool prev_chk = false;                 // previous round produced a non-finite term: add with the NaN rule
-    T nx0 = 0, nx1 = 0, nx2 = 0;           // the next round's point of this lane, fetched one round ahead
-#ifdef NDT_PROFILE_STATS
-    long long tL = 0, tA = 0, tB = 0, tS = clock64();
-#endif
-    for (unsigned base = 0; base < n; base += 32) {
-#ifdef NDT_PROFILE_STATS
-        long long c0 = clock64();
-#endif
-        const int m = (int)(n - base < 32u ? n - base : 32u);
-        double x0 = 0, x1 = 0, x2 = 0, c = 1.0, rh = 1.0, rl = 0.0;
-        if (base == 0 && lane < m) { nx0 = p[lane * 3 + 0]; nx1 = p[lane * 3 + 1]; nx2 = p[lane * 3 + 2]; }
-        if (lane < m) {
-            x0 = (double)nx0; x1 = (double)nx1; x2 = (double)nx2;
-            c = (double)(base + lane + 1);
-            rh = 1.0 / c;
-            rl = fma(-c, rh, 1.0) * rh;
-            rs[lane] = make_double2(rh, rl);
-            xs[lane][0] = make_double2(x0, x0 * rl);
-            xs[lane][1] = make_double2(x1, x1 * rl);
-            xs[lane][2] = make_double2(x2, x2 * rl);
-        }
-        if (base + 32 + lane < n) {          // issue the next round's global loads now; they land during phase A
-            const T *pn = p + (size_t)(base + 32 + lane) * 3;
-            nx0 = pn[0]; nx1 = pn[1]; nx2 = pn[2];
+    bool fin_mu = false, fin_acc = false;  // this lane's voxel is finished: its result is parked in mu_fin / acc_fin
+    double mu_fin = 0.0, acc_fin = 0.0;    // (the straight-line rounds of the longer voxel keep clobbering mu / acc)
+    T nx[2][3] = {{0, 0, 0}, {0, 0, 0}};   // the next round's point of this lane (per voxel), fetched one round ahead
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+        if ((unsigned)lane < nn[q]) { nx[q][0] = pp[q][lane * 3 + 0]; nx[q][1] = pp[q][lane * 3 + 1]; nx[q][2] = pp[q][lane * 3 + 2]; }
+
+    for (unsigned base = 0; base < nmax; base += 32) {
+        int m[2];
+        double x[2][3];
+#pragma unroll
+        for (int q = 0; q < 2; q++) m[q] = base >= nn[q] ? 0 : (int)(nn[q] - base < 32u ? nn[q] - base : 32u);
+        const double c = (double)(base + lane + 1);
+        const double rh = 1.0 / c;
+        const double rl = fma(-c, rh, 1.0) * rh;
+        rs[lane] = make_double2(rh, rl);
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) x[q][j] = (double)nx[q][j];
+            if (lane < m[q]) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) s_x[warp][q][lane][j] = make_double2(x[q][j], x[q][j] * rl);
+            }
+            if (base + 32 + lane < nn[q]) {      // issue the next round's global loads now; they land during phase A
+                const T *pn = pp[q] + (size_t)(base + 32 + lane) * 3;
+                nx[q][0] = pn[0]; nx[q][1] = pn[1]; nx[q][2] = pn[2];
+            }
         }
         __syncwarp();
-        // ---- A (this round's means) fused with C (previous round's running sums).  Per point the warp
-        //      issues only the dependency chain {d, t} -> q -> mu, one store and one add:
-        //      q = RN(d / count) is fma(d, rh, t) with t = (x - mu) * rl formed as fma(-mu, rl, x * rl) so that
-        //      it does not wait for d (see div_by_count for why the quotient is exact; the cancellation in t is
-        //      harmless while |d| >= 2^-22 |x|).  Whether every operand of the round was inside the proven
-        //      range is checked afterwards, in parallel, by phase B; if not, the round is redone with the IEEE
-        //      division.
-        const double(*tp)[6] = s_t[warp][buf ^ 1];
+        // ---- A (this round's means) fused with C (previous round's running sums).  Per point the warp issues only
+        //      the dependency chain {d, t} -> q -> mu, one store and one add: q = RN(d / count) is fma(d, rh, t) with
+        //      t = (x - mu) * rl formed as fma(-mu, rl, x * rl) so that it does not wait for d (see div_by_count for
+        //      why the quotient is exact; the cancellation in t is harmless while |d| >= 2^-22 |x|).  Whether every
+        //      operand of the round was inside the proven range is checked afterwards, in parallel, by phase B; if
+        //      not, the round is redone with the IEEE division.
+        const double2(*xs)[3] = s_x[warp][cq];
+        double(*mus)[3] = s_mu[warp][cq];
+        const double(*tp)[6] = s_t[warp][buf ^ 1][aq];
         const double mu_start = mu;
-#ifdef NDT_PROFILE_STATS
-        long long c1 = clock64(); tL += c1 - c0;
-#endif
-        if (!prev_chk && m == 32 && prev_m == 32) {
-            // full rounds (all but the first and last of a voxel): straight-line, no per-step predicates,
-            // operands of the next four points are fetched while the current four are on the chain
+        const int my_m = m[cq], my_pm = prev_m[aq];
+        if (!fin_mu && m[cq] == 0) { fin_mu = true; mu_fin = mu; }
+        if (!fin_acc && m[aq] == 0 && prev_m[aq] == 0) { fin_acc = true; acc_fin = acc; }
+        const bool full0 = m[0] == 32 && prev_m[0] == 32, done0 = m[0] == 0 && prev_m[0] == 0;
+        const bool full1 = m[1] == 32 && prev_m[1] == 32, done1 = m[1] == 0 && prev_m[1] == 0;
+        if (!prev_chk && (full0 || done0) && (full1 || done1)) {
+            // full rounds: straight-line, no per-step predicates, operands of the next four points are fetched
+            // while the current four are on the chain
             double2 xv[4], rv[4], xn[4], rn[4];
             double tv[4], tn[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { xv[j] = xs[j][cl]; rv[j] = rs[j]; tv[j] = tp[j][al]; }
+            for (int j = 0; j < 4; j++) { xv[j] = xs[j][cj]; rv[j] = rs[j]; tv[j] = tp[j][at]; }
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 4) {
                 if (k0 + 4 < 32) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { xn[j] = xs[k0 + 4 + j][cl]; rn[j] = rs[k0 + 4 + j]; tn[j] = tp[k0 + 4 + j][al]; }
+                    for (int j = 0; j < 4; j++) { xn[j] = xs[k0 + 4 + j][cj]; rn[j] = rs[k0 + 4 + j]; tn[j] = tp[k0 + 4 + j][at]; }
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const double d = xv[j].x - mu;
                     const double t = fma(-mu, rv[j].y, xv[j].y);
                     mu = mu + fma(d, rv[j].x, t);
-                    if (lane < 3) mus[k0 + j + 1][lane] = mu;
+                    if (chain_lane) mus[k0 + j + 1][cj] = mu;
                     acc += tv[j];
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) { xv[j] = xn[j]; rv[j] = rn[j]; tv[j] = tn[j]; }
             }
-        } else if (!prev_chk) {
-            for (int k0 = 0; k0 < m; k0 += 4) {
-                double2 xv[4], rv[4];
-                double tv[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) { const int k = (k0 + j) & 31; xv[j] = xs[k][cl]; rv[j] = rs[k]; tv[j] = tp[k][al]; }
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int k = k0 + j;
-                    if (k < m) {
-                        const double d = xv[j].x - mu;
-                        const double t = fma(-mu, rv[j].y, xv[j].y);
-                        mu = mu + fma(d, rv[j].x, t);
-                        if (lane < 3) mus[k + 1][lane] = mu;
-                    }
-                    if (k < prev_m) acc += tv[j];
-                }
-            }
-            for (int k = (m + 3) & ~3; k < prev_m; k++) acc += tp[k][al];   // last round shorter than the one before
         } else {
-            for (int k = 0; k < m; k++) {
-                const double d = xs[k][cl].x - mu;
-                mu = mu + fma(d, rs[k].x, fma(-mu, rs[k].y, xs[k][cl].y));
-                if (lane < 3) mus[k + 1][lane] = mu;
-            }
-            for (int k = 0; k < prev_m; k++) {
-                const double a2 = acc + tp[k][al];
-                acc = (lane >= 3 && a2 != a2) ? 0.0 : a2;                   // NaN -> 0 (normal_distributions.c:98-100)
-            }
-        }
-        __syncwarp();
-#ifdef NDT_PROFILE_STATS
-        long long c2 = clock64(); tA += c2 - c1;
-#endif
-        // ---- B: per-point terms, all lanes in parallel; also validates the operands of the round
-        bool redone = false;
-        while (true) {
-            bool bad = false, nonfinite = false;
-            if (lane < m) {
-                const double o0 = mus[lane][0], o1 = mus[lane][1], o2 = mus[lane][2];
-                const double n0 = mus[lane + 1][0], n1 = mus[lane + 1][1], n2 = mus[lane + 1][2];
-                const double d0 = x0 - o0, d1 = x1 - o1, d2 = x2 - o2;          // the chain's d, bit for bit
-                const double a0 = fabs(d0), a1 = fabs(d1), a2 = fabs(d2);
-                bad = !(a0 > 1e-250 && a0 < 1e290 && a0 * 4194304.0 >= fabs(x0)) ||
-                      !(a1 > 1e-250 && a1 < 1e290 && a1 * 4194304.0 >= fabs(x1)) ||
-                      !(a2 > 1e-250 && a2 < 1e290 && a2 * 4194304.0 >= fabs(x2));
-                double(*t)[6] = s_t[warp][buf];
-                const double e0 = x0 - n0, e1 = x1 - n1;
-                const double t0 = d0 * e0, t1 = d1 * e1, t2 = d2 * (x2 - n2);
-                // (x_j - new_j)(x_k - old_k) / count: mu_k (k > j) is not yet updated when dimension j runs
-                const double p01 = e0 * d1, p02 = e0 * d2, p12 = e1 * d2;
-                double q01 = fma(p01, rh, p01 * rl), q02 = fma(p02, rh, p02 * rl), q12 = fma(p12, rh, p12 * rl);
-                {
-                    const double b0 = fabs(p01), b1 = fabs(p02), b2 = fabs(p12);
-                    const bool ok = b0 > 1e-250 && b0 < 1e290 && b1 > 1e-250 && b1 < 1e290 && b2 > 1e-250 && b2 < 1e290;
-                    if (!ok) { q01 = p01 / c; q02 = p02 / c; q12 = p12 / c; }     // zeros, tiny or huge products: IEEE division
+            // first / last rounds of a voxel, or a round after non-finite terms: per-lane predicates
+            for (int k = 0; k < 32; k++) {
+                if (k < my_m) {
+                    const double d = xs[k][cj].x - mu;
+                    mu = mu + fma(d, rs[k].x, fma(-mu, rs[k].y, xs[k][cj].y));
+                    if (chain_lane) mus[k + 1][cj] = mu;
                 }
-                t[lane][0] = t0; t[lane][1] = t1; t[lane][2] = t2; t[lane][3] = q01; t[lane][4] = q02; t[lane][5] = q12;
-                const double big = 1.7976931348623157e308;
-                nonfinite = !(fabs(t0) <= big && fabs(t1) <= big && fabs(t2) <= big && fabs(q01) <= big && fabs(q02) <= big && fabs(q12) <= big);
+                if (k < my_pm) {
+                    const double a2 = acc + tp[k][at];
+                    acc = (prev_chk && cov_lane && a2 != a2) ? 0.0 : a2;          // NaN -> 0 (normal_distributions.c:98-100)
+                }
             }
-            prev_chk = __any_sync(0xffffffffu, nonfinite);
-            if (redone || !__any_sync(0xffffffffu, bad)) break;
-            // rare: redo this round's means with the IEEE division, then its terms
-            mu = mu_start;
-            for (int k = 0; k < m; k++) {
-                const double cnt = (double)(base + k + 1);
-                mu = mu + (xs[k][cl].x - mu) / cnt;
-                if (lane < 3) mus[k + 1][lane] = mu;
-            }
-            redone = true;
-            __syncwarp();
         }
         __syncwarp();
-        if (lane < 3) mus[0][lane] = mus[m][lane];
-        prev_m = m; buf ^= 1;
+        // ---- B: per-point terms, all lanes in parallel, one voxel after the other; also validates the operands
+        bool nonfinite = false;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            bool redone = false;
+            while (true) {
+                bool bad = false;
+                if (lane < m[q]) {
+                    const double(*mq)[3] = s_mu[warp][q];
+                    const double o0 = mq[lane][0], o1 = mq[lane][1], o2 = mq[lane][2];
+                    const double n0 = mq[lane + 1][0], n1 = mq[lane + 1][1], n2 = mq[lane + 1][2];
+                    const double x0 = x[q][0], x1 = x[q][1], x2 = x[q][2];
+                    const double d0 = x0 - o0, d1 = x1 - o1, d2 = x2 - o2;          // the chain's d, bit for bit
+                    const double a0 = fabs(d0), a1 = fabs(d1), a2 = fabs(d2);
+                    bad = !(a0 > 1e-250 && a0 < 1e290 && a0 * 4194304.0 >= fabs(x0)) ||
+                          !(a1 > 1e-250 && a1 < 1e290 && a1 * 4194304.0 >= fabs(x1)) ||
+                          !(a2 > 1e-250 && a2 < 1e290 && a2 * 4194304.0 >= fabs(x2));
+                    double(*t)[6] = s_t[warp][buf][q];
+                    const double e0 = x0 - n0, e1 = x1 - n1;
+                    const double t0 = d0 * e0, t1 = d1 * e1, t2 = d2 * (x2 - n2);
+                    // (x_j - new_j)(x_k - old_k) / count: mu_k (k > j) is not yet updated when dimension j runs
+                    const double p01 = e0 * d1, p02 = e0 * d2, p12 = e1 * d2;
+                    double q01 = fma(p01, rh, p01 * rl), q02 = fma(p02, rh, p02 * rl), q12 = fma(p12, rh, p12 * rl);
+                    {
+                        const double b0 = fabs(p01), b1 = fabs(p02), b2 = fabs(p12);
+                        const bool ok = b0 > 1e-250 && b0 < 1e290 && b1 > 1e-250 && b1 < 1e290 && b2 > 1e-250 && b2 < 1e290;
+                        if (!ok) { q01 = p01 / c; q02 = p02 / c; q12 = p12 / c; }     // zeros, tiny or huge products: IEEE division
+                    }
+                    t[lane][0] = t0; t[lane][1] = t1; t[lane][2] = t2; t[lane][3] = q01; t[lane][4] = q02; t[lane][5] = q12;
+                    const double big = 1.7976931348623157e308;
+                    nonfinite |= !(fabs(t0) <= big && fabs(t1) <= big && fabs(t2) <= big && fabs(q01) <= big && fabs(q02) <= big && fabs(q12) <= big);
+                }
+                if (redone || !__any_sync(0xffffffffu, bad)) break;
+                // rare: redo this voxel's round with the IEEE division on its three chain lanes, then its terms
+                if (chain_lane && cq == q) {
+                    mu = mu_start;
+                    for (int k = 0; k < m[q]; k++) {
+                        const double cnt = (double)(base + k + 1);
+                        mu = mu + (s_x[warp][q][k][cj].x - mu) / cnt;
+                        s_mu[warp][q][k + 1][cj] = mu;
+                    }
+                }
+                redone = true;
+                __syncwarp();
+            }
+        }
+        prev_chk = __any_sync(0xffffffffu, nonfinite);
         __syncwarp();
-#ifdef NDT_PROFILE_STATS
-        tB += clock64() - c2;
-#endif
+        if (chain_lane && my_m > 0) s_mu[warp][cq][0][cj] = s_mu[warp][cq][my_m][cj];
+        prev_m[0] = m[0]; prev_m[1] = m[1]; buf ^= 1;
+        __syncwarp();
     }
-#ifdef NDT_PROFILE_STATS
-    if (lane == 0 && n > 6000 && b < 2) printf("stats b %d idx %u n %u rounds %u: load %lld A %lld B %lld total %lld cycles (start %lld)\n", b, idx, n, (n + 31) / 32, tL, tA, tB, clock64() - tS, tS);
-#endif
-    {   // C for the last round
-        const double(*tp)[6] = s_t[warp][buf ^ 1];
-        for (int k = 0; k < prev_m; k++) {
-            const double a2 = acc + tp[k][al];
-            acc = (lane >= 3 && a2 != a2) ? 0.0 : a2;
+    {   // C for the last round of each voxel (a shorter voxel's last terms were already added: its prev_m became 0)
+        const double(*tp)[6] = s_t[warp][buf ^ 1][aq];
+        const int my_pm = prev_m[aq];
+        for (int k = 0; k < my_pm; k++) {
+            const double a2 = acc + tp[k][at];
+            acc = (cov_lane && a2 != a2) ? 0.0 : a2;
         }
     }
+    if (fin_mu) mu = mu_fin;
+    if (fin_acc) acc = acc_fin;
     // variances m2 / n (normal_distributions.c:86-89), NaN -> 0
-    const double cntn = (double)n;
-    double var = acc / cntn;
-    if (isnan(var)) var = 0.0;
-    const double out = lane < 3 ? var : acc;
-    const double v0 = __shfl_sync(0xffffffffu, out, 0), v1 = __shfl_sync(0xffffffffu, out, 1), v2 = __shfl_sync(0xffffffffu, out, 2);
-    const double c01 = __shfl_sync(0xffffffffu, out, 3), c02 = __shfl_sync(0xffffffffu, out, 4), c12 = __shfl_sync(0xffffffffu, out, 5);
-    const double m0 = __shfl_sync(0xffffffffu, mu, 0), m1 = __shfl_sync(0xffffffffu, mu, 1), m2 = __shfl_sync(0xffffffffu, mu, 2);
-    if (lane == 0) {
-        double *mo = mean + ((size_t)b * vcap + v) * 3;
-        mo[0] = m0; mo[1] = m1; mo[2] = m2;
-        double *co = cov + ((size_t)b * vcap + v) * 9;
-        co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        if (nn[q] == 0) continue;
+        const double cntn = (double)nn[q];
+        double var = acc / cntn;
+        if (var != var) var = 0.0;
+        const double out = (lane < 12 && at < 3) ? var : acc;
+        const double v0 = __shfl_sync(0xffffffffu, out, q * 6 + 0), v1 = __shfl_sync(0xffffffffu, out, q * 6 + 1), v2 = __shfl_sync(0xffffffffu, out, q * 6 + 2);
+        const double c01 = __shfl_sync(0xffffffffu, out, q * 6 + 3), c02 = __shfl_sync(0xffffffffu, out, q * 6 + 4), c12 = __shfl_sync(0xffffffffu, out, q * 6 + 5);
+        const double m0 = __shfl_sync(0xffffffffu, mu, q * 3 + 0), m1 = __shfl_sync(0xffffffffu, mu, q * 3 + 1), m2 = __shfl_sync(0xffffffffu, mu, q * 3 + 2);
+        if (lane == 0) {
+            double *mo = mean + ((size_t)b * vcap + vv[q]) * 3;
+            mo[0] = m0; mo[1] = m1; mo[2] = m2;
+            double *co = cov + ((size_t)b * vcap + vv[q]) * 9;
+            co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
+        }
     }
 }
 
@@ -1237,7 +1246,8 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         if (!w.side) { CK(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&w.ev_join, cudaEventDisableTiming)); }
         CK(cudaEventRecord(w.ev_fork, st));
         CK(cudaStreamWaitEvent(w.side, w.ev_fork, 0));
-        k_stats<T><<<dim3(B, (max_heavy + kStatsWarps - 1) / kStatsWarps), 32 * kStatsWarps, 0, st>>>(
+        const unsigned max_pairs = (max_heavy + 1) / 2;
+        k_stats<T><<<dim3(B, (max_pairs + kStatsWarps - 1) / kStatsWarps), 32 * kStatsWarps, 0, st>>>(
             w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov);
         DBG("k_stats");
         k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, 0, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start,
