@@ -13,12 +13,16 @@
 #include <cstring>
 
 #ifndef NDT_STATS_WARPS
-#define NDT_STATS_WARPS 4
+#define NDT_STATS_WARPS 2
 #endif
 #ifndef NDT_STATS_MIN_BLOCKS
 #define NDT_STATS_MIN_BLOCKS 4
 #endif
-constexpr int kStatsWarps = NDT_STATS_WARPS;   // warps (= heavy voxels) per CTA of k_stats
+constexpr int kStatsWarps = NDT_STATS_WARPS;   // warps per CTA of k_stats
+#ifndef NDT_STATS_Q
+#define NDT_STATS_Q 4
+#endif
+constexpr int kQ = NDT_STATS_Q;                // heavy voxels each warp of k_stats runs in lockstep (3 kQ chain lanes, 6 kQ sum lanes <= 32)
 
 namespace ndt {
 
@@ -477,20 +481,20 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
                                                const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                                const unsigned *__restrict__ vox_order,
                                                double *__restrict__ mean, double *__restrict__ cov) {
-    // Each warp runs TWO heavy voxels (neighbours in the size-ordered list, so of similar length) in lockstep: the
-    // three mean chains of voxel 0 sit on lanes 0-2, those of voxel 1 on lanes 3-5, the six running sums on lanes
-    // 0-5 / 6-11, so the paced instruction stream (phase A) is shared by both voxels.
+    // Each warp runs kQ heavy voxels (neighbours in the size-ordered list, so of similar length) in lockstep: the
+    // three mean chains of voxel q sit on lanes 3q..3q+2, its six running sums on lanes 6q..6q+5, so the paced
+    // instruction stream (phase A) is shared by all of them.
     const int b = blockIdx.x;
     const CloudState &s = states[b];
     if (s.status != 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned pair = blockIdx.y * kStatsWarps + warp;
-    if (pair * 2 >= s.n_heavy) return;            // lighter voxels: k_stats_light
-    unsigned vv[2], nn[2];
-    const T *pp[2];
+    if (pair * kQ >= s.n_heavy) return;            // lighter voxels: k_stats_light
+    unsigned vv[kQ], nn[kQ];
+    const T *pp[kQ];
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const unsigned idx = pair * 2 + q;
+    for (int q = 0; q < kQ; q++) {
+        const unsigned idx = pair * kQ + q;
         if (idx < s.n_heavy) {
             vv[q] = vox_order[(size_t)b * vcap + idx];
             const unsigned st = vox_start[(size_t)b * (vcap + 1) + vv[q]], en = vox_start[(size_t)b * (vcap + 1) + vv[q] + 1];
@@ -501,39 +505,44 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
 
     // point-major layouts: in phase A the chain lanes (accumulator lanes) read consecutive banks and every other
     // lane reads the same word as a neighbour (broadcast): no bank conflicts on the paced path
-    __shared__ double2 s_x[kStatsWarps][2][32][3];      // per voxel, point, dimension: {x, x * rl}
+    __shared__ double2 s_x[kStatsWarps][kQ][32][3];      // per voxel, point, dimension: {x, x * rl}
     __shared__ double2 s_r[kStatsWarps][32];            // 1 / count as an unevaluated sum {rh, rl} (~106 bits), shared by both voxels
-    __shared__ double s_mu[kStatsWarps][2][33][3];      // means: [0][.] before the round's first point, [k+1][.] after point k
-    __shared__ double s_t[kStatsWarps][2][2][32][6];    // [buffer][voxel] terms of the round: m2 x3, c01, c02, c12
+    __shared__ double s_mu[kStatsWarps][kQ][33][3];      // means: [0][.] before the round's first point, [k+1][.] after point k
+    __shared__ double s_t[kStatsWarps][2][kQ][32][6];    // [buffer][voxel] terms of the round: m2 x3, c01, c02, c12
     double2 *rs = s_r[warp];
 
-    const int cq = lane < 6 ? lane / 3 : 1, cj = lane < 6 ? lane % 3 : 2;     // chain lane -> (voxel, dimension)
-    const int aq = lane < 12 ? lane / 6 : 1, at = lane < 12 ? lane % 6 : 5;   // accumulator lane -> (voxel, term)
-    const bool chain_lane = lane < 6, cov_lane = lane < 12 && at >= 3;
+    const int cq = lane < 3 * kQ ? lane / 3 : kQ - 1, cj = lane < 3 * kQ ? lane % 3 : 2;     // chain lane -> (voxel, dimension)
+    const int aq = lane < 6 * kQ ? lane / 6 : kQ - 1, at = lane < 6 * kQ ? lane % 6 : 5;     // accumulator lane -> (voxel, term)
+    const bool chain_lane = lane < 3 * kQ, acc_lane = lane < 6 * kQ, cov_lane = acc_lane && at >= 3;
     double mu = 0.0, acc = 0.0;
     if (chain_lane) s_mu[warp][cq][0][cj] = 0.0;
-    const unsigned nmax = nn[0] > nn[1] ? nn[0] : nn[1];
-    int prev_m[2] = {0, 0};
+    unsigned nmax = 0;
+    int prev_m[kQ];
+#pragma unroll
+    for (int q = 0; q < kQ; q++) { nmax = nn[q] > nmax ? nn[q] : nmax; prev_m[q] = 0; }
     int buf = 0;
     bool prev_chk = false;                 // previous round produced a non-finite term: add with the NaN rule
     bool fin_mu = false, fin_acc = false;  // this lane's voxel is finished: its result is parked in mu_fin / acc_fin
     double mu_fin = 0.0, acc_fin = 0.0;    // (the straight-line rounds of the longer voxel keep clobbering mu / acc)
-    T nx[2][3] = {{0, 0, 0}, {0, 0, 0}};   // the next round's point of this lane (per voxel), fetched one round ahead
+    T nx[kQ][3];                           // the next round's point of this lane (per voxel), fetched one round ahead
 #pragma unroll
-    for (int q = 0; q < 2; q++)
+    for (int q = 0; q < kQ; q++)
+    {
+        nx[q][0] = nx[q][1] = nx[q][2] = 0;
         if ((unsigned)lane < nn[q]) { nx[q][0] = pp[q][lane * 3 + 0]; nx[q][1] = pp[q][lane * 3 + 1]; nx[q][2] = pp[q][lane * 3 + 2]; }
+    }
 
     for (unsigned base = 0; base < nmax; base += 32) {
-        int m[2];
-        double x[2][3];
+        int m[kQ];
+        double x[kQ][3];
 #pragma unroll
-        for (int q = 0; q < 2; q++) m[q] = base >= nn[q] ? 0 : (int)(nn[q] - base < 32u ? nn[q] - base : 32u);
+        for (int q = 0; q < kQ; q++) m[q] = base >= nn[q] ? 0 : (int)(nn[q] - base < 32u ? nn[q] - base : 32u);
         const double c = (double)(base + lane + 1);
         const double rh = 1.0 / c;
         const double rl = fma(-c, rh, 1.0) * rh;
         rs[lane] = make_double2(rh, rl);
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
+        for (int q = 0; q < kQ; q++) {
 #pragma unroll
             for (int j = 0; j < 3; j++) x[q][j] = (double)nx[q][j];
             if (lane < m[q]) {
@@ -559,9 +568,10 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
         const int my_m = m[cq], my_pm = prev_m[aq];
         if (!fin_mu && m[cq] == 0) { fin_mu = true; mu_fin = mu; }
         if (!fin_acc && m[aq] == 0 && prev_m[aq] == 0) { fin_acc = true; acc_fin = acc; }
-        const bool full0 = m[0] == 32 && prev_m[0] == 32, done0 = m[0] == 0 && prev_m[0] == 0;
-        const bool full1 = m[1] == 32 && prev_m[1] == 32, done1 = m[1] == 0 && prev_m[1] == 0;
-        if (!prev_chk && (full0 || done0) && (full1 || done1)) {
+        bool straight = !prev_chk;             // every voxel is either in a full round after a full round, or finished
+#pragma unroll
+        for (int q = 0; q < kQ; q++) straight = straight && ((m[q] == 32 && prev_m[q] == 32) || (m[q] == 0 && prev_m[q] == 0));
+        if (straight) {
             // full rounds: straight-line, no per-step predicates, operands of the next four points are fetched
             // while the current four are on the chain
             double2 xv[4], rv[4], xn[4], rn[4];
@@ -603,7 +613,7 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
         // ---- B: per-point terms, all lanes in parallel, one voxel after the other; also validates the operands
         bool nonfinite = false;
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
+        for (int q = 0; q < kQ; q++) {
             bool redone = false;
             while (true) {
                 bool bad = false;
@@ -649,7 +659,9 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
         prev_chk = __any_sync(0xffffffffu, nonfinite);
         __syncwarp();
         if (chain_lane && my_m > 0) s_mu[warp][cq][0][cj] = s_mu[warp][cq][my_m][cj];
-        prev_m[0] = m[0]; prev_m[1] = m[1]; buf ^= 1;
+#pragma unroll
+        for (int q = 0; q < kQ; q++) prev_m[q] = m[q];
+        buf ^= 1;
         __syncwarp();
     }
     {   // C for the last round of each voxel (a shorter voxel's last terms were already added: its prev_m became 0)
@@ -664,12 +676,12 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
     if (fin_acc) acc = acc_fin;
     // variances m2 / n (normal_distributions.c:86-89), NaN -> 0
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
+    for (int q = 0; q < kQ; q++) {
         if (nn[q] == 0) continue;
         const double cntn = (double)nn[q];
         double var = acc / cntn;
         if (var != var) var = 0.0;
-        const double out = (lane < 12 && at < 3) ? var : acc;
+        const double out = (acc_lane && at < 3) ? var : acc;
         const double v0 = __shfl_sync(0xffffffffu, out, q * 6 + 0), v1 = __shfl_sync(0xffffffffu, out, q * 6 + 1), v2 = __shfl_sync(0xffffffffu, out, q * 6 + 2);
         const double c01 = __shfl_sync(0xffffffffu, out, q * 6 + 3), c02 = __shfl_sync(0xffffffffu, out, q * 6 + 4), c12 = __shfl_sync(0xffffffffu, out, q * 6 + 5);
         const double m0 = __shfl_sync(0xffffffffu, mu, q * 3 + 0), m1 = __shfl_sync(0xffffffffu, mu, q * 3 + 1), m2 = __shfl_sync(0xffffffffu, mu, q * 3 + 2);
@@ -1246,7 +1258,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         if (!w.side) { CK(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&w.ev_join, cudaEventDisableTiming)); }
         CK(cudaEventRecord(w.ev_fork, st));
         CK(cudaStreamWaitEvent(w.side, w.ev_fork, 0));
-        const unsigned max_pairs = (max_heavy + 1) / 2;
+        const unsigned max_pairs = (max_heavy + kQ - 1) / kQ;
         k_stats<T><<<dim3(B, (max_pairs + kStatsWarps - 1) / kStatsWarps), 32 * kStatsWarps, 0, st>>>(
             w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov);
         DBG("k_stats");
