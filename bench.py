@@ -122,15 +122,15 @@ def build_network(device):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference(n_clouds: int, seed0: int, threads: int):
+def cpu_reference(n_clouds: int, seed0: int, threads: int, variant: str = "threaded"):
     """The reference path on the host: per-cloud ndt_downsample of the reference's own C core (8 pthreads inside,
     oracle/_ref/libndnet_ref.so = unmodified core_legacy sources, -O0 as its CMake builds them) through the same
     marshalling as ndnet/preprocessing/ndt_legacy.py, float32 + nan_to_num as ndtnet_preprocessing.py:60-69, then the
     fp32 torch network on all host threads.  Returns (seconds, kind)."""
     from oracle import ref_ctypes
     torch.set_num_threads(threads)
-    if ref_ctypes.have_ref("threaded"):
-        lib, kind = ref_ctypes.load(ref_ctypes.ref_lib_path("threaded")), "reference"
+    if ref_ctypes.have_ref(variant):
+        lib, kind = ref_ctypes.load(ref_ctypes.ref_lib_path(variant)), "reference"
         run = lambda p, l: ref_ctypes.downsample(lib, p, N_NDS, l, N_CLASSES, out_rows=N_NDS + 256)   # noqa: E731
         unpack = lambda r: (r.points[:N_NDS], r.covs[:N_NDS])                                         # noqa: E731
     else:
@@ -328,6 +328,10 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": n / dt, "unit": "clouds/s", "cores": os.cpu_count() or 1, "kind": kind,
                                 "sample": f"{n} scans of the same workload; NDT = reference C core (8 pthreads, -O0, GSL shim) serial over "
                                           f"scans, network = torch fp32 on all host threads"}
+        # courtesy number: the same reference sources compiled with -O2
+        dt2, kind2 = cpu_reference(n, 500_000, os.cpu_count() or 1, variant="O2")
+        if kind2 == "reference":
+            line["cpu_baseline"]["value_O2_build"] = n / dt2
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -714,8 +714,11 @@ __global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restric
     const T *p = sorted + ((size_t)b * N + st) * 3;
     double mu0 = 0, mu1 = 0, mu2 = 0, m20 = 0, m21 = 0, m22 = 0, c01 = 0, c02 = 0, c12 = 0;
     const unsigned n = en - st;
+    T a0 = 0, a1 = 0, a2 = 0;
+    if (n > 0) { a0 = p[0]; a1 = p[1]; a2 = p[2]; }
     for (unsigned k = 0; k < n; k++) {
-        const double x0 = (double)p[(size_t)k * 3 + 0], x1 = (double)p[(size_t)k * 3 + 1], x2 = (double)p[(size_t)k * 3 + 2];
+        const double x0 = (double)a0, x1 = (double)a1, x2 = (double)a2;
+        if (k + 1 < n) { a0 = p[(size_t)(k + 1) * 3 + 0]; a1 = p[(size_t)(k + 1) * 3 + 1]; a2 = p[(size_t)(k + 1) * 3 + 2]; }   // overlaps this point's chain
         const double c = (double)(k + 1);
         const double rh = 1.0 / c;
         const double rl = fma(-c, rh, 1.0) * rh;
