@@ -432,11 +432,12 @@ namespace {
 
 template <int BN, int STAGES>
 bool launch_gemm(const CUtensorMap &a, const CUtensorMap &b, const GemmArgs &g, dim3 grid, cudaStream_t st) {
-    static bool attr = false;
+    static bool attr[64] = {};          // function attributes are per device
     constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
-    if (!attr) {
+    int dev = 0; cudaGetDevice(&dev);
+    if (!attr[dev & 63]) {
         if (cudaFuncSetAttribute(k_gemm<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-        attr = true;
+        attr[dev & 63] = true;
     }
     k_gemm<BN, STAGES><<<grid, kGemmThreads, smem, st>>>(a, b, g);
     return cudaGetLastError() == cudaSuccess;
@@ -478,10 +479,11 @@ struct Fwd {
         CUtensorMap mw, mx;
         if (!make_map(&mw, w, K, C, 1, 128) || !make_map(&mx, act, K, P, B, 64)) { ok = false; *err = "cuTensorMapEncodeTiled failed"; return; }
         GemmArgs g{}; g.K = K; g.P = P; g.mode = MODE_CHMAX; g.relu = relu ? 1 : 0; g.n_valid = C; g.bias = bias; g.gmax = gmax; g.ldg = ldg;
-        static bool attr = false;
-        if (!attr) {
+        static bool attr[64] = {};      // function attributes are per device
+        int dev = 0; cudaGetDevice(&dev);
+        if (!attr[dev & 63]) {
             if (cudaFuncSetAttribute(k_gemm_chmax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChmaxSmemBytes) != cudaSuccess) { ok = false; *err = "smem attribute"; return; }
-            attr = true;
+            attr[dev & 63] = true;
         }
         dim3 grid((C + 511) / 512, B);
         k_gemm_chmax<<<grid, kGemmThreads, kChmaxSmemBytes, st>>>(mw, mx, g);

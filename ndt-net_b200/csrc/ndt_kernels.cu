@@ -1287,8 +1287,9 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         size_t bytes = P * 12;
         const size_t max_dyn = 200 * 1024;
         while (bytes > max_dyn) { smem_cap >>= 1; bytes = (size_t)smem_cap * 12; }
-        static bool attr_set = false;
-        if (!attr_set) { CK(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn)); attr_set = true; }
+        static bool attr_set[64] = {};   // function attributes are per device
+        int dev = 0; cudaGetDevice(&dev);
+        if (!attr_set[dev & 63]) { CK(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn)); attr_set[dev & 63] = true; }
         k_select<<<B, 1024, bytes, st>>>(w.states, vcap, D, w.vox_cell, w.vox_n, w.mean, w.cov_final, w.cls, labels ? 1 : 0,
                                          w.kl_div, w.kl_flag, w.key, w.seq, kcap, smem_cap, w.firstpos, w.removed, flags,
                                          out_feat, out_feat64, out_labels, out_voxel, w.list_div, w.list_seq, info);
