@@ -185,6 +185,33 @@ int ndnet_b200_infer_device(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const 
  * Defaults: 2 lanes, 64 scans.  The lane count is fixed at the first infer call. */
 int ndnet_b200_set_pipeline(ndnet_b200_ctx *ctx, int lanes, int chunk);
 
+/* ------------------------------------------------------------------ (3) ASCII-PLY ingest
+ * Replaces the per-line Python loop of /root/reference/ndnet/datasets/CARLA_Seg.py:96-183 (`get_data_pcl`):
+ * skip `num_header_lines` lines (:115), then per line float(data[0..2]) and int(data[-1]) (:117-123), refuse a tag
+ * above n_classes (:127-128); points are held as float32 (:173), tags as uint16 (:146).  `text` is the file's bytes
+ * (host, or device when text_on_device != 0).  The parsed cloud stays resident on the GPU behind the handle; its
+ * buffers come from the device's stream-ordered pool on `stream`, which must outlive the handle.
+ * Returns 0, or (first offending line in *bad_line, 0-based in the file; the tag in *bad_value for -303):
+ *   -301  a data line has fewer than three tokens                (IndexError in the reference)
+ *   -302  a token is not a float()/int() literal                  (ValueError)
+ *   -303  class tag > n_classes                                   (ValueError "Class tag {tag} out of bounds", :128)
+ *   -304  literal outside what is converted exactly: inf/nan/underscores, more than 19 significant digits,
+ *         |decimal exponent| > 55 — refused, never approximated
+ *   -305  negative class tag                                      (OverflowError at :146)
+ *   -306  lone '\r' line ends or non-ASCII bytes
+ * Decimal -> double is correctly rounded (CPython float()), then rounded to float32 as torch's .float(). */
+typedef struct ndnet_b200_ply ndnet_b200_ply;
+int ndnet_b200_ply_load(int device, const char *text, size_t nbytes, int text_on_device, int num_header_lines,
+                        int n_classes, void *stream, ndnet_b200_ply **out, unsigned long *num_points, long *bad_line,
+                        long *bad_value);
+long ndnet_b200_ply_num_points(const ndnet_b200_ply *ply);
+/* Gathers rows `indexes[0..n)` (host int64, or device when indexes_on_device != 0; NULL = every point in file
+ * order) into DEVICE outputs, any of which may be NULL: points [n,3] f32, labels [n] u16, one-hot [n, n_classes+1]
+ * f32 (:141-147,173-179).  -307 when an index is out of range. */
+int ndnet_b200_ply_sample(ndnet_b200_ply *ply, const int64_t *indexes, size_t n, int indexes_on_device,
+                          float *out_points, uint16_t *out_labels, float *out_onehot, void *stream);
+void ndnet_b200_ply_free(ndnet_b200_ply *ply);
+
 #ifdef __cplusplus
 }
 #endif

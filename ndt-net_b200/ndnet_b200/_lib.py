@@ -78,6 +78,15 @@ def lib() -> C.CDLL:
     L.ndnet_b200_infer_device.argtypes = [vp, vp, vp, i, vp, i, l, i, l, vp, l, vp]
     L.ndnet_b200_set_pipeline.restype = i
     L.ndnet_b200_set_pipeline.argtypes = [vp, i, i]
+    L.ndnet_b200_ply_load.restype = i
+    L.ndnet_b200_ply_load.argtypes = [i, vp, C.c_size_t, i, i, i, vp, C.POINTER(vp), C.POINTER(C.c_ulong), C.POINTER(l),
+                                      C.POINTER(l)]
+    L.ndnet_b200_ply_num_points.restype = l
+    L.ndnet_b200_ply_num_points.argtypes = [vp]
+    L.ndnet_b200_ply_sample.restype = i
+    L.ndnet_b200_ply_sample.argtypes = [vp, vp, C.c_size_t, i, vp, vp, vp, vp]
+    L.ndnet_b200_ply_free.restype = None
+    L.ndnet_b200_ply_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -89,4 +98,5 @@ EXPORTED = [
     "ndnet_b200_last_kl_list", "ndnet_b200_selftest_div", "ndnet_b200_launch_count", "ndnet_b200_stage_timing", "ndnet_b200_stage_times",
     "ndnet_b200_model_create", "ndnet_b200_model_input_dim", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
     "ndnet_b200_infer_host", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline",
+    "ndnet_b200_ply_load", "ndnet_b200_ply_num_points", "ndnet_b200_ply_sample", "ndnet_b200_ply_free",
 ]
