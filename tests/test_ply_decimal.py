@@ -80,7 +80,7 @@ def test_literals_next_to_rounding_boundaries(host):
         mid = (Decimal(d) + Decimal(math.nextafter(d, math.inf))) / 2
         for q in ("ROUND_FLOOR", "ROUND_CEILING"):
             getcontext().rounding = q
-            t = format(+mid.normalize(), "e") if False else "{:.18e}".format(mid)   # 19 significant digits
+            t = "{:.18e}".format(mid)                     # 19 significant digits, rounded down / up
             m, e = t.split("e")
             if abs(int(e)) + 18 <= 55:
                 toks.append(m.replace(".", "") + "e" + str(int(e) - 18))
