@@ -212,6 +212,28 @@ int ndnet_b200_ply_sample(ndnet_b200_ply *ply, const int64_t *indexes, size_t n,
                           float *out_points, uint16_t *out_labels, float *out_onehot, void *stream);
 void ndnet_b200_ply_free(ndnet_b200_ply *ply);
 
+/* ------------------------------------------------------------------ (4) training step of the network
+ * Train-mode forward and backward of NDTNetSegmentation (/root/reference/ndnet/models/ndtnet.py:33-62,112-164,
+ * 218-243) as run by the reference's training loop (/root/reference/tools/train.py:66-76): BatchNorm with batch
+ * statistics over all rows (running statistics updated in place, momentum 0.1, eps 1e-5), fp32 throughout.
+ * `names`/`shapes` describe the module's parameters AND buffers (state_dict keys); `tensors[i]` / `grads[i]` of the
+ * forward/backward calls are DEVICE pointers in that same order (grads[i] may be NULL for buffers; int64
+ * num_batches_tracked buffers are passed through the same array and incremented).  The loss stays with the caller:
+ * forward writes log-probabilities [B,N,C+1], backward takes dL/dlogp of the same shape and OVERWRITES each grads[i].
+ * B >= 2 (BatchNorm over the FC layers of the T-Nets needs more than one cloud). */
+typedef struct ndnet_b200_trainer ndnet_b200_trainer;
+int ndnet_b200_trainer_create(int device, int n_tensors, const char *const *names, const int64_t *const *shapes,
+                              const int *ndims, ndnet_b200_trainer **out);
+int ndnet_b200_trainer_forward(ndnet_b200_trainer *t, const float *feat /* [B,N,12] */, int B, int N,
+                               float *const *tensors, float *out_logp, int update_running_stats, void *stream);
+int ndnet_b200_trainer_backward(ndnet_b200_trainer *t, const float *dlogp, float *const *tensors, float *const *grads,
+                                void *stream);
+const char *ndnet_b200_trainer_last_error(const ndnet_b200_trainer *t);
+/* Test hook: copies one internal activation/gradient buffer of the last pass ("h3.dA", "t2.c1.Y", "c1.A", "t1.T", ...)
+ * to `out` (device, may be NULL to query the size); returns the element count or -200. */
+long ndnet_b200_trainer_debug_buffer(ndnet_b200_trainer *t, const char *name, float *out, void *stream);
+void ndnet_b200_trainer_destroy(ndnet_b200_trainer *t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,7 +4,8 @@ signatures, outputs and - so that reference checkpoints load unchanged - the sam
 
 `forward` is the plain PyTorch fp32 definition of the network (it is what the parity tests compare the
 CUDA path against).  `forward_b200` runs the same network through libndnet_b200.so (tcgen05/TMA bf16 GEMMs
-with fused bias/BN/ReLU/max-pool epilogues, eval mode only).
+with fused bias/BN/ReLU/max-pool epilogues) in eval mode, and through the fp32 training kernels (train.cu, with
+gradients) when the segmentation module is in training mode.
 """
 from __future__ import annotations
 
@@ -84,7 +85,14 @@ class _B200Mixin:
     def forward_b200(self, points: torch.Tensor, covariances: torch.Tensor) -> torch.Tensor:
         from ndnet_b200.model import B200Model
         if self.training:
-            raise RuntimeError("forward_b200 folds BatchNorm running statistics: call .eval() first")
+            if self._kind != 1:
+                raise RuntimeError("forward_b200 in training mode is built for NDTNetSegmentation only; call .eval() first")
+            from ndnet_b200.train import SegTrainer          # train-mode BatchNorm + gradients from train.cu
+            tr = getattr(self, "_b200_trainer", None)
+            if tr is None or tr.device != points.device:
+                tr = SegTrainer(self, points.device)
+                object.__setattr__(self, "_b200_trainer", tr)
+            return tr(points, covariances)
         m = getattr(self, "_b200_model", None)
         if m is None or m.device != points.device:
             m = B200Model(self, self._kind, points.device)

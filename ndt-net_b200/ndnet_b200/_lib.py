@@ -87,6 +87,18 @@ def lib() -> C.CDLL:
     L.ndnet_b200_ply_sample.argtypes = [vp, vp, C.c_size_t, i, vp, vp, vp, vp]
     L.ndnet_b200_ply_free.restype = None
     L.ndnet_b200_ply_free.argtypes = [vp]
+    L.ndnet_b200_trainer_create.restype = i
+    L.ndnet_b200_trainer_create.argtypes = [i, i, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i), C.POINTER(vp)]
+    L.ndnet_b200_trainer_forward.restype = i
+    L.ndnet_b200_trainer_forward.argtypes = [vp, vp, i, i, C.POINTER(vp), vp, i, vp]
+    L.ndnet_b200_trainer_backward.restype = i
+    L.ndnet_b200_trainer_backward.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
+    L.ndnet_b200_trainer_last_error.restype = C.c_char_p
+    L.ndnet_b200_trainer_last_error.argtypes = [vp]
+    L.ndnet_b200_trainer_debug_buffer.restype = l
+    L.ndnet_b200_trainer_debug_buffer.argtypes = [vp, C.c_char_p, vp, vp]
+    L.ndnet_b200_trainer_destroy.restype = None
+    L.ndnet_b200_trainer_destroy.argtypes = [vp]
     _lib = L
     return L
 
@@ -99,4 +111,6 @@ EXPORTED = [
     "ndnet_b200_model_create", "ndnet_b200_model_input_dim", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
     "ndnet_b200_infer_host", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline",
     "ndnet_b200_ply_load", "ndnet_b200_ply_num_points", "ndnet_b200_ply_sample", "ndnet_b200_ply_free",
+    "ndnet_b200_trainer_create", "ndnet_b200_trainer_forward", "ndnet_b200_trainer_backward", "ndnet_b200_trainer_last_error",
+    "ndnet_b200_trainer_debug_buffer", "ndnet_b200_trainer_destroy",
 ]

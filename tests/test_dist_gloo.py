@@ -55,3 +55,42 @@ def test_shard_range_covers_everything():
         for world in (1, 2, 3, 8):
             items = [i for r in range(world) for i in shard_range(n, r, world)]
             assert items == list(range(n))
+
+
+def _grad_worker(rank, world, port, out):
+    from ndnet_b200.train import allreduce_gradients
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.BatchNorm1d(7), torch.nn.Linear(7, 3))
+        net[2].bias.requires_grad_(False)                       # parameters without a gradient are skipped
+        x = torch.full((4, 5), float(rank + 1))
+        (net(x) ** 2).sum().backward()
+        local = [p.grad.clone() for p in net.parameters() if p.grad is not None]
+        n = allreduce_gradients(net)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [g.numpy() for g in local])
+        if rank == 0:
+            out.put((n, [p.grad.numpy() for p in net.parameters() if p.grad is not None], gathered))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_averages_over_two_ranks():
+    """The training path's only collective: one flat all-reduce, mean over ranks."""
+    import numpy as np
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    n, reduced, gathered = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert n == sum(g.size for g in reduced)
+    for k, g in enumerate(reduced):
+        assert np.allclose(g, (gathered[0][k] + gathered[1][k]) / 2, rtol=1e-6, atol=1e-7)

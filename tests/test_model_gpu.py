@@ -74,8 +74,11 @@ def test_classification_forward_matches_torch_fp32(B, N):
     assert torch.allclose(got.sum(1), torch.ones_like(got[:, 0]), atol=1e-4)
 
 
-def test_forward_b200_refuses_training_mode():
-    net = _seg().train()
+def test_forward_b200_refuses_training_mode_without_a_training_path():
+    """Eval-mode kernels fold the running statistics; only the segmentation module has training kernels (train.cu)."""
+    net = NDTNetClassification()
+    net.load_state_dict(deterministic_state_dict(net, 1))
+    net = net.cuda().train()
     p, c = inputs(1, 2, 64)
     with pytest.raises(RuntimeError):
         net.forward_b200(torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda())

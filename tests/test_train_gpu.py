@@ -1,0 +1,313 @@
+"""GPU parity of the training kernels (ndt-net_b200/csrc/train.cu) against torch's fp32 autograd on
+the same network definition (ndnet/models/ndtnet.py mirror of the reference modules, pinned to them by
+tests/test_model_cpu.py), as the reference's training loop runs it (/root/reference/tools/train.py:66-76): train-mode
+BatchNorm, cross_entropy on the (B, N, C+1) output.
+
+Stated tolerance.  The network is ill-conditioned in fp32 (BatchNorm over the 2-16 rows of the T-Net FC layers, ReLU
+masks of elements within rounding of zero): torch's OWN fp32 autograd deviates from its fp64 autograd by ~1e-2
+relative per parameter gradient.  So the yardstick is fp64 autograd, and the bar is "as exact as torch fp32":
+  whole graph vs fp64 autograd: per parameter ||g_ours - g_64|| <= 0.1 ||g_64|| and cosine >= 0.995, all parameters
+  together <= 5e-2 (a wiring error is O(1)); log-probabilities max|ours - fp64| <= max(3 max|torch32 - fp64|, 2e-4);
+  running statistics 1e-5 against torch fp32.
+Independently of conditioning, the backward kernels are checked piecewise against an fp64 replay from the library's own
+saved activations (1e-5 relative): that is the statement that the kernel arithmetic itself is exact to fp32 rounding.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from ndnet.models.ndtnet import NDTNetSegmentation
+from ndnet_b200.model import deterministic_state_dict
+from ndnet_b200.train import SegTrainer, reference_loss
+from tests.golden.make_model_golden import inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def fp32_reference():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _net(F, C, seed):
+    net = NDTNetSegmentation(num_classes=C, feature_dim=F)
+    net.load_state_dict(deterministic_state_dict(net, seed))
+    return net.cuda().train()
+
+
+def _batch(seed, B, N, C):
+    p, c = inputs(seed, B, N)
+    rng = np.random.default_rng(seed)
+    gt = np.zeros((B, N, C + 1), np.float32)
+    lab = rng.integers(0, C + 1, (B, N))
+    np.put_along_axis(gt, lab[..., None], 1.0, axis=2)
+    return torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda(), torch.from_numpy(gt).cuda()
+
+
+def _compare_grads(net_64, net_b):
+    """Whole-graph check against fp64 autograd.  The per-draw error is dominated by ReLU-mask / arg-max flips of elements
+    within fp32 rounding of a tie (tools/gpu_check_train.py: torch's own fp32 autograd shows 1e-3..4e-2 per parameter on
+    these shapes), so the bound is loose; the tight statement is the layer-by-layer replay below."""
+    num = den = 0.0
+    gmax = max(p.grad.norm().item() for p in net_64.parameters())
+    for (name, p64), (_, pb) in zip(net_64.named_parameters(), net_b.named_parameters()):
+        g, gb = p64.grad.flatten(), pb.grad.double().flatten()
+        err, ref = (gb - g).norm().item(), g.norm().item()
+        num += err ** 2
+        den += ref ** 2
+        if ref > 1e-3 * gmax:
+            assert err <= 0.1 * ref, (name, err, ref)
+            assert torch.dot(g, gb).item() / (ref * gb.norm().item()) >= 0.995, name
+        else:
+            assert err <= 1e-3 * gmax, (name, err, ref)          # analytically-zero gradients (biases in front of a BatchNorm)
+    assert (num / den) ** 0.5 <= 5e-2, (num / den) ** 0.5
+
+
+@pytest.mark.parametrize("B,N,F,C,loss", [(4, 200, 768, 28, "reference"), (8, 77, 1024, 16, "nll"), (16, 128, 768, 28, "nll")])
+def test_forward_backward_match_torch_autograd(B, N, F, C, loss):
+    net_a = _net(F, C, 3)
+    net_b = copy.deepcopy(net_a)
+    net_64 = copy.deepcopy(net_a).double()
+    pts, cov, gt = _batch(B * 1000 + N, B, N, C)
+    fn = reference_loss if loss == "reference" else (lambda pred, gt: -(pred * gt).sum() / (B * N))
+    out_a = net_a(pts, cov)
+    fn(out_a, gt).backward()
+    out_64 = net_64(pts.double(), cov.double())
+    fn(out_64, gt.double()).backward()
+    trainer = SegTrainer(net_b)
+    out_b = trainer(pts, cov)
+    fn(out_b, gt).backward()
+    assert out_b.shape == out_a.shape
+    e32 = (out_a.double() - out_64).abs().max().item()
+    eb = (out_b.double() - out_64).abs().max().item()
+    assert eb <= max(3 * e32, 2e-4), (eb, e32)
+    _compare_grads(net_64, net_b)
+    for (name, ba), (_, bb) in zip(net_a.named_buffers(), net_b.named_buffers()):
+        if name.endswith("num_batches_tracked"):
+            assert int(ba) == int(bb) == 2, name         # the fixture starts at 1
+        else:
+            assert torch.allclose(ba, bb, atol=1e-5, rtol=1e-5), name
+
+
+def test_forward_b200_in_training_mode_is_the_training_path_and_steps_like_torch():
+    """Three Adam steps (tools/train.py:147 optimizer) through module.forward_b200 track the torch-autograd run."""
+    B, N, C = 4, 256, 28
+    net_a = _net(768, C, 5)
+    net_b = copy.deepcopy(net_a)
+    opt_a = torch.optim.Adam(net_a.parameters(), lr=1e-3)
+    opt_b = torch.optim.Adam(net_b.parameters(), lr=1e-3)
+    losses = []
+    for step in range(3):
+        pts, cov, gt = _batch(100 + step, B, N, C)
+        la = reference_loss(net_a(pts, cov), gt)
+        opt_a.zero_grad(); la.backward(); opt_a.step()
+        lb = reference_loss(net_b.forward_b200(pts, cov), gt)
+        opt_b.zero_grad(); lb.backward(); opt_b.step()
+        losses.append((la.item(), lb.item()))
+        assert abs(la.item() - lb.item()) <= 2e-2 * abs(la.item()) + 1e-4, losses
+    # Adam's first steps are +-lr whatever the gradient's size, so parameters are compared on the step scale only
+    for (name, pa), (_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        assert (pa - pb).abs().max().item() <= 3 * 2 * 1e-3 + 1e-6, name
+    for (name, ba), (_, bb) in zip(net_a.named_buffers(), net_b.named_buffers()):
+        if name.endswith("num_batches_tracked"):
+            assert int(ba) == int(bb) == 4, name
+
+
+class _Replay:
+    """fp64 re-computation of every layer of one pass from the library's OWN saved inputs of that layer (debug buffers):
+    each check is local, so it is exact to fp32 rounding no matter how ill-conditioned the whole network is."""
+
+    def __init__(self, net, tr, B, N, feat, out, dlogp, tol=2e-5):
+        self.net, self.tr, self.B, self.N, self.M, self.tol = net, tr, B, N, B * N, tol
+        self.feat = feat.double().cpu().view(B * N, 12)
+        self.out, self.dlogp = out.detach().double().cpu(), dlogp.double().cpu()
+        self.F, self.C = net.feature_dim, net.num_classes + 1
+        self.grads = {n: p.grad.double().cpu() for n, p in net.named_parameters()}
+        self.params = {n: p.detach().double().cpu() for n, p in net.named_parameters()}
+
+    def buf(self, name, *shape):
+        return self.tr.debug_buffer(name).double().cpu().view(*shape)
+
+    def close(self, got, want, what, scale=None):
+        """||got - want|| <= tol * scale; scale defaults to ||want||, and is the norm of the sum of |terms| for column
+        sums that cancel analytically (the shift gradient in front of another BatchNorm is exactly zero)."""
+        err = (got - want).norm().item()
+        ref = want.norm().item() if scale is None else scale.norm().item()
+        assert err <= self.tol * ref + 1e-12, (what, err, ref)
+
+    def W(self, lin):
+        w = self.params[lin + ".weight"]
+        return w.view(w.shape[0], w.shape[1])
+
+    # ---- forward
+    def block_fwd(self, name, X, lin, bn, relu):
+        rows, out = X.shape[0], self.W(lin).shape[0]
+        Y = self.buf(name + ".Y", rows, out)
+        self.close(Y, X @ self.W(lin).t() + self.params[lin + ".bias"], name + ".Y")
+        if bn is None:
+            return Y
+        mean, var = Y.mean(0), Y.var(0, unbiased=False)
+        self.close(self.buf(name + ".mean", out), mean, name + ".mean")
+        self.close(self.buf(name + ".rstd", out), 1 / torch.sqrt(var + 1e-5), name + ".rstd")
+        A = (Y - mean) / torch.sqrt(var + 1e-5) * self.params[bn + ".weight"] + self.params[bn + ".bias"]
+        A = A.clamp_min(0) if relu else A
+        got = self.buf(name + ".A", rows, out)
+        self.close(got, A, name + ".A")
+        return got
+
+    def tnet_fwd(self, t, X, p, d):
+        B, N = self.B, self.N
+        a = self.block_fwd(t + ".c1", X, p + ".conv1", p + ".bn1", True)
+        a = self.block_fwd(t + ".c2", a, p + ".conv2", p + ".bn2", True)
+        a = self.block_fwd(t + ".c3", a, p + ".conv3", p + ".bn3", True)
+        G = self.buf(t + ".G", B, 1024)
+        assert torch.equal(G, a.view(B, N, 1024).amax(1)), t + ".G"
+        f = self.block_fwd(t + ".f1", G, p + ".fc1", p + ".bn4", True)
+        f = self.block_fwd(t + ".f2", f, p + ".fc2", p + ".bn5", True)
+        y = self.block_fwd(t + ".f3", f, p + ".fc3", None, False)
+        T = self.buf(t + ".T", B, d, d)
+        self.close(T, y.view(B, d, d) + torch.eye(d, dtype=torch.float64), t + ".T")
+        return T
+
+    def forward(self):
+        B, N, M, F = self.B, self.N, self.M, self.F
+        fe = "feature_extractor"
+        T1 = self.tnet_fwd("t1", self.feat[:, :3], fe + ".t1", 3)
+        p = torch.einsum("bik,bnk->bni", T1, self.feat[:, :3].reshape(B, N, 3))
+        c = torch.einsum("bik,bnkj->bnij", T1, self.feat[:, 3:].reshape(B, N, 3, 3))
+        X12 = self.buf("X12", M, 12)
+        self.close(X12, torch.cat((p, c.reshape(B, N, 9)), 2).view(M, 12), "X12")
+        X1 = self.block_fwd("c1", X12, fe + ".conv1", fe + ".bn1", False)
+        T2 = self.tnet_fwd("t2", X1, fe + ".t2", 64)
+        X2 = self.buf("X2", M, 64)
+        self.close(X2, (X1.view(B, N, 64) @ T2).view(M, 64), "X2")
+        X3 = self.block_fwd("c2", X2, fe + ".conv2", fe + ".bn2", False)
+        X4 = self.block_fwd("c3", X3, fe + ".conv3", fe + ".bn3", False)
+        Gf = self.buf("Gf", B, F)
+        assert torch.equal(Gf, X4.view(B, N, F).amax(1)), "Gf"
+        H0 = self.buf("H0", M, 64 + F)
+        assert torch.equal(H0, torch.cat((X2.view(B, N, 64), Gf[:, None, :].expand(B, N, F)), 2).reshape(M, 64 + F)), "H0"
+        h = self.block_fwd("h1", H0, "conv1", "bn1", True)
+        h = self.block_fwd("h2", h, "conv2", "bn2", True)
+        h = self.block_fwd("h3", h, "conv3", "bn3", True)
+        Z = self.block_fwd("h4", h, "conv4", None, False)
+        self.close(self.out.view(M, self.C), torch.log_softmax(Z, 1), "logp")
+
+    # ---- backward.  Every block's ".dA" buffer holds dL/dY (after the in-place BatchNorm/ReLU gradient) once the pass is over.
+    def block_bwd(self, name, X, lin, bn, relu, dA):
+        """dA = fp64 gradient w.r.t. the block output, built by the caller from OUR downstream gradients.  Checks
+        dgamma/dbeta, dL/dY, dW, db; returns our dL/dY and the fp64 dL/dX computed from it."""
+        rows, out = dA.shape
+        if bn is not None:
+            Y, A = self.buf(name + ".Y", rows, out), self.buf(name + ".A", rows, out)
+            m = dA * (A > 0) if relu else dA
+            mean, rstd = Y.mean(0), 1 / torch.sqrt(Y.var(0, unbiased=False) + 1e-5)
+            xhat = (Y - mean) * rstd
+            dbeta, dgamma = m.sum(0), (m * xhat).sum(0)
+            self.close(self.grads[bn + ".bias"], dbeta, bn + ".bias.grad", m.abs().sum(0))
+            self.close(self.grads[bn + ".weight"], dgamma, bn + ".weight.grad", (m * xhat).abs().sum(0))
+            dY_want = self.params[bn + ".weight"] * rstd * (m - dbeta / rows - xhat * dgamma / rows)
+            # over the 2-16 rows of the T-Net FC layers the three terms cancel almost completely (1 - xhat^2 = eps/(var+eps)
+            # for two rows): measure the error against the size of the terms, not of their difference
+            scale = (self.params[bn + ".weight"] * rstd).abs() * (m.abs() + (dbeta / rows).abs() + (xhat * dgamma / rows).abs())
+        else:
+            dY_want, scale = dA, None
+        dY = self.buf(name + ".dA", rows, out)
+        self.close(dY, dY_want, name + ".dY", scale)
+        self.close(self.grads[lin + ".weight"].view(out, -1), dY.t() @ X, lin + ".weight.grad")
+        self.close(self.grads[lin + ".bias"], dY.sum(0), lin + ".bias.grad", dY.abs().sum(0))   # sums to ~0 before a BatchNorm
+        return dY, dY @ self.W(lin)
+
+    def scatter_max(self, dG, A, C):
+        B, N = self.B, self.N
+        idx = A.view(B, N, C).argmax(1)                    # first maximum, as k_maxpool_fwd
+        d = torch.zeros(B, N, C, dtype=torch.float64)
+        d.scatter_(1, idx[:, None, :], dG[:, None, :])
+        return d.view(B * N, C)
+
+    def tnet_bwd(self, t, X, p, d, dT):
+        B, N = self.B, self.N
+        f2A, f1A, G = self.buf(t + ".f2.A", B, 256), self.buf(t + ".f1.A", B, 512), self.buf(t + ".G", B, 1024)
+        _, d2 = self.block_bwd(t + ".f3", f2A, p + ".fc3", None, False, dT.reshape(B, d * d))
+        _, d1 = self.block_bwd(t + ".f2", f1A, p + ".fc2", p + ".bn5", True, d2)
+        _, dG = self.block_bwd(t + ".f1", G, p + ".fc1", p + ".bn4", True, d1)
+        self.close(self.buf(t + ".dG", B, 1024), dG, t + ".dG")
+        dG = self.buf(t + ".dG", B, 1024)
+        c3A, c2A, c1A = self.buf(t + ".c3.A", B * N, 1024), self.buf(t + ".c2.A", B * N, 128), self.buf(t + ".c1.A", B * N, 64)
+        _, dc2 = self.block_bwd(t + ".c3", c2A, p + ".conv3", p + ".bn3", True, self.scatter_max(dG, c3A, 1024))
+        _, dc1 = self.block_bwd(t + ".c2", c1A, p + ".conv2", p + ".bn2", True, dc2)
+        _, dX = self.block_bwd(t + ".c1", X, p + ".conv1", p + ".bn1", True, dc1)
+        return dX
+
+    def backward(self):
+        B, N, M, F, C = self.B, self.N, self.M, self.F, self.C
+        fe = "feature_extractor"
+        dl, logp = self.dlogp.view(M, C), self.out.view(M, C)
+        dZ = dl - logp.exp() * dl.sum(1, keepdim=True)
+        h3A, h2A, h1A, H0 = self.buf("h3.A", M, 128), self.buf("h2.A", M, 256), self.buf("h1.A", M, 512), self.buf("H0", M, 64 + F)
+        _, d3 = self.block_bwd("h4", h3A, "conv4", None, False, dZ)
+        _, d2 = self.block_bwd("h3", h2A, "conv3", "bn3", True, d3)
+        _, d1 = self.block_bwd("h2", h1A, "conv2", "bn2", True, d2)
+        _, dH0_h1 = self.block_bwd("h1", H0, "conv1", "bn1", True, d1)
+        dH0 = self.buf("dH0", M, 64 + F)
+        self.close(dH0[:, 64:], dH0_h1[:, 64:], "dH0[:, 64:]")
+        dGf = self.buf("dGf", B, F)
+        self.close(dGf, dH0[:, 64:].reshape(B, N, F).sum(1), "dGf")
+        c3A, c2A, X2, X1, X12 = (self.buf("c3.A", M, F), self.buf("c2.A", M, 128), self.buf("X2", M, 64), self.buf("c1.A", M, 64),
+                                 self.buf("X12", M, 12))
+        _, dc2 = self.block_bwd("c3", c2A, fe + ".conv3", fe + ".bn3", False, self.scatter_max(dGf, c3A, F))
+        _, dX2_c2 = self.block_bwd("c2", X2, fe + ".conv2", fe + ".bn2", False, dc2)
+        self.close(dH0[:, :64], dH0_h1[:, :64] + dX2_c2, "dX2 (two consumers)")
+        dX2 = dH0[:, :64].reshape(B, N, 64)
+        T2 = self.buf("t2.T", B, 64, 64)
+        dT2 = self.buf("t2.dT", B, 64, 64)
+        self.close(dT2, X1.view(B, N, 64).transpose(1, 2) @ dX2, "t2.dT")
+        dX1_t2 = self.tnet_bwd("t2", X1, fe + ".t2", 64, dT2)
+        dX1 = (dX2 @ T2.transpose(1, 2)).reshape(M, 64) + dX1_t2
+        _, dX12_want = self.block_bwd("c1", X12, fe + ".conv1", fe + ".bn1", False, dX1)
+        dX12 = self.buf("dX12", M, 12)
+        self.close(dX12, dX12_want, "dX12")
+        f = self.feat.view(B, N, 12)
+        d = dX12.view(B, N, 12)
+        dT1 = torch.einsum("bni,bnk->bik", d[:, :, :3], f[:, :, :3]) + torch.einsum(
+            "bnij,bnkj->bik", d[:, :, 3:].reshape(B, N, 3, 3), f[:, :, 3:].reshape(B, N, 3, 3))
+        self.close(self.buf("t1.dT", B, 3, 3), dT1, "t1.dT")
+        self.tnet_bwd("t1", self.feat[:, :3], fe + ".t1", 3, self.buf("t1.dT", B, 3, 3))
+
+
+@pytest.mark.parametrize("B,N,F,C", [(2, 1000, 768, 28), (4, 200, 768, 28), (5, 130, 1024, 16)])
+def test_every_layer_matches_an_fp64_replay_of_its_own_inputs(B, N, F, C):
+    """Forward and backward, layer by layer (config 3's per-GPU shape first: 2 clouds x 1000 distributions)."""
+    net = _net(F, C, 3)
+    pts, cov, gt = _batch(11 + B, B, N, C)
+    tr = SegTrainer(net)
+    out = tr(pts, cov)
+    out.retain_grad()
+    reference_loss(out, gt).backward()
+    rp = _Replay(net, tr, B, N, torch.cat((pts, cov), 2), out, out.grad)
+    rp.forward()
+    rp.backward()
+
+
+def test_eval_after_training_uses_the_updated_running_statistics():
+    net = _net(768, 28, 7)
+    pts, cov, gt = _batch(9, 4, 128, 28)
+    reference_loss(net.forward_b200(pts, cov), gt).backward()
+    net.eval()
+    with torch.no_grad():
+        want = net(pts, cov)
+        got = net.forward_b200(pts, cov)
+    assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+
+
+def test_trainer_rejects_single_cloud_batches():
+    net = _net(768, 28, 1)
+    pts, cov, _ = _batch(1, 1, 64, 28)
+    with pytest.raises(RuntimeError):            # train.py:50-51 skips such batches; BatchNorm cannot normalise one row
+        SegTrainer(net)(pts, cov)
