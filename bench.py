@@ -353,6 +353,11 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly one JSON line: native libraries that write to fd 1 (NCCL prints its version banner there)
+    # are pointed at stderr, Python's own stdout keeps the real descriptor
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -77,6 +77,9 @@ def main():
     ap.add_argument("--cpu-clouds", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    real_stdout = os.dup(1)          # NCCL's version banner goes to fd 1: keep stdout for the JSON line
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     import torch.distributed as dist
     from ndnet.preprocessing.ndtnet_preprocessing import ndt_preprocessing
     from ndnet_b200 import _lib
@@ -123,7 +126,7 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item() / args.steps, float(loss), L.ndnet_b200_launch_count() - launches0
+        return ms.item() / args.steps, float(loss.detach()), L.ndnet_b200_launch_count() - launches0
 
     ms_ours, loss_ours, ndt_launches = run("ours")
     ms_torch, loss_torch, _ = run("torch")
