@@ -76,6 +76,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-clouds", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--only-ours", action="store_true", help="skip the torch-autograd comparison run (for ncu launch lists)")
     args = ap.parse_args()
     real_stdout = os.dup(1)          # NCCL's version banner goes to fd 1: keep stdout for the JSON line
     os.dup2(2, 1)
@@ -129,7 +130,7 @@ def main():
         return ms.item() / args.steps, float(loss.detach()), L.ndnet_b200_launch_count() - launches0
 
     ms_ours, loss_ours, ndt_launches = run("ours")
-    ms_torch, loss_torch, _ = run("torch")
+    ms_torch, loss_torch, _ = (float("nan"), float("nan"), 0) if args.only_ours else run("torch")
     if rank == 0:
         line = {"metric": "clouds/sec (NDT + NDTNetSegmentation fwd+bwd + Adam), 100k-point scans, D=1000, F=768",
                 "config": {"workload": "config3: README training shape", "clouds_per_gpu_per_step": B, "n_gpus": world,
