@@ -82,7 +82,7 @@ static cudaError_t alloc(T *&p, size_t count) {
 void Workspace::release() {
     const bool keep = keep_point_voxels;
     cudaStream_t keep_side = side; cudaEvent_t keep_fork = ev_fork, keep_join = ev_join;
-    void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, vox_order, slot_rank, tile_cnt, hist, point_voxel, sorted, sorted_labels,
+    void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, vox_order, slot_rank, tile_cnt, hist, point_voxel, sorted,
                     mean, cov, cov_final, cls, kl_div, kl_flag, key, seq, firstpos, removed, list_div, list_seq};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = Workspace();
@@ -118,8 +118,7 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     A(tile_cnt, (size_t)nB * ntiles_cap * vcap);
     A(hist, (size_t)nB * vcap * (nbins > 0 ? nbins : 1));
     A(point_voxel, (size_t)nB * nN);
-    A(sorted_labels, (size_t)nB * nN);
-    if ((e = cudaMalloc(&sorted, (size_t)nB * nN * 3 * sizeof(double) + 16)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&sorted, (size_t)nB * nN * 4 * sizeof(double))) != cudaSuccess) return e;     // {x, y, z, label} records
     A(mean, (size_t)nB * vcap * 3);
     A(cov, (size_t)nB * vcap * 9);
     A(cov_final, (size_t)nB * vcap * 9);

@@ -23,6 +23,7 @@ constexpr unsigned kSmemBitmapBits = 1u << 18; // grids up to this many cells ar
 constexpr int kCountPointsPerCta = 4096;
 constexpr int kRankTile = 2048;                // points per rank tile (one warp walks one tile in order)
 constexpr unsigned kDropped = 0xFFFFFFFFu;
+constexpr int kSortedStride = 4;               // voxel-sorted points are {x, y, z, label bits}: one 16-byte store per point
 constexpr int kSmemLabelBins = 64;
 constexpr unsigned kHeavyVoxel = 512;           // voxels with at least this many points get a warp each in k_stats
 
@@ -272,5 +273,28 @@ __device__ __forceinline__ bool pseudo_kl(const double P[9], int psign, const do
     div = 0.5 * (first_part_result + trace - log(q_det / p_det) - 3);   // :115
     return true;
 }
+
+// Voxel-sorted point records {x, y, z, label bits} (k_scatter writes them with ONE vector store per point: the scatter is
+// bound by L2 store transactions, not bytes; k_stats / k_stats_light / k_votes read them back).
+template <typename T> __device__ __forceinline__ void store_sorted(T *q, T x, T y, T z, unsigned label);
+template <> __device__ __forceinline__ void store_sorted<float>(float *q, float x, float y, float z, unsigned label) {
+    *reinterpret_cast<float4 *>(q) = make_float4(x, y, z, __uint_as_float(label));
+}
+template <> __device__ __forceinline__ void store_sorted<double>(double *q, double x, double y, double z, unsigned label) {
+    *reinterpret_cast<double2 *>(q) = make_double2(x, y);
+    *reinterpret_cast<double2 *>(q + 2) = make_double2(z, __longlong_as_double((long long)label));
+}
+template <typename T> __device__ __forceinline__ void load_sorted(const T *p, T &x, T &y, T &z);
+template <> __device__ __forceinline__ void load_sorted<float>(const float *p, float &x, float &y, float &z) {
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    x = v.x; y = v.y; z = v.z;
+}
+template <> __device__ __forceinline__ void load_sorted<double>(const double *p, double &x, double &y, double &z) {
+    const double2 v = *reinterpret_cast<const double2 *>(p);
+    x = v.x; y = v.y; z = p[2];
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ unsigned sorted_label(const float *p) { return __float_as_uint(p[3]); }
+__device__ __forceinline__ unsigned sorted_label(const double *p) { return (unsigned)__double_as_longlong(p[3]); }
 
 }  // namespace ndt

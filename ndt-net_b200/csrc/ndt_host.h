@@ -48,7 +48,6 @@ struct Workspace {
     unsigned *slot_rank = nullptr, *tile_cnt = nullptr, *hist = nullptr;
     int *point_voxel = nullptr;
     void *sorted = nullptr;
-    uint16_t *sorted_labels = nullptr;
     bool keep_point_voxels = false;   // inspection only: k_rank also records every point's voxel id
     double *mean = nullptr, *cov = nullptr, *cov_final = nullptr;
     uint16_t *cls = nullptr;

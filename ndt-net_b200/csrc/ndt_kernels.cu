@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(256) k_scatter(const T *__restrict__ pts, cons
                                                  const CloudState *__restrict__ states, unsigned vcap, int ntiles,
                                                  const unsigned *__restrict__ slot_rank, const unsigned *__restrict__ tile_cnt,
                                                  const unsigned *__restrict__ vox_start, T *__restrict__ sorted,
-                                                 uint16_t *__restrict__ sorted_labels, unsigned *__restrict__ hist, int nbins) {
+                                                 unsigned *__restrict__ hist, int nbins) {
     const int b = blockIdx.y;
     if (states[b].status != 0) return;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -436,14 +436,10 @@ __global__ void __launch_bounds__(256) k_scatter(const T *__restrict__ pts, cons
     const int tile = (int)(i / kRankTile);
     const unsigned pos = vox_start[(size_t)b * (vcap + 1) + slot] + tile_cnt[((size_t)b * ntiles + tile) * vcap + slot] + rank;
     const T *p = pts + ((size_t)b * N + i) * 3;
-    T *q = sorted + ((size_t)b * N + pos) * 3;
-    q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
-    if (labels) {
-        const unsigned l = labels[(size_t)b * N + i];
-        sorted_labels[(size_t)b * N + pos] = (uint16_t)l;
-        // wide label sets (> kSmemLabelBins classes) vote through global atomics; small ones are counted by k_stats
-        if (hist && l < (unsigned)nbins) atomicAdd(&hist[((size_t)b * vcap + slot) * nbins + l], 1u);
-    }
+    const unsigned l = labels ? labels[(size_t)b * N + i] : 0u;
+    store_sorted<T>(sorted + ((size_t)b * N + pos) * kSortedStride, p[0], p[1], p[2], l);
+    // wide label sets (> kSmemLabelBins classes) vote through global atomics; small ones are counted by k_votes
+    if (labels && hist && l < (unsigned)nbins) atomicAdd(&hist[((size_t)b * vcap + slot) * nbins + l], 1u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -499,7 +495,7 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
             vv[q] = vox_order[(size_t)b * vcap + idx];
             const unsigned st = vox_start[(size_t)b * (vcap + 1) + vv[q]], en = vox_start[(size_t)b * (vcap + 1) + vv[q] + 1];
             nn[q] = en - st;
-            pp[q] = sorted + ((size_t)b * N + st) * 3;
+            pp[q] = sorted + ((size_t)b * N + st) * kSortedStride;
         } else { vv[q] = 0; nn[q] = 0; pp[q] = sorted; }
     }
 
@@ -529,7 +525,9 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
     for (int q = 0; q < kQ; q++)
     {
         nx[q][0] = nx[q][1] = nx[q][2] = 0;
-        if ((unsigned)lane < nn[q]) { nx[q][0] = pp[q][lane * 3 + 0]; nx[q][1] = pp[q][lane * 3 + 1]; nx[q][2] = pp[q][lane * 3 + 2]; }
+        if ((unsigned)lane < nn[q]) load_sorted<T>(pp[q] + lane * kSortedStride, nx[q][0], nx[q][1], nx[q][2]);
+        if ((unsigned)lane + 32u < nn[q]) prefetch_l2(pp[q] + (size_t)(lane + 32) * kSortedStride);
+        if ((unsigned)lane + 64u < nn[q]) prefetch_l2(pp[q] + (size_t)(lane + 64) * kSortedStride);
     }
 
     for (unsigned base = 0; base < nmax; base += 32) {
@@ -549,9 +547,10 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
 #pragma unroll
                 for (int j = 0; j < 3; j++) s_x[warp][q][lane][j] = make_double2(x[q][j], x[q][j] * rl);
             }
+            // a round lasts ~800 cycles, about one DRAM round trip: pull the records of the round after the next two into L2 now
+            if (base + 96 + lane < nn[q]) prefetch_l2(pp[q] + (size_t)(base + 96 + lane) * kSortedStride);
             if (base + 32 + lane < nn[q]) {      // issue the next round's global loads now; they land during phase A
-                const T *pn = pp[q] + (size_t)(base + 32 + lane) * 3;
-                nx[q][0] = pn[0]; nx[q][1] = pn[1]; nx[q][2] = pn[2];
+                load_sorted<T>(pp[q] + (size_t)(base + 32 + lane) * kSortedStride, nx[q][0], nx[q][1], nx[q][2]);
             }
         }
         __syncwarp();
@@ -711,14 +710,14 @@ __global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restric
     if (idx >= s.V) return;
     const unsigned v = vox_order[(size_t)b * vcap + idx];
     const unsigned st = vox_start[(size_t)b * (vcap + 1) + v], en = vox_start[(size_t)b * (vcap + 1) + v + 1];
-    const T *p = sorted + ((size_t)b * N + st) * 3;
+    const T *p = sorted + ((size_t)b * N + st) * kSortedStride;
     double mu0 = 0, mu1 = 0, mu2 = 0, m20 = 0, m21 = 0, m22 = 0, c01 = 0, c02 = 0, c12 = 0;
     const unsigned n = en - st;
     T a0 = 0, a1 = 0, a2 = 0;
-    if (n > 0) { a0 = p[0]; a1 = p[1]; a2 = p[2]; }
+    if (n > 0) load_sorted<T>(p, a0, a1, a2);
     for (unsigned k = 0; k < n; k++) {
         const double x0 = (double)a0, x1 = (double)a1, x2 = (double)a2;
-        if (k + 1 < n) { a0 = p[(size_t)(k + 1) * 3 + 0]; a1 = p[(size_t)(k + 1) * 3 + 1]; a2 = p[(size_t)(k + 1) * 3 + 2]; }   // overlaps this point's chain
+        if (k + 1 < n) load_sorted<T>(p + (size_t)(k + 1) * kSortedStride, a0, a1, a2);   // overlaps this point's chain
         const double c = (double)(k + 1);
         const double rh = 1.0 / c;
         const double rl = fma(-c, rh, 1.0) * rh;
@@ -756,10 +755,11 @@ __global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restric
 }
 
 // Label vote (normal_distributions.c:107-121): most frequent class of the voxel, lowest index on ties.  One warp
-// per voxel over its (sorted) labels, counts in shared memory; wide label sets were counted by k_scatter's global
+// per voxel over the label lane of its sorted point records, counts in shared memory; wide label sets were counted by k_scatter's global
 // atomics and only need the arg-max here.  grid (B, ceil(vcap/4)), block 128.
+template <typename T>
 __global__ void __launch_bounds__(128) k_votes(const CloudState *__restrict__ states, unsigned vcap, long N,
-                                               const uint16_t *__restrict__ sorted_labels, const unsigned *__restrict__ vox_start,
+                                               const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                                const unsigned *__restrict__ hist, int nbins, uint16_t *__restrict__ cls) {
     const int b = blockIdx.x;
     const CloudState &s = states[b];
@@ -775,9 +775,9 @@ __global__ void __launch_bounds__(128) k_votes(const CloudState *__restrict__ st
         for (int j = lane; j < kSmemLabelBins; j += 32) s_h[warp][j] = 0;
         __syncwarp();
         const unsigned st = vox_start[(size_t)b * (vcap + 1) + v], en = vox_start[(size_t)b * (vcap + 1) + v + 1];
-        const uint16_t *sl = sorted_labels + (size_t)b * N;
+        const T *sl = sorted + (size_t)b * N * kSortedStride;
         for (unsigned i = st + lane; i < en; i += 32) {
-            const unsigned l = sl[i];
+            const unsigned l = sorted_label(sl + (size_t)i * kSortedStride);
             if (l < (unsigned)nbins) atomicAdd(&s_h[warp][l], 1u);
         }
         __syncwarp();
@@ -1248,7 +1248,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     if (N > 0) {
         k_scatter<T><<<dim3((unsigned)((N + 255) / 256), B), 256, 0, st>>>(
             pts, labels, N, w.states, vcap, ntiles, w.slot_rank, w.tile_cnt, w.vox_start, (T *)w.sorted,
-            w.sorted_labels, wide_labels ? w.hist : nullptr, nbins);
+            wide_labels ? w.hist : nullptr, nbins);
         DBG("k_scatter");
     }
     tm.mark(ST_STATS, st);
@@ -1268,7 +1268,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, 0, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start,
                                                                          w.vox_order, w.mean, w.cov);
         if (labels) {
-            k_votes<<<dim3(B, (vcap + 3) / 4), 128, 0, w.side>>>(w.states, vcap, N, w.sorted_labels, w.vox_start,
+            k_votes<T><<<dim3(B, (vcap + 3) / 4), 128, 0, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start,
                                                                 wide_labels ? w.hist : nullptr, nbins, w.cls);
         }
         CK(cudaEventRecord(w.ev_join, w.side));
