@@ -228,6 +228,13 @@ int ndnet_b200_trainer_forward(ndnet_b200_trainer *t, const float *feat /* [B,N,
                                float *const *tensors, float *out_logp, int update_running_stats, void *stream);
 int ndnet_b200_trainer_backward(ndnet_b200_trainer *t, const float *dlogp, float *const *tensors, float *const *grads,
                                 void *stream);
+/* tf32 = 1: the large GEMMs (forward, dgrad, wgrad) run on the tensor cores (tcgen05 kind::tf32, operands read from the
+ * fp32 buffers, fp32 accumulation); tf32 = 0 (default): fp32 FMA everywhere (the parity configuration). */
+int ndnet_b200_trainer_set_precision(ndnet_b200_trainer *t, int tf32);
+/* Test hook: C[M,N] (+)= A[M,K] . B[N,K]^T (+ bias) through the training GEMM kernels, device pointers, row strides in
+ * floats.  mode 0 = fp32 FMA kernel, 1 = tcgen05 TF32 kernel (-206 when the shape/alignment is not eligible for it). */
+int ndnet_b200_debug_train_gemm(int mode, const float *A, long lda, const float *B, long ldb, float *C, long ldc, int M, int N,
+                                int K, const float *bias, int accumulate, void *stream);
 const char *ndnet_b200_trainer_last_error(const ndnet_b200_trainer *t);
 /* Test hook: copies one internal activation/gradient buffer of the last pass ("h3.dA", "t2.c1.Y", "c1.A", "t1.T", ...)
  * to `out` (device, may be NULL to query the size); returns the element count or -200. */

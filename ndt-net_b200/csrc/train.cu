@@ -12,6 +12,7 @@
 // GEMMs move to tcgen05.  At config 3's per-GPU size (2 clouds x 1000 rows) the step is launch-latency bound, not
 // FLOP bound.  Rows are [B*N, C] row-major fp32 throughout.
 #include "../../include/ndnet_b200.h"
+#include "train_gemm.cuh"
 
 #include <cuda_runtime.h>
 
@@ -340,6 +341,9 @@ struct Trainer {
     int *idxf = nullptr;
     float *logp = nullptr, *dZ = nullptr;
     const float *feat = nullptr;
+    int tf32 = 0;                         // 1: eligible GEMMs run on the tensor cores (kind::tf32), 0: fp32 FMA everywhere
+    float *sT1 = nullptr, *sT2 = nullptr, *sW = nullptr;      // transposed dY / X / W for the tensor-core wgrad and dgrad
+    long ldT = 0;
     std::string err;
 };
 
@@ -427,6 +431,13 @@ static void layout(Trainer &t, Bump &b, char *base, int B, int N) {
     TAKE(float, t.Gf, (size_t)B * t.F); TAKE(float, t.dGf, (size_t)B * t.F); TAKE(float, t.dX4, (size_t)M * t.F);
     TAKE(int, t.idxf, (size_t)B * t.F);
     TAKE(float, t.logp, (size_t)M * t.C); TAKE(float, t.dZ, (size_t)M * t.C);
+    {
+        const long ldT = (M + 3) / 4 * 4;
+        const size_t wide = (size_t)(64 + t.F > 1024 ? 64 + t.F : 1024);
+        if (base) t.ldT = ldT;
+        TAKE(float, t.sT1, wide * ldT); TAKE(float, t.sT2, wide * ldT);
+        TAKE(float, t.sW, (size_t)1024 * (64 + t.F > 1024 ? 64 + t.F : 1024));
+    }
     // the region zeroed at the start of every pass: reduction accumulators
     b.off = (b.off + 255) & ~(size_t)255;
     if (base) t.zero_begin = b.off;
@@ -482,6 +493,99 @@ static void gemm(cudaStream_t st, const float *A, long sai, long sak, const floa
     k_gemm32<<<grid, 256, 0, st>>>(p);
 }
 
+// ---- tcgen05 / TF32 path (train_gemm.cuh) --------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// fp32 [rows, K] row-major (ld floats between rows), read as TF32 (TMA rounds to nearest on load), 128-byte K-blocks
+static bool make_map_tf32(CUtensorMap *m, const float *ptr, long ld, int K, int rows, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * (cuuint64_t)rows};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<float *>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool tf32_eligible(const float *A, long lda, const float *Bm, long ldb, int M, int N, int K) {
+    return M >= 64 && N >= 32 && K >= 32 && lda % 4 == 0 && ldb % 4 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)Bm & 15) == 0;
+}
+
+template <int BN>
+static bool launch_tf32(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const Tf32Args &a, dim3 grid) {
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = tf32_smem_bytes<BN>();
+    if (dev < 64 && !attr_done[dev]) {
+        if (cudaFuncSetAttribute(k_gemm_tf32<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+        attr_done[dev] = true;
+    }
+    k_gemm_tf32<BN><<<grid, mlp::kGemmThreads, smem, st>>>(ma, mb, a);
+    return true;
+}
+
+// C[M, N] (+)= A[M, K] . B[N, K]^T (+ bias) on the tensor cores; false when the shape / alignment is not eligible
+static bool gemm_tf32(cudaStream_t st, const float *A, long lda, const float *Bm, long ldb, float *C, long ldc, int M, int N, int K,
+                      const float *bias, bool accumulate) {
+    if (!tf32_eligible(A, lda, Bm, ldb, M, N, K)) return false;
+    const int BN = N > 64 ? 128 : 64;
+    CUtensorMap ma, mb;
+    if (!make_map_tf32(&ma, A, lda, K, M, 128) || !make_map_tf32(&mb, Bm, ldb, K, N, BN)) return false;
+    Tf32Args a;
+    a.M = M; a.N = N; a.K = K; a.C = C; a.ldc = ldc; a.bias = bias; a.accumulate = accumulate ? 1 : 0;
+    const int nkb = (K + 31) / 32;
+    const long tiles = (long)cdiv(M, 128) * cdiv(N, BN);
+    int splitk = 1;
+    if (tiles < 74 && nkb >= 16) {
+        splitk = (int)((148 + tiles - 1) / tiles);
+        if (splitk > nkb / 4) splitk = nkb / 4;
+        if (splitk < 1) splitk = 1;
+    }
+    a.kb_per_split = (nkb + splitk - 1) / splitk;
+    a.splitk = (nkb + a.kb_per_split - 1) / a.kb_per_split;          // every z gets at least one K-block
+    if (a.splitk > 1 && !accumulate) {
+        if (ldc == N) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st);
+        else cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st);
+    }
+    dim3 grid(cdiv(N, BN), cdiv(M, 128), a.splitk);
+    return BN == 128 ? launch_tf32<128>(st, ma, mb, a, grid) : launch_tf32<64>(st, ma, mb, a, grid);
+}
+
+// dst[c, r] = src[r, c]  (dst row stride ldd >= rows, a multiple of 4 floats for the TMA)
+__global__ void __launch_bounds__(256) k_transpose(const float *__restrict__ src, long lds, int rows, int cols, float *__restrict__ dst, long ldd) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    for (int k = ty; k < 32; k += 8) {
+        const int r = r0 + k, c = c0 + tx;
+        tile[k][tx] = (r < rows && c < cols) ? src[(long)r * lds + c] : 0.f;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int c = c0 + k, r = r0 + tx;
+        if (c < cols && r < rows) dst[(long)c * ldd + r] = tile[tx][k];
+    }
+}
+
+static void transpose(cudaStream_t st, const float *src, long lds, int rows, int cols, float *dst, long ldd) {
+    k_transpose<<<dim3(cdiv(cols, 32), cdiv(rows, 32)), 256, 0, st>>>(src, lds, rows, cols, dst, ldd);
+}
+
 template <int OP>
 static void colred(cudaStream_t st, RedP p, int batch) {
     const unsigned ysplit = p.rows >= 4096 ? 32 : p.rows >= 512 ? 8 : 1;
@@ -501,7 +605,8 @@ struct Pass {
 
 static void block_fwd(const Pass &ps, Block &k, const float *X, long ldx) {
     const int out = k.lin.out, in = k.lin.in;
-    gemm(ps.st, X, ldx, 1, ps.P(k.lin.w), in, 1, k.Y, out, (int)k.rows, out, in, ps.P(k.lin.b), false);
+    if (!(ps.t.tf32 && gemm_tf32(ps.st, X, ldx, ps.P(k.lin.w), in, k.Y, out, (int)k.rows, out, in, ps.P(k.lin.b), false)))
+        gemm(ps.st, X, ldx, 1, ps.P(k.lin.w), in, 1, k.Y, out, (int)k.rows, out, in, ps.P(k.lin.b), false);
     if (!k.has_bn) return;
     RedP r{};
     r.P = k.Y; r.ldp = out; r.rows = (int)k.rows; r.cols = out; r.s0 = k.red; r.s1 = k.red + out;
@@ -530,10 +635,25 @@ static void block_bwd(const Pass &ps, Block &k, const float *X, long ldx, float 
         colred<RED_SUM>(ps.st, r, 1);
         k_sum_finalize<<<cdiv(out, 128), 128, 0, ps.st>>>(k.red_bias, out, ps.Gr(k.lin.b));
     }
-    if (ps.Gr(k.lin.w))      // dW[o, i] = sum_rows dY[r, o] X[r, i]
-        gemm(ps.st, dY, 1, out, X, 1, ldx, ps.Gr(k.lin.w), in, out, in, (int)k.rows, nullptr, false);
-    if (dX)                  // dX[r, i] = sum_o dY[r, o] W[o, i]
-        gemm(ps.st, dY, out, 1, ps.P(k.lin.w), 1, in, dX, lddx, (int)k.rows, in, out, nullptr, accumulate_dx);
+    Trainer &t = ps.t;
+    const int rows = (int)k.rows;
+    if (ps.Gr(k.lin.w)) {    // dW[o, i] = sum_rows dY[r, o] X[r, i]
+        bool done = false;
+        if (t.tf32 && rows >= 256 && out >= 64 && in >= 32) {      // contraction over the rows: both operands transposed to K-major
+            transpose(ps.st, dY, out, rows, out, t.sT1, t.ldT);
+            transpose(ps.st, X, ldx, rows, in, t.sT2, t.ldT);
+            done = gemm_tf32(ps.st, t.sT1, t.ldT, t.sT2, t.ldT, ps.Gr(k.lin.w), in, out, in, rows, nullptr, false);
+        }
+        if (!done) gemm(ps.st, dY, 1, out, X, 1, ldx, ps.Gr(k.lin.w), in, out, in, rows, nullptr, false);
+    }
+    if (dX) {                // dX[r, i] = sum_o dY[r, o] W[o, i]
+        bool done = false;
+        if (t.tf32 && rows >= 256 && in >= 32 && out >= 32 && out % 4 == 0) {
+            transpose(ps.st, ps.P(k.lin.w), in, out, in, t.sW, out);          // W^T [in, out]
+            done = gemm_tf32(ps.st, dY, out, t.sW, out, dX, lddx, rows, in, out, nullptr, accumulate_dx);
+        }
+        if (!done) gemm(ps.st, dY, out, 1, ps.P(k.lin.w), 1, in, dX, lddx, rows, in, out, nullptr, accumulate_dx);
+    }
 }
 
 static void tnet_fwd(const Pass &ps, TNet &n, const float *X, long ldx) {
@@ -668,6 +788,27 @@ extern "C" int ndnet_b200_trainer_create(int device, int n_tensors, const char *
     if (!ok) return fail("tensor binding failed");
     *out = h;
     return 0;
+}
+
+extern "C" int ndnet_b200_trainer_set_precision(ndnet_b200_trainer *h, int tf32) {
+    if (!h || (tf32 != 0 && tf32 != 1)) return -200;
+    h->t.tf32 = tf32;
+    return 0;
+}
+
+// Test hook: C[M,N] (+)= A[M,K] . B[N,K]^T (+ bias) through the training GEMMs.  mode 0 = fp32 FMA kernel, 1 = tcgen05 TF32
+// kernel (-206 when the shape is not eligible for it).
+extern "C" int ndnet_b200_debug_train_gemm(int mode, const float *A, long lda, const float *B, long ldb, float *C, long ldc, int M,
+                                           int N, int K, const float *bias, int accumulate, void *stream) {
+    if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return -200;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 1) {
+        if (!train::gemm_tf32(st, A, lda, B, ldb, C, ldc, M, N, K, bias, accumulate != 0)) return -206;
+    } else {
+        train::gemm(st, A, lda, 1, B, ldb, 1, C, ldc, M, N, K, bias, accumulate != 0);
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -100 - (int)e;
 }
 
 extern "C" const char *ndnet_b200_trainer_last_error(const ndnet_b200_trainer *h) { return h ? h->t.err.c_str() : "null trainer"; }

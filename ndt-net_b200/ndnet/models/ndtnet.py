@@ -90,7 +90,7 @@ class _B200Mixin:
             from ndnet_b200.train import SegTrainer          # train-mode BatchNorm + gradients from train.cu
             tr = getattr(self, "_b200_trainer", None)
             if tr is None or tr.device != points.device:
-                tr = SegTrainer(self, points.device)
+                tr = SegTrainer(self, points.device, tf32=bool(getattr(self, "b200_tf32", False)))
                 object.__setattr__(self, "_b200_trainer", tr)
             return tr(points, covariances)
         m = getattr(self, "_b200_model", None)

@@ -93,6 +93,10 @@ def lib() -> C.CDLL:
     L.ndnet_b200_trainer_forward.argtypes = [vp, vp, i, i, C.POINTER(vp), vp, i, vp]
     L.ndnet_b200_trainer_backward.restype = i
     L.ndnet_b200_trainer_backward.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
+    L.ndnet_b200_trainer_set_precision.restype = i
+    L.ndnet_b200_trainer_set_precision.argtypes = [vp, i]
+    L.ndnet_b200_debug_train_gemm.restype = i
+    L.ndnet_b200_debug_train_gemm.argtypes = [i, vp, l, vp, l, vp, l, i, i, i, vp, i, vp]
     L.ndnet_b200_trainer_last_error.restype = C.c_char_p
     L.ndnet_b200_trainer_last_error.argtypes = [vp]
     L.ndnet_b200_trainer_debug_buffer.restype = l
@@ -112,5 +116,5 @@ EXPORTED = [
     "ndnet_b200_infer_host", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline",
     "ndnet_b200_ply_load", "ndnet_b200_ply_num_points", "ndnet_b200_ply_sample", "ndnet_b200_ply_free",
     "ndnet_b200_trainer_create", "ndnet_b200_trainer_forward", "ndnet_b200_trainer_backward", "ndnet_b200_trainer_last_error",
-    "ndnet_b200_trainer_debug_buffer", "ndnet_b200_trainer_destroy",
+    "ndnet_b200_trainer_set_precision", "ndnet_b200_debug_train_gemm", "ndnet_b200_trainer_debug_buffer", "ndnet_b200_trainer_destroy",
 ]

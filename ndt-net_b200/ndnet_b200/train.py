@@ -19,7 +19,9 @@ from . import _lib
 
 
 class SegTrainer:
-    def __init__(self, module: torch.nn.Module, device: torch.device | int | None = None):
+    def __init__(self, module: torch.nn.Module, device: torch.device | int | None = None, tf32: bool = False):
+        """tf32=False: fp32 FMA everywhere (parity configuration).  tf32=True: the large GEMMs run on the tensor cores
+        (tcgen05 kind::tf32, fp32 accumulation) — the counterpart of torch.backends.cuda.matmul.allow_tf32."""
         self.module = module
         p0 = next(module.parameters())
         dev = p0.device if device is None else (torch.device("cuda", device) if isinstance(device, int) else torch.device(device))
@@ -44,6 +46,8 @@ class SegTrainer:
         if rc != 0:
             raise RuntimeError(f"ndnet_b200_trainer_create failed ({rc}): not an NDTNetSegmentation state_dict?")
         self._h = h
+        self.tf32 = bool(tf32)
+        self._L.ndnet_b200_trainer_set_precision(h, int(self.tf32))
         self.num_out = int(module.num_classes) + 1
 
     def _tensors(self):
@@ -111,6 +115,19 @@ class _SegTrainFn(torch.autograd.Function):
                                                     trainer._ptr_array(grads + [None] * (len(tensors) - n_params)), stream)
         trainer._check(rc, "ndnet_b200_trainer_backward")
         return (None, None, *grads)
+
+
+def debug_gemm(mode: int, A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, bias: torch.Tensor | None = None,
+               accumulate: bool = False) -> int:
+    """Test hook: C (+)= A @ B.T (+ bias) through the training GEMM kernels (0 = fp32 FMA, 1 = tcgen05 TF32).  2-D CUDA fp32
+    tensors whose last dimension is contiguous (row strides may exceed the width).  Returns the library's status code."""
+    L = _lib.lib()
+    M, K = A.shape
+    N = B.shape[0]
+    assert B.shape[1] == K and tuple(C.shape) == (M, N) and A.stride(1) == B.stride(1) == C.stride(1) == 1
+    return L.ndnet_b200_debug_train_gemm(mode, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), C.data_ptr(), C.stride(0), M, N, K,
+                                         bias.data_ptr() if bias is not None else None, int(accumulate),
+                                         torch.cuda.current_stream(A.device).cuda_stream)
 
 
 def allreduce_gradients(module: torch.nn.Module, world_size: int | None = None) -> int:

@@ -311,3 +311,47 @@ def test_trainer_rejects_single_cloud_batches():
     pts, cov, _ = _batch(1, 1, 64, 28)
     with pytest.raises(RuntimeError):            # train.py:50-51 skips such batches; BatchNorm cannot normalise one row
         SegTrainer(net)(pts, cov)
+
+
+@pytest.mark.parametrize("M,N,K,pad,bias,acc", [(2000, 832, 512, 0, True, False), (256, 128, 64, 0, False, False),
+                                                (2000, 64, 128, 0, True, True), (512, 832, 2000, 0, False, False),
+                                                (128, 64, 16000, 0, False, False), (300, 100, 36, 4, True, False),
+                                                (1000, 1024, 128, 8, False, True), (64, 32, 32, 0, False, False)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_training_gemm_kernels(mode, M, N, K, pad, bias, acc):
+    """C (+)= A . B^T (+ bias): the fp32 FMA kernel to 1e-5, the tcgen05 TF32 kernel to TF32 precision (operands rounded to
+    10 mantissa bits, fp32 accumulation: 2e-3 of the row/column norms).  Covers split-K (few tiles, long K), ragged tiles,
+    padded row strides, bias and accumulation."""
+    from ndnet_b200.train import debug_gemm
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn((M, K + pad), device="cuda", generator=g)[:, :K]
+    B = torch.randn((N, K + pad), device="cuda", generator=g)[:, :K]
+    C0 = torch.randn((M, N + pad), device="cuda", generator=g)
+    C = C0.clone()[:, :N]
+    b = torch.randn((N,), device="cuda", generator=g) if bias else None
+    rc = debug_gemm(mode, A, B, C, b, acc)
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    want = A.double() @ B.double().t()
+    if bias:
+        want = want + b.double()
+    if acc:
+        want = want + C0[:, :N].double()
+    scale = A.double().norm(dim=1, keepdim=True) * B.double().norm(dim=1)[None, :] + 1.0
+    err = ((C.double() - want).abs() / scale).max().item()
+    assert err <= (2e-3 if mode == 1 else 1e-5), err
+
+
+@pytest.mark.parametrize("B,N", [(2, 1000), (4, 200)])
+def test_every_layer_matches_the_replay_with_tensor_core_gemms(B, N):
+    """tf32=True: same layer-by-layer replay, tolerance at TF32 precision (3e-3)."""
+    F, C = 768, 28
+    net = _net(F, C, 3)
+    pts, cov, gt = _batch(11 + B, B, N, C)
+    tr = SegTrainer(net, tf32=True)
+    out = tr(pts, cov)
+    out.retain_grad()
+    reference_loss(out, gt).backward()
+    rp = _Replay(net, tr, B, N, torch.cat((pts, cov), 2), out, out.grad, tol=3e-3)
+    rp.forward()
+    rp.backward()

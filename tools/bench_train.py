@@ -76,6 +76,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-clouds", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fp32", action="store_true", help="train.cu GEMMs on the fp32 FMA kernel instead of tcgen05 TF32")
     ap.add_argument("--only-ours", action="store_true", help="skip the torch-autograd comparison run (for ncu launch lists)")
     args = ap.parse_args()
     real_stdout = os.dup(1)          # NCCL's version banner goes to fd 1: keep stdout for the JSON line
@@ -99,6 +100,7 @@ def main():
 
     def run(mode):
         net = build(dev)
+        net.b200_tf32 = not args.fp32
         opt = torch.optim.Adam(net.parameters(), lr=0.034)              # tools/train.py:108,147
 
         def step(i):
@@ -139,7 +141,7 @@ def main():
                 "network_on_torch_autograd": {"value": B * world / (ms_torch * 1e-3), "ms_per_step": ms_torch, "loss_last": loss_torch,
                                               "note": "same NDT kernels, network fwd/bwd through torch (cuBLAS/cuDNN) instead of train.cu"},
                 "ndt_launches_per_step": ndt_launches / args.steps, "steps": args.steps, "warmup": args.warmup,
-                "dtype": "f64 (NDT) + f32 (network fwd/bwd)", "data": "synthetic"}
+                "dtype": "f64 (NDT) + " + ("f32" if args.fp32 else "tf32 tensor-core GEMMs, f32 accumulate/elementwise") + " (network fwd/bwd)", "data": "synthetic"}
         if not args.no_cpu and world == 1:
             threads = os.cpu_count() or 1
             cpu_reference_step(2, threads)
