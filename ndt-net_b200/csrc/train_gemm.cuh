@@ -102,6 +102,7 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
         const int row = a_row0 + warp * 32 + lane;
         const bool add_bias = args.bias != nullptr && blockIdx.z == 0;
+        const bool vec = args.splitk == 1 && args.ldc % 4 == 0 && ((uintptr_t)args.C & 15) == 0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             if (b_row0 + c0 >= args.N) break;                 // warp-uniform
@@ -110,15 +111,30 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             ptx::tmem_ld_wait();
             if (row < args.M) {
                 float *dst = args.C + (size_t)row * args.ldc + b_row0 + c0;
+                if (vec && b_row0 + c0 + 32 <= args.N) {          // full 32-column chunk: eight 16-byte stores per row
+                    float4 *d4 = reinterpret_cast<float4 *>(dst);
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int col = b_row0 + c0 + j;
-                    if (col < args.N) {
-                        float r = __uint_as_float(v[j]);
-                        if (add_bias) r += args.bias[col];
-                        if (args.splitk > 1) atomicAdd(dst + j, r);
-                        else if (args.accumulate) dst[j] += r;
-                        else dst[j] = r;
+                    for (int q = 0; q < 8; q++) {
+                        float4 r = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                               __uint_as_float(v[4 * q + 3]));
+                        if (add_bias) {
+                            const float *bq = args.bias + b_row0 + c0 + 4 * q;
+                            r.x += bq[0]; r.y += bq[1]; r.z += bq[2]; r.w += bq[3];
+                        }
+                        if (args.accumulate) { const float4 o = d4[q]; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+                        d4[q] = r;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int col = b_row0 + c0 + j;
+                        if (col < args.N) {
+                            float r = __uint_as_float(v[j]);
+                            if (add_bias) r += args.bias[col];
+                            if (args.splitk > 1) atomicAdd(dst + j, r);
+                            else if (args.accumulate) dst[j] += r;
+                            else dst[j] = r;
+                        }
                     }
                 }
             }
