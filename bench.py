@@ -200,6 +200,8 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from ndnet_b200.dist import bind_to_gpu_numa_node
+    print(f"[rank {rank}] {bind_to_gpu_numa_node(local)}", file=sys.stderr)      # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()

@@ -113,3 +113,9 @@ def test_product_path_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "from oracle" not in text and "libndt_oracle" not in text, f
+
+
+def test_cpulist_parser():
+    from ndnet_b200.dist import _parse_cpulist
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
