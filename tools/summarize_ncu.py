@@ -44,7 +44,10 @@ def launches(path, out):
 def kernel(rep, name, batch, out):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    H, U, V = rows[0], rows[1], rows[2]
+    H, U = rows[0], rows[1]
+    kn = H.index("Kernel Name")
+    base = lambda r: r[kn].split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()   # noqa: E731
+    V = next((r for r in rows[2:] if len(r) > kn and base(r) == name), rows[2])       # the report may hold several kernels
     keep = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
