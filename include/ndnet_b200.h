@@ -228,6 +228,16 @@ int ndnet_b200_trainer_forward(ndnet_b200_trainer *t, const float *feat /* [B,N,
                                float *const *tensors, float *out_logp, int update_running_stats, void *stream);
 int ndnet_b200_trainer_backward(ndnet_b200_trainer *t, const float *dlogp, float *const *tensors, float *const *grads,
                                 void *stream);
+/* Same, with the gradients of all parameters written into ONE flat device buffer: parameter i (a weight, bias or
+ * BatchNorm scale/shift) starts at offsets[i] floats (16-byte aligned; -1 for buffers), total length = the return value
+ * of ndnet_b200_trainer_grad_layout. */
+int ndnet_b200_trainer_backward_flat(ndnet_b200_trainer *t, const float *dlogp, float *const *tensors, float *flat_grads,
+                                     void *stream);
+long ndnet_b200_trainer_grad_layout(const ndnet_b200_trainer *t, long *offsets, int n_tensors);
+/* enable = 1: the ~100 / ~250 kernel launches of a forward / backward pass are captured into CUDA graphs (one per shape
+ * and pointer set; the first pass of a configuration runs eagerly) and replayed; inputs and outputs are staged through
+ * library-owned buffers so the replayed pointers never change.  Default 0. */
+int ndnet_b200_trainer_set_graph(ndnet_b200_trainer *t, int enable);
 /* tf32 = 1: the large GEMMs (forward, dgrad, wgrad) run on the tensor cores (tcgen05 kind::tf32, operands read from the
  * fp32 buffers, fp32 accumulation); tf32 = 0 (default): fp32 FMA everywhere (the parity configuration). */
 int ndnet_b200_trainer_set_precision(ndnet_b200_trainer *t, int tf32);

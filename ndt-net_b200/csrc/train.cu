@@ -341,6 +341,15 @@ struct Trainer {
     int *idxf = nullptr;
     float *logp = nullptr, *dZ = nullptr;
     const float *feat = nullptr;
+    // CUDA graphs: the ~100 (forward) / ~250 (backward) launches of one pass are captured once per (shape, pointer set) and
+    // replayed; the first pass of a configuration runs eagerly (one-time attribute calls stay out of the capture)
+    int use_graph = 0;
+    cudaStream_t cap = nullptr;
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; std::vector<const void *> key; int seen = 0; } gf, gb;
+    float *feat_static = nullptr, *dlogp_static = nullptr, *flat_grad = nullptr;
+    std::vector<long> grad_off;           // per tensor: offset (floats) of its gradient in the flat buffer, -1 for buffers
+    long flat_elems = 0;
+    std::vector<float *> static_grads;
     int tf32 = 0;                         // 1: eligible GEMMs run on the tensor cores (kind::tf32), 0: fp32 FMA everywhere
     float *sT1 = nullptr, *sT2 = nullptr, *sW = nullptr;      // transposed dY / X / W for the tensor-core wgrad and dgrad
     long ldT = 0;
@@ -431,6 +440,7 @@ static void layout(Trainer &t, Bump &b, char *base, int B, int N) {
     TAKE(float, t.Gf, (size_t)B * t.F); TAKE(float, t.dGf, (size_t)B * t.F); TAKE(float, t.dX4, (size_t)M * t.F);
     TAKE(int, t.idxf, (size_t)B * t.F);
     TAKE(float, t.logp, (size_t)M * t.C); TAKE(float, t.dZ, (size_t)M * t.C);
+    TAKE(float, t.feat_static, (size_t)M * 12); TAKE(float, t.dlogp_static, (size_t)M * t.C); TAKE(float, t.flat_grad, (size_t)t.flat_elems);
     {
         const long ldT = (M + 3) / 4 * 4;
         const size_t wide = (size_t)(64 + t.F > 1024 ? 64 + t.F : 1024);
@@ -704,7 +714,7 @@ static int forward(Trainer &t, const float *feat, int B, int N, float *const *te
     block_fwd(ps, t.h3, t.h2.A, 256);
     block_fwd(ps, t.h4, t.h3.A, 128);                                                     // :236
     k_logsm_fwd<<<cdiv(M, 128), 128, 0, st>>>(t.h4.Y, M, t.C, t.logp);                    // :239
-    cudaMemcpyAsync(out_logp, t.logp, sizeof(float) * M * t.C, cudaMemcpyDeviceToDevice, st);
+    if (out_logp) cudaMemcpyAsync(out_logp, t.logp, sizeof(float) * M * t.C, cudaMemcpyDeviceToDevice, st);
     e = cudaGetLastError();
     if (e != cudaSuccess) { t.err = std::string("forward: ") + cudaGetErrorString(e); return -100 - (int)e; }
     return 0;
@@ -742,6 +752,75 @@ static int backward(Trainer &t, const float *dlogp, float *const *tensors, float
     tnet_bwd(ps, t.t1, t.feat, 12, nullptr, 0, false);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { t.err = std::string("backward: ") + cudaGetErrorString(e); return -100 - (int)e; }
+    return 0;
+}
+
+// ---- CUDA-graph replay of a pass ------------------------------------------------------------------------------------
+template <typename Body>
+static int run_graphed(Trainer &t, Trainer::GraphSlot &g, const std::vector<const void *> &key, cudaStream_t st, Body body) {
+    if (g.key != key) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g.exec = nullptr; g.key = key; g.seen = 0;
+    }
+    if (g.seen == 0) { g.seen = 1; return body(st); }              // first pass of this configuration: eager
+    if (g.seen == 1) {
+        if (!t.cap && cudaStreamCreateWithFlags(&t.cap, cudaStreamNonBlocking) != cudaSuccess) return body(st);
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(t.cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return body(st); }
+        const int rc = body(t.cap);
+        cudaError_t e = cudaStreamEndCapture(t.cap, &graph);
+        if (rc != 0 || e != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); g.seen = 0; return rc != 0 ? rc : body(st); }
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; g.seen = 0; return body(st); }
+        g.seen = 2;
+    }
+    const cudaError_t e = cudaGraphLaunch(g.exec, st);
+    if (e != cudaSuccess) { t.err = std::string("graph launch: ") + cudaGetErrorString(e); return -100 - (int)e; }
+    return 0;
+}
+
+static std::vector<const void *> pass_key(const Trainer &t, float *const *tensors, int extra) {
+    std::vector<const void *> key;
+    key.reserve(t.n_tensors + 4);
+    key.push_back((const void *)t.arena);
+    key.push_back((const void *)(uintptr_t)(((uint64_t)t.B << 32) | (uint32_t)t.N));
+    key.push_back((const void *)(uintptr_t)((t.tf32 << 8) | extra));
+    for (int i = 0; i < t.n_tensors; i++) key.push_back(tensors[i]);
+    return key;
+}
+
+static int forward_entry(Trainer &t, const float *feat, int B, int N, float *const *tensors, float *out_logp, int update_running, cudaStream_t st) {
+    if (!t.use_graph) return forward(t, feat, B, N, tensors, out_logp, update_running, st);
+    cudaError_t e = reserve(t, B, N);
+    if (e != cudaSuccess) { t.err = std::string("workspace: ") + cudaGetErrorString(e); return -100 - (int)e; }
+    const long M = (long)B * N;
+    cudaMemcpyAsync(t.feat_static, feat, sizeof(float) * M * 12, cudaMemcpyDeviceToDevice, st);
+    const int rc = run_graphed(t, t.gf, pass_key(t, tensors, update_running ? 1 : 0), st, [&](cudaStream_t s) {
+        return forward(t, t.feat_static, B, N, tensors, nullptr, update_running, s);
+    });
+    if (rc != 0) return rc;
+    cudaMemcpyAsync(out_logp, t.logp, sizeof(float) * M * t.C, cudaMemcpyDeviceToDevice, st);
+    return 0;
+}
+
+// gradients of all parameters into one flat buffer (layout: Trainer::grad_off)
+static int backward_flat(Trainer &t, const float *dlogp, float *const *tensors, float *flat_out, cudaStream_t st) {
+    if (!t.arena || !t.feat) { t.err = "backward without forward"; return -204; }
+    std::vector<float *> grads(t.n_tensors, nullptr);
+    if (!t.use_graph) {
+        for (int i = 0; i < t.n_tensors; i++) if (t.grad_off[i] >= 0) grads[i] = flat_out + t.grad_off[i];
+        return backward(t, dlogp, tensors, grads.data(), st);
+    }
+    const long M = (long)t.B * t.N;
+    cudaMemcpyAsync(t.dlogp_static, dlogp, sizeof(float) * M * t.C, cudaMemcpyDeviceToDevice, st);
+    t.static_grads.assign(t.n_tensors, nullptr);
+    for (int i = 0; i < t.n_tensors; i++) if (t.grad_off[i] >= 0) t.static_grads[i] = t.flat_grad + t.grad_off[i];
+    const int rc = run_graphed(t, t.gb, pass_key(t, tensors, 2), st, [&](cudaStream_t s) {
+        return backward(t, t.dlogp_static, tensors, t.static_grads.data(), s);
+    });
+    if (rc != 0) return rc;
+    cudaMemcpyAsync(flat_out, t.flat_grad, sizeof(float) * t.flat_elems, cudaMemcpyDeviceToDevice, st);
     return 0;
 }
 
@@ -786,7 +865,46 @@ extern "C" int ndnet_b200_trainer_create(int device, int n_tensors, const char *
               bind_block(t, t.h2, "conv2", "bn2", 512, 256, true) && bind_block(t, t.h3, "conv3", "bn3", 256, 128, true) &&
               bind_block(t, t.h4, "conv4", "", 128, t.C, false);
     if (!ok) return fail("tensor binding failed");
+    {   // flat gradient layout: parameters (weights, biases, BatchNorm scale/shift) in tensor order, 16-byte aligned
+        t.grad_off.assign(n_tensors, -1);
+        std::vector<char> is_param(n_tensors, 0);
+        Block *all[] = {&t.t1.c1, &t.t1.c2, &t.t1.c3, &t.t1.f1, &t.t1.f2, &t.t1.f3, &t.t2.c1, &t.t2.c2, &t.t2.c3, &t.t2.f1, &t.t2.f2, &t.t2.f3,
+                        &t.c1, &t.c2, &t.c3, &t.h1, &t.h2, &t.h3, &t.h4};
+        for (Block *k : all) {
+            is_param[k->lin.w] = is_param[k->lin.b] = 1;
+            if (k->has_bn) is_param[k->bn.g] = is_param[k->bn.be] = 1;
+        }
+        long off = 0;
+        for (int i = 0; i < n_tensors; i++) {
+            if (!is_param[i]) continue;
+            long numel = 1;
+            for (auto v : t.shapes[i]) numel *= v;
+            t.grad_off[i] = off;
+            off += (numel + 3) / 4 * 4;
+        }
+        t.flat_elems = off;
+    }
     *out = h;
+    return 0;
+}
+
+extern "C" int ndnet_b200_trainer_backward_flat(ndnet_b200_trainer *h, const float *dlogp, float *const *tensors, float *flat_grads,
+                                                void *stream) {
+    if (!h || !dlogp || !tensors || !flat_grads) return -200;
+    cudaError_t e = cudaSetDevice(h->t.device);
+    if (e != cudaSuccess) return -100 - (int)e;
+    return train::backward_flat(h->t, dlogp, tensors, flat_grads, (cudaStream_t)stream);
+}
+
+extern "C" long ndnet_b200_trainer_grad_layout(const ndnet_b200_trainer *h, long *offsets, int n) {
+    if (!h) return -200;
+    for (int i = 0; offsets && i < n && i < h->t.n_tensors; i++) offsets[i] = h->t.grad_off[i];
+    return h->t.flat_elems;
+}
+
+extern "C" int ndnet_b200_trainer_set_graph(ndnet_b200_trainer *h, int enable) {
+    if (!h || (enable != 0 && enable != 1)) return -200;
+    h->t.use_graph = enable;
     return 0;
 }
 
@@ -818,7 +936,7 @@ extern "C" int ndnet_b200_trainer_forward(ndnet_b200_trainer *h, const float *fe
     if (!h || !feat || !tensors || !out_logp || B < 2 || N < 1) return -200;      // BatchNorm needs more than one row per channel
     cudaError_t e = cudaSetDevice(h->t.device);
     if (e != cudaSuccess) return -100 - (int)e;
-    return train::forward(h->t, feat, B, N, tensors, out_logp, update_running_stats, (cudaStream_t)stream);
+    return train::forward_entry(h->t, feat, B, N, tensors, out_logp, update_running_stats, (cudaStream_t)stream);
 }
 
 extern "C" int ndnet_b200_trainer_backward(ndnet_b200_trainer *h, const float *dlogp, float *const *tensors, float *const *grads,
@@ -877,6 +995,9 @@ extern "C" long ndnet_b200_trainer_debug_buffer(ndnet_b200_trainer *h, const cha
 extern "C" void ndnet_b200_trainer_destroy(ndnet_b200_trainer *h) {
     if (!h) return;
     cudaSetDevice(h->t.device);
+    if (h->t.gf.exec) cudaGraphExecDestroy(h->t.gf.exec);
+    if (h->t.gb.exec) cudaGraphExecDestroy(h->t.gb.exec);
+    if (h->t.cap) cudaStreamDestroy(h->t.cap);
     if (h->t.arena) cudaFree(h->t.arena);
     delete h;
 }

@@ -93,6 +93,12 @@ def lib() -> C.CDLL:
     L.ndnet_b200_trainer_forward.argtypes = [vp, vp, i, i, C.POINTER(vp), vp, i, vp]
     L.ndnet_b200_trainer_backward.restype = i
     L.ndnet_b200_trainer_backward.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), vp]
+    L.ndnet_b200_trainer_backward_flat.restype = i
+    L.ndnet_b200_trainer_backward_flat.argtypes = [vp, vp, C.POINTER(vp), vp, vp]
+    L.ndnet_b200_trainer_grad_layout.restype = l
+    L.ndnet_b200_trainer_grad_layout.argtypes = [vp, vp, i]
+    L.ndnet_b200_trainer_set_graph.restype = i
+    L.ndnet_b200_trainer_set_graph.argtypes = [vp, i]
     L.ndnet_b200_trainer_set_precision.restype = i
     L.ndnet_b200_trainer_set_precision.argtypes = [vp, i]
     L.ndnet_b200_debug_train_gemm.restype = i
@@ -116,5 +122,6 @@ EXPORTED = [
     "ndnet_b200_infer_host", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline",
     "ndnet_b200_ply_load", "ndnet_b200_ply_num_points", "ndnet_b200_ply_sample", "ndnet_b200_ply_free",
     "ndnet_b200_trainer_create", "ndnet_b200_trainer_forward", "ndnet_b200_trainer_backward", "ndnet_b200_trainer_last_error",
+    "ndnet_b200_trainer_backward_flat", "ndnet_b200_trainer_grad_layout", "ndnet_b200_trainer_set_graph",
     "ndnet_b200_trainer_set_precision", "ndnet_b200_debug_train_gemm", "ndnet_b200_trainer_debug_buffer", "ndnet_b200_trainer_destroy",
 ]

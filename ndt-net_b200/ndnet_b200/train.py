@@ -19,9 +19,10 @@ from . import _lib
 
 
 class SegTrainer:
-    def __init__(self, module: torch.nn.Module, device: torch.device | int | None = None, tf32: bool = False):
+    def __init__(self, module: torch.nn.Module, device: torch.device | int | None = None, tf32: bool = False, graph: bool = True):
         """tf32=False: fp32 FMA everywhere (parity configuration).  tf32=True: the large GEMMs run on the tensor cores
-        (tcgen05 kind::tf32, fp32 accumulation) — the counterpart of torch.backends.cuda.matmul.allow_tf32."""
+        (tcgen05 kind::tf32, fp32 accumulation) — the counterpart of torch.backends.cuda.matmul.allow_tf32.
+        graph=True: each pass is captured into a CUDA graph per (shape, parameter storage) and replayed."""
         self.module = module
         p0 = next(module.parameters())
         dev = p0.device if device is None else (torch.device("cuda", device) if isinstance(device, int) else torch.device(device))
@@ -48,6 +49,11 @@ class SegTrainer:
         self._h = h
         self.tf32 = bool(tf32)
         self._L.ndnet_b200_trainer_set_precision(h, int(self.tf32))
+        self._L.ndnet_b200_trainer_set_graph(h, int(bool(graph)))
+        offs = np.full(n, -1, np.int64)
+        self._flat_elems = int(self._L.ndnet_b200_trainer_grad_layout(h, offs.ctypes.data, n))
+        self._grad_off = [int(o) for o in offs]
+        assert all((o >= 0) == (k in set(self.param_names)) for o, k in zip(self._grad_off, self.names)), "gradient layout mismatch"
         self.num_out = int(module.num_classes) + 1
 
     def _tensors(self):
@@ -108,12 +114,12 @@ class _SegTrainFn(torch.autograd.Function):
         (feat,) = ctx.saved_tensors                      # keeps the input alive: the library reads it again
         tensors = trainer._tensors()
         n_params = len(trainer.param_names)
-        grads = [torch.empty_like(t) for t in tensors[:n_params]]
+        flat = torch.empty((trainer._flat_elems,), dtype=torch.float32, device=dout.device)    # fresh storage every pass
         dout = dout.float().contiguous()
         stream = torch.cuda.current_stream(dout.device).cuda_stream
-        rc = trainer._L.ndnet_b200_trainer_backward(trainer._h, dout.data_ptr(), trainer._ptr_array(tensors),
-                                                    trainer._ptr_array(grads + [None] * (len(tensors) - n_params)), stream)
-        trainer._check(rc, "ndnet_b200_trainer_backward")
+        rc = trainer._L.ndnet_b200_trainer_backward_flat(trainer._h, dout.data_ptr(), trainer._ptr_array(tensors), flat.data_ptr(), stream)
+        trainer._check(rc, "ndnet_b200_trainer_backward_flat")
+        grads = [flat[o:o + t.numel()].view_as(t) for o, t in zip(trainer._grad_off[:n_params], tensors[:n_params])]
         return (None, None, *grads)
 
 

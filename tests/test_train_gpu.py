@@ -355,3 +355,29 @@ def test_every_layer_matches_the_replay_with_tensor_core_gemms(B, N):
     rp = _Replay(net, tr, B, N, torch.cat((pts, cov), 2), out, out.grad, tol=3e-3)
     rp.forward()
     rp.backward()
+
+
+def test_graph_replayed_pass_matches_the_layer_replay():
+    """CUDA-graph capture (default): the third pass of a configuration is a pure graph replay (pass 1 eager, pass 2
+    capture); it must satisfy the same layer-by-layer fp64 replay as the eager launch sequence, and gradients handed
+    out by an earlier pass must not be overwritten by a later one (every pass returns fresh storage)."""
+    B, N, C = 3, 160, 28
+    net = _net(768, C, 9)
+    tr = SegTrainer(net, graph=True)
+    kept = None
+    for step in range(3):
+        pts, cov, gt = _batch(50 + step, B, N, C)
+        net.zero_grad(set_to_none=True)
+        out = tr(pts, cov)
+        out.retain_grad()
+        reference_loss(out, gt).backward()
+        if step == 1:
+            kept = [(p.grad, p.grad.clone()) for p in net.parameters()]
+    rp = _Replay(net, tr, B, N, torch.cat((pts, cov), 2), out, out.grad)
+    rp.forward()
+    rp.backward()
+    assert all(torch.equal(g, c) for g, c in kept)
+    # the eager path gives the same structure of results
+    tr2 = SegTrainer(_net(768, C, 9), graph=False)
+    out2 = tr2(pts, cov)
+    assert out2.shape == out.shape
