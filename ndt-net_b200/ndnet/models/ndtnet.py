@@ -78,6 +78,12 @@ class NDTNet(nn.Module):
         return x, x_t2
 
 
+def _state_stamp(module: nn.Module):
+    """Changes whenever a parameter or buffer was modified in place (optimizer step, load_state_dict, BatchNorm update) or
+    replaced: the eval-mode CUDA model holds folded copies and must be rebuilt then."""
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
 class _B200Mixin:
     """Builds (once) and runs the CUDA model for an eval-mode module."""
     _kind = 0
@@ -94,9 +100,11 @@ class _B200Mixin:
                 object.__setattr__(self, "_b200_trainer", tr)
             return tr(points, covariances)
         m = getattr(self, "_b200_model", None)
-        if m is None or m.device != points.device:
-            m = B200Model(self, self._kind, points.device)
+        stamp = _state_stamp(self)
+        if m is None or m.device != points.device or getattr(self, "_b200_stamp", None) != stamp:
+            m = B200Model(self, self._kind, points.device)       # folds BatchNorm into bf16 weights: rebuilt when the state changed
             object.__setattr__(self, "_b200_model", m)
+            object.__setattr__(self, "_b200_stamp", stamp)
         feat = torch.cat((points, covariances), dim=2).float().contiguous()
         return m(feat)
 

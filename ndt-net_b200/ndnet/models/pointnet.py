@@ -35,10 +35,13 @@ class _B200PointMixin:
         from ndnet_b200.model import B200Model
         if self.training:
             raise RuntimeError("forward_b200 folds BatchNorm running statistics: call .eval() first")
+        from .ndtnet import _state_stamp
         m = getattr(self, "_b200_model", None)
-        if m is None or m.device != points.device:
-            m = B200Model(self, self._kind, points.device)
+        stamp = _state_stamp(self)
+        if m is None or m.device != points.device or getattr(self, "_b200_stamp", None) != stamp:
+            m = B200Model(self, self._kind, points.device)       # rebuilt when a parameter or buffer changed
             object.__setattr__(self, "_b200_model", m)
+            object.__setattr__(self, "_b200_stamp", stamp)
         return m(points.float().contiguous())
 
 

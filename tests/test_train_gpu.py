@@ -306,6 +306,27 @@ def test_eval_after_training_uses_the_updated_running_statistics():
     assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
 
 
+def test_eval_model_is_rebuilt_when_the_weights_change():
+    """train -> eval -> train -> eval: the eval-mode CUDA model folds BatchNorm into copies of the weights and must follow
+    optimizer steps and load_state_dict."""
+    net = _net(768, 28, 7)
+    opt = torch.optim.SGD(net.parameters(), lr=0.05)
+    pts, cov, gt = _batch(9, 4, 128, 28)
+    for _ in range(2):
+        net.train()
+        opt.zero_grad()
+        reference_loss(net.forward_b200(pts, cov), gt).backward()
+        opt.step()
+        net.eval()
+        with torch.no_grad():
+            want, got = net(pts, cov), net.forward_b200(pts, cov)
+        assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+    net.load_state_dict(deterministic_state_dict(net, 8))
+    with torch.no_grad():
+        want, got = net(pts, cov), net.forward_b200(pts, cov)
+    assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+
+
 def test_trainer_rejects_single_cloud_batches():
     net = _net(768, 28, 1)
     pts, cov, _ = _batch(1, 1, 64, 28)
