@@ -564,7 +564,7 @@ static bool gemm_tf32(cudaStream_t st, const float *A, long lda, const float *Bm
     if (tiles < 74 && nkb >= 16) {
         splitk = (int)((148 + tiles - 1) / tiles);
         if (splitk > nkb / 4) splitk = nkb / 4;
-        if (splitk > 32) splitk = 32;          // more splits only multiply the atomics into the same small output (profiles/r1_train_gemm_tf32_ncu.md)
+        if (splitk > 32) splitk = 32;          // more splits only multiply the atomics into the same small output
         if (splitk < 1) splitk = 1;
     }
     a.kb_per_split = (nkb + splitk - 1) / splitk;
