@@ -87,10 +87,14 @@ def test_oracle_matches_reference_golden():
 def test_oracle_matches_reference_live():
     lib = ref_ctypes.load(ref_ctypes.ref_lib_path("det"))
     rng = np.random.default_rng(5)
-    for k in range(6):
-        n = int(rng.integers(500, 9000))
-        d = int(rng.integers(20, 400))
+    for k in range(24):
+        n = int(rng.integers(500, 9000)) if k < 12 else int(rng.integers(9, 400))
+        d = int(rng.integers(20, 400)) if k < 12 else int(rng.integers(2, max(3, n // 3)))
         pts = (rng.normal(size=(n, 3)) * rng.uniform(0.5, 20, 3)).astype(np.float32)
+        if k % 5 == 4:
+            pts[n // 2:] = pts[: n - n // 2]                          # exact duplicates
+        if k % 7 == 6:
+            pts = np.round(pts * 4) / 4                               # lattice points: cells on exact boundaries
         labels = rng.integers(0, 7, n).astype(np.uint16) if k % 2 else None
         r = ref_ctypes.downsample(lib, pts.astype(np.float64), d, labels, 6 if labels is not None else 0, introspect=True)
         o = ndt_oracle.run(pts, d, labels, 6 if labels is not None else 0)
