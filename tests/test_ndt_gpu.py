@@ -98,6 +98,24 @@ def test_small_cases_match_oracle(engine, case):
     _check_against_oracle(engine, *case)
 
 
+def test_random_clouds_match_oracle(engine):
+    """Differential run on 40 seeded random clouds (sizes 9..9000, D 2..400, with and without labels, exact duplicates,
+    lattice points whose cells sit on exact boundaries, anisotropic scales) - the same generator the oracle is checked
+    with against the reference build (tests/test_oracle.py::test_oracle_matches_reference_live)."""
+    rng = np.random.default_rng(5)
+    for k in range(40):
+        n = int(rng.integers(500, 9000)) if k % 2 == 0 else int(rng.integers(9, 400))
+        d = int(rng.integers(20, 400)) if k % 2 == 0 else int(rng.integers(2, max(3, n // 3)))
+        pts = (rng.normal(size=(n, 3)) * rng.uniform(0.5, 20, 3)).astype(np.float32)
+        if k % 5 == 4:
+            pts[n // 2:] = pts[: n - n // 2]
+        if k % 7 == 6:
+            pts = np.round(pts * 4) / 4
+        ncls = 6 if k % 3 == 1 else (70 if k % 3 == 2 else 0)          # 70 classes: the global-histogram vote path
+        labels = rng.integers(0, ncls + 1, n).astype(np.uint16) if ncls else None
+        _check_against_oracle(engine, f"random{k}", pts, labels, ncls, d)
+
+
 @pytest.mark.parametrize("case", cases.medium_cases(), ids=lambda c: c[0])
 def test_baseline_sized_clouds_match_oracle(engine, case):
     _check_against_oracle(engine, *case)
