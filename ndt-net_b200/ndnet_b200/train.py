@@ -104,6 +104,8 @@ class _SegTrainFn(torch.autograd.Function):
         rc = trainer._L.ndnet_b200_trainer_forward(trainer._h, feat.data_ptr(), B, N, trainer._ptr_array(tensors), out.data_ptr(),
                                                    int(trainer.module.training), stream)
         trainer._check(rc, "ndnet_b200_trainer_forward")
+        trainer._pass = getattr(trainer, "_pass", 0) + 1      # the library keeps the activations of ONE forward pass
+        ctx.pass_id = trainer._pass
         ctx.trainer = trainer
         ctx.save_for_backward(feat)
         return out
@@ -111,6 +113,10 @@ class _SegTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout: torch.Tensor):
         trainer: SegTrainer = ctx.trainer
+        if ctx.pass_id != trainer._pass:
+            raise RuntimeError("ndnet_b200 trainer: backward of an earlier forward pass - its activations were overwritten by a "
+                               "later forward through the same module (run backward before the next forward, or use one "
+                               "SegTrainer per in-flight pass)")
         (feat,) = ctx.saved_tensors                      # keeps the input alive: the library reads it again
         tensors = trainer._tensors()
         n_params = len(trainer.param_names)

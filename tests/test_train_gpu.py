@@ -327,6 +327,20 @@ def test_eval_model_is_rebuilt_when_the_weights_change():
     assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
 
 
+def test_backward_of_an_overwritten_pass_is_refused():
+    """The library holds the activations of one forward pass per trainer: a stale backward must fail loudly, not silently
+    use the wrong activations."""
+    net = _net(768, 28, 2)
+    tr = SegTrainer(net)
+    p1, c1, g1 = _batch(1, 2, 64, 28)
+    p2, c2, g2 = _batch(2, 2, 64, 28)
+    out1 = tr(p1, c1)
+    out2 = tr(p2, c2)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        reference_loss(out1, g1).backward()
+    reference_loss(out2, g2).backward()               # the latest pass is fine
+
+
 def test_trainer_rejects_single_cloud_batches():
     net = _net(768, 28, 1)
     pts, cov, _ = _batch(1, 1, 64, 28)
