@@ -78,6 +78,8 @@ def lib() -> C.CDLL:
     L.ndnet_b200_infer_device.argtypes = [vp, vp, vp, i, vp, i, l, i, l, vp, l, vp]
     L.ndnet_b200_set_pipeline.restype = i
     L.ndnet_b200_set_pipeline.argtypes = [vp, i, i]
+    L.ndnet_b200_set_device_chunk.restype = i
+    L.ndnet_b200_set_device_chunk.argtypes = [vp, i]
     L.ndnet_b200_ply_load.restype = i
     L.ndnet_b200_ply_load.argtypes = [i, vp, C.c_size_t, i, i, i, vp, C.POINTER(vp), C.POINTER(C.c_ulong), C.POINTER(l),
                                       C.POINTER(l)]
@@ -119,7 +121,7 @@ EXPORTED = [
     "ndnet_b200_downsample_batch", "ndnet_b200_downsample_batch_host", "ndnet_b200_keep_point_voxels", "ndnet_b200_last_point_voxels",
     "ndnet_b200_last_kl_list", "ndnet_b200_selftest_div", "ndnet_b200_launch_count", "ndnet_b200_stage_timing", "ndnet_b200_stage_times",
     "ndnet_b200_model_create", "ndnet_b200_model_input_dim", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
-    "ndnet_b200_infer_host", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline",
+    "ndnet_b200_infer_host", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline", "ndnet_b200_set_device_chunk",
     "ndnet_b200_ply_load", "ndnet_b200_ply_num_points", "ndnet_b200_ply_sample", "ndnet_b200_ply_free",
     "ndnet_b200_trainer_create", "ndnet_b200_trainer_forward", "ndnet_b200_trainer_backward", "ndnet_b200_trainer_last_error",
     "ndnet_b200_trainer_backward_flat", "ndnet_b200_trainer_grad_layout", "ndnet_b200_trainer_set_graph",

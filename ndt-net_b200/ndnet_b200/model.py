@@ -134,10 +134,15 @@ class B200Model:
                                f"{self._L.ndnet_b200_last_error(self.engine.handle).decode()}")
         return out.unsqueeze(-1) if self.kind == KIND_CLS else out
 
-    def set_pipeline(self, lanes: int, chunk: int) -> None:
+    def set_pipeline(self, lanes: int, chunk: int, device_chunk: int | None = None) -> None:
+        """lanes x chunk scans for infer_host; `device_chunk` scans per chunk for infer_device (library default 128)."""
         rc = self._L.ndnet_b200_set_pipeline(self.engine.handle, int(lanes), int(chunk))
         if rc != 0:
             raise RuntimeError(f"ndnet_b200_set_pipeline failed ({rc})")
+        if device_chunk is not None:
+            rc = self._L.ndnet_b200_set_device_chunk(self.engine.handle, int(device_chunk))
+            if rc != 0:
+                raise RuntimeError(f"ndnet_b200_set_device_chunk failed ({rc})")
 
 
 def smoke_forward(engine, feat: torch.Tensor) -> None:
