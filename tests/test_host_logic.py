@@ -119,3 +119,22 @@ def test_cpulist_parser():
     from ndnet_b200.dist import _parse_cpulist
     assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
     assert _parse_cpulist("") == set()
+
+
+def test_state_stamp_follows_in_place_updates_and_loads():
+    """The eval-mode CUDA model is rebuilt when this stamp changes (ndnet/models/ndtnet.py::_state_stamp)."""
+    import torch
+    from ndnet.models.ndtnet import NDTNetSegmentation, _state_stamp
+    net = NDTNetSegmentation(num_classes=4, feature_dim=64)
+    s0 = _state_stamp(net)
+    assert _state_stamp(net) == s0                                   # reading does not change it
+    with torch.no_grad():
+        net.conv4.bias.add_(1.0)                                     # what an optimizer step does
+    s1 = _state_stamp(net)
+    assert s1 != s0
+    net.load_state_dict(net.state_dict())                            # copy_ into every tensor
+    s2 = _state_stamp(net)
+    assert s2 != s1
+    net.train()
+    net(torch.randn(2, 16, 3), torch.randn(2, 16, 9))                # BatchNorm running statistics move
+    assert _state_stamp(net) != s2
