@@ -124,3 +124,45 @@ def test_int_tokens(host, tok, want):
 def test_rejected_int_tokens(host, tok, code):
     v = C.c_longlong()
     assert host.ply_host_parse_int(tok.encode(), len(tok), C.byref(v)) == code
+
+
+def test_grammar_agrees_with_python_on_random_tokens(host):
+    """300 000 random tokens over the alphabet of decimal literals: accepted <=> float() accepts (same bits), rejected with
+    the 'bad literal' code <=> float() raises ValueError, 'unsupported' only for literals float() accepts but that lie
+    outside what the parser converts exactly (more than 19 significant digits or a decimal exponent beyond +-55)."""
+    rng = random.Random(7)
+    alphabet = "0123456789" * 3 + "+-..eE"
+    toks = ["".join(rng.choice(alphabet) for _ in range(rng.randint(1, 14))) for _ in range(300_000)]
+    out, st = parse_many(host, toks)
+    n_ok = n_bad = n_unsup = 0
+    for t, v, s in zip(toks, out, st):
+        try:
+            want = float(t)
+            ok = True
+        except ValueError:
+            ok = False
+        if s == 0:
+            assert ok and bits(float(v)) == bits(want), (t, float(v))
+            n_ok += 1
+        elif s == 2:
+            assert not ok, t
+            n_bad += 1
+        else:
+            assert s == 4 and ok, (t, s)
+            n_unsup += 1
+    assert n_ok > 50_000 and n_bad > 50_000                      # both branches are exercised
+    assert n_unsup < n_ok // 2                                   # refusals are the exception (huge exponents like 9e9999)
+
+
+def test_int_grammar_agrees_with_python_on_random_tokens(host):
+    rng = random.Random(8)
+    alphabet = "0123456789" * 4 + "+-.e"
+    for _ in range(50_000):
+        t = "".join(rng.choice(alphabet) for _ in range(rng.randint(1, 9)))
+        v = C.c_longlong()
+        s = host.ply_host_parse_int(t.encode(), len(t), C.byref(v))
+        try:
+            want = int(t)
+            assert s == 0 and v.value == want, (t, s, v.value)
+        except ValueError:
+            assert s == 2, (t, s)
