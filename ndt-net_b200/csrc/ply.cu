@@ -27,11 +27,6 @@ constexpr int kScanThreads = 256;
 constexpr int kBytesPerThread = 16;
 constexpr int kBytesPerCta = kScanThreads * kBytesPerThread;   // 4 KB of text per CTA
 
-__device__ __forceinline__ bool is_space(unsigned c) {
-    // str.split() / str.strip() whitespace within ASCII: \t \n \v \f \r, FS GS RS US, space
-    return c == 0x20u || (c >= 0x09u && c <= 0x0du) || (c >= 0x1cu && c <= 0x1fu);
-}
-
 __device__ __forceinline__ unsigned newline_mask(uint4 v, long base, long nbytes, const unsigned char *text, unsigned *bad) {
     // bit i set when byte i of the 16 is '\n'; flags non-ASCII bytes and '\r' not followed by '\n'
     const unsigned w[4] = {v.x, v.y, v.z, v.w};
@@ -165,27 +160,9 @@ __global__ void __launch_bounds__(128) k_ply_parse(const unsigned char *__restri
     if (line >= n_lines) return;
     long a = (long)line_start[line];
     long b = line + 1 < n_lines ? (long)line_start[line + 1] : nbytes;    // one past the line's last byte (incl. its '\n')
-    // tokens 0,1,2 and the last one
-    long ta[3], tb[3], la = -1, lb = -1;
-    int ntok = 0;
-    long i = a;
-    while (i < b) {
-        while (i < b && is_space(text[i])) i++;
-        if (i >= b) break;
-        const long s = i;
-        while (i < b && !is_space(text[i])) i++;
-        if (ntok < 3) { ta[ntok] = s; tb[ntok] = i; }
-        la = s; lb = i;
-        ntok++;
-    }
     double xyz[3];
-    for (int k = 0; k < 3; k++) {                     // evaluation order of CARLA_Seg.py:120-122
-        if (ntok <= k) { report(err, line, kErrShortLine); return; }
-        const int r = parse_float(text, ta[k], tb[k], &xyz[k]);
-        if (r) { report(err, line, r); return; }
-    }
     long long tag = 0;
-    const int r = parse_int(text, la, lb, &tag);      // data[-1] (:123)
+    const int r = parse_line(text, a, b, xyz, &tag);          // tokens, float(data[0..2]), int(data[-1]) in the reference's order
     if (r) { report(err, line, r); return; }
     if (tag > (long long)n_classes) { report(err, line, kErrClassBound); return; }
     if (tag < 0) { report(err_negative, line, kErrNegativeClass); return; }

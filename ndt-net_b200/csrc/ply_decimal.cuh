@@ -194,4 +194,31 @@ PLY_HD inline int parse_int(const unsigned char *t, long a, long b, long long *o
     return 0;
 }
 
+// str.split() / str.strip() whitespace within ASCII: \t \n \v \f \r, FS GS RS US, space
+PLY_HD inline bool is_space(unsigned c) { return c == 0x20u || (c >= 0x09u && c <= 0x0du) || (c >= 0x1cu && c <= 0x1fu); }
+
+// One data line text[a, b) as the reference reads it (CARLA_Seg.py:118-123):
+//   data = point.strip().split(); x = float(data[0]); y = float(data[1]); z = float(data[2]); class_tag = int(data[-1])
+// in that evaluation order.  Returns 0 or the error code of the first failing step.
+PLY_HD inline int parse_line(const unsigned char *text, long a, long b, double xyz[3], long long *tag) {
+    long ta[3], tb[3], la = -1, lb = -1;
+    int ntok = 0;
+    long i = a;
+    while (i < b) {
+        while (i < b && is_space(text[i])) i++;
+        if (i >= b) break;
+        const long s = i;
+        while (i < b && !is_space(text[i])) i++;
+        if (ntok < 3) { ta[ntok] = s; tb[ntok] = i; }
+        la = s; lb = i;
+        ntok++;
+    }
+    for (int k = 0; k < 3; k++) {
+        if (ntok <= k) return kErrShortLine;
+        const int r = parse_float(text, ta[k], tb[k], &xyz[k]);
+        if (r) return r;
+    }
+    return parse_int(text, la, lb, tag);
+}
+
 }  // namespace ply

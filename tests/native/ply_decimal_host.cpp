@@ -13,3 +13,6 @@ extern "C" int ply_host_parse_many(const char *buf, const long *off, long count,
         status[i] = ply::parse_float(reinterpret_cast<const unsigned char *>(buf), off[i], off[i + 1], &out[i]);
     return 0;
 }
+extern "C" int ply_host_parse_line(const char *s, long n, double *xyz, long long *tag) {
+    return ply::parse_line(reinterpret_cast<const unsigned char *>(s), 0, n, xyz, tag);
+}
