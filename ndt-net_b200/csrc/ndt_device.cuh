@@ -5,6 +5,7 @@
 // parity is bit-level.  Reference lines each piece follows are cited inline
 // (paths relative to /root/reference/core_legacy/).
 #pragma once
+#include "ndt_cell.cuh"
 #include <cfloat>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -60,20 +61,8 @@ __device__ __forceinline__ double dec_f64(unsigned long long u) {
     return __longlong_as_double((long long)u);
 }
 
-// floor((p - off) / vs) exactly as voxel.c:89-91 computes it (IEEE subtraction, IEEE division, floor), but
-// without the division in the common case: with rv = RN(1/vs), q0 = RN(a * rv) is within 2 ulp of the
-// IEEE quotient, so whenever q0 is further than 2^-48 (relative) from an integer both have the same floor;
-// only the rare near-integer cases take the real division.
-__device__ __forceinline__ unsigned axis_cell(double p, double off, double vs, double rv) {
-    const double a = p - off;
-    const double q0 = a * rv;
-    const double f = floor(q0);
-    const double t = q0 - f;                                  // exact (Sterbenz / small integers)
-    const double eps = q0 * 3.5527136788005009e-15;           // 2^-48 * q0  (>= 16 ulp)
-    // a >= 0 (off is the minimum), so the quotient cannot fall below cell 0: no lower-boundary ambiguity there
-    if ((t > eps || f == 0.0) && (1.0 - t) > eps) return (unsigned)f;
-    return (unsigned)floor(a / vs);
-}
+// floor((p - off) / vs) exactly as voxel.c:89-91 computes it: see ndt_cell.cuh (shared with the host-side property test)
+__device__ __forceinline__ unsigned axis_cell(double p, double off, double vs, double rv) { return cell_exact64(p, off, vs, rv); }
 
 // voxel.c:83-103 + :177-189.  Returns false when the point is outside the grid.
 __device__ __forceinline__ bool voxel_of(double x, double y, double z, const double off[3], double vs, double rv,
@@ -104,25 +93,10 @@ __device__ __forceinline__ GridCtx make_grid_ctx(const CloudState &s) {
     return g;
 }
 
-// fp32 prefilter for fp32 inputs: the offset is the minimum of fp32 values, hence itself an fp32 value, so
-// q32 = RN32(RN32(p - off) * RN32(1/vs)) differs from the reference's fp64 quotient by less than 2e-7 q.  When q32
-// is further than 4e-7 q from an integer the two have the same floor; otherwise (about 1e-5 of the points) the
-// exact fp64 path decides.  The floor itself is taken with the 2^23 magic-number add (FADD/integer pipes): the
-// conversion instructions (F2F/FRND/F2I) all issue on the quarter-rate XU pipe, which is what bounded k_count.
+// fp32 prefilter (ndt_cell.cuh) with the out-of-line exact fallback
 __device__ __forceinline__ unsigned axis_cell32(float p, int a, const GridCtx &g) {
-    const float d = p - g.off32[a];
-    const float q = d * g.rv32;
-    if (q >= 0.0f && q < 4194304.0f) {
-        const float m = q + 8388608.0f;                       // RN(q) in the low mantissa bits
-        int ri = __float_as_int(m) - 0x4B000000;
-        float rf = m - 8388608.0f;
-        if (rf > q) { ri -= 1; rf -= 1.0f; }                  // nearest -> floor
-        const float t = q - rf;
-        const float eps = q * 4e-7f;
-        // d >= 0 (off is the minimum, an fp32 value), so cell 0 has no lower-boundary ambiguity: flat ground at
-        // the minimum z puts most of a scan exactly there
-        if ((t > eps || ri == 0) && (1.0f - t) > eps) return (unsigned)ri;
-    }
+    unsigned cell;
+    if (cell_prefilter32(p, g.off32[a], g.rv32, cell)) return cell;
     return axis_cell_rare((double)p, g.off[a], g.vs, g.rv);
 }
 
