@@ -78,7 +78,9 @@ typedef struct ndnet_b200_ctx ndnet_b200_ctx;
 /* Per-cloud record written by ndnet_b200_downsample_batch (device memory, one per cloud). */
 typedef struct ndnet_b200_cloud_info {
     int32_t status;        /* 0 ok; -1 grid too large (stands in for malloc failure, ndt.c:151-155);
-                              -3 voxel-size search did not converge (ndt.c:191-194) */
+                              -3 voxel-size search did not converge (ndt.c:191-194);
+                              -5 a coordinate is NaN: refused, outputs zero (undefined behaviour in the reference,
+                                 voxel.c:89-91; +-inf coordinates end in -1: the grid cannot be held) */
     int32_t prune_status;  /* 0, or -2 when the walk hit the end of the list (ndt.c:53-56) */
     int32_t evaluations;   /* estimate passes the search made (<= 15) */
     uint32_t len[3];       /* accepted grid */
@@ -140,6 +142,9 @@ long ndnet_b200_launch_count(void);
 /* Self test: compares the statistics kernel's reciprocal+FMA division by an integer count with the IEEE
  * division on n pseudo-random operand pairs; returns the number of mismatching results (0 expected). */
 long ndnet_b200_selftest_div(long n, unsigned seed);
+/* Test hook: the next workspace allocation of this context fails as if the device were out of memory (the call that
+ * triggers it returns the allocation error; the one after must allocate afresh and succeed). */
+int ndnet_b200_test_fail_next_reserve(ndnet_b200_ctx *ctx);
 int ndnet_b200_stage_timing(ndnet_b200_ctx *ctx, int enable);
 int ndnet_b200_stage_times(ndnet_b200_ctx *ctx, double *ms, int cap, long *runs);
 
@@ -167,6 +172,13 @@ int ndnet_b200_model_input_dim(const ndnet_b200_model *model);
  * cls: out device [B, num_classes] f32 (softmax);  seg: out device [B, D, num_classes+1] f32 (log_softmax). */
 int ndnet_b200_model_forward(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const float *feat, int B, int D,
                              float *out, void *stream);
+
+/* Inspection (parity tests): one internal activation of the LAST ndnet_b200_model_forward of `model` on `ctx`, converted
+ * to fp32 into the device buffer `out` of capacity `cap` floats (out == NULL: size query).  Names: "t1" [B,d,d] and "t2"
+ * [B,64,64] (the T-Net transforms, ndtnet.py:33-62), "t1.pool" / "t2.pool" [B,1024], "trunk.l1" [B,N,64] (ndtnet.py:149),
+ * "trunk.xt2" [B,N,64] (:153-155), "trunk.pool" [B,F] (max over points of :161), "head.l1/l2/l3" [B,N,512/256/128]
+ * (:231-233; segmentation) or "trunk.l2" [B,N,128] (classification).  Returns the element count or a negative error. */
+long ndnet_b200_model_tap(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const char *name, float *out, long cap, void *stream);
 
 /* The whole hot path in one call from HOST buffers (what bench.py times as `e2e`): H2D of points (+labels),
  * NDT (NaN/inf -> 0 as ndtnet_preprocessing.py:66-69), network forward, D2H of the result

@@ -80,15 +80,28 @@ static cudaError_t alloc(T *&p, size_t count) {
     return cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
 }
 
+// Frees the device arrays and resets every capacity to zero (a later reserve() starts from scratch); the side
+// stream and its events survive so that a workspace can grow without re-creating them (destroy() ends them).
 void Workspace::release() {
     const bool keep = keep_point_voxels;
     cudaStream_t keep_side = side; cudaEvent_t keep_fork = ev_fork, keep_join = ev_join;
+    const StageTimer keep_timer = timer;
     void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, vox_order, slot_rank, tile_cnt, hist, point_voxel, sorted,
                     mean, cov, cov_final, cls, kl_div, kl_flag, key, seq, firstpos, removed, list_div, list_seq};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = Workspace();
     keep_point_voxels = keep;
     side = keep_side; ev_fork = keep_fork; ev_join = keep_join;
+    timer = keep_timer;
+}
+
+void Workspace::destroy() {
+    release();
+    if (timer.created) { for (auto &e : timer.ev) cudaEventDestroy(e); timer = StageTimer(); }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
+    side = nullptr; ev_fork = ev_join = nullptr;
 }
 
 cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
@@ -107,9 +120,12 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     ntiles_cap = (int)((nN + 2047) / 2048);
     const size_t kcap = (size_t)vcap * 6;
     cudaError_t e;
-#define A(ptr, count) if ((e = alloc(ptr, (size_t)(count))) != cudaSuccess) return e
-    if ((e = cudaMalloc((void **)&states, cloud_state_size() * nB)) != cudaSuccess) return e;
-    A(lim_enc, (size_t)nB * 6);
+    // a failed allocation leaves NO capacity behind: release() frees what was obtained and zeroes the caps, so the next
+    // call re-allocates instead of passing the early-out above with null or partial buffers
+#define A(ptr, count) if ((e = alloc(ptr, (size_t)(count))) != cudaSuccess) { release(); return e; }
+    if (fail_next_reserve) { fail_next_reserve = false; e = cudaErrorMemoryAllocation; release(); return e; }
+    if ((e = cudaMalloc((void **)&states, cloud_state_size() * nB)) != cudaSuccess) { release(); return e; }
+    A(lim_enc, (size_t)nB * 8);
     A(bitmap, (size_t)nB * bitmap_stride);
     A(vox_cell, (size_t)nB * vcap);
     A(vox_n, (size_t)nB * vcap);
@@ -119,7 +135,7 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     A(tile_cnt, (size_t)nB * ntiles_cap * vcap);
     A(hist, (size_t)nB * vcap * (nbins > 0 ? nbins : 1));
     A(point_voxel, (size_t)nB * nN);
-    if ((e = cudaMalloc(&sorted, (size_t)nB * nN * 4 * sizeof(double))) != cudaSuccess) return e;     // {x, y, z, label} records
+    if ((e = cudaMalloc(&sorted, (size_t)nB * nN * 4 * sizeof(double))) != cudaSuccess) { release(); return e; }     // {x, y, z, label} records
     A(mean, (size_t)nB * vcap * 3);
     A(cov, (size_t)nB * vcap * 9);
     A(cov_final, (size_t)nB * vcap * 9);
@@ -164,12 +180,12 @@ extern "C" int ndnet_b200_create(ndnet_b200_ctx **out, int device) {
 extern "C" void ndnet_b200_destroy(ndnet_b200_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    c->ws.release();
+    c->ws.destroy();
     c->mlp_scratch.release();
     void *ptrs[] = {c->d_points, c->d_labels, c->d_feat, c->d_feat64, c->d_olab, c->d_ovox, c->d_info, c->d_logits};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &l : c->lanes) {
-        l.ws.release(); l.scratch.release();
+        l.ws.destroy(); l.scratch.release();
         void *lp[] = {l.d_points, l.d_labels, l.d_feat, l.d_logits};
         for (void *p : lp) if (p) cudaFree(p);
         if (l.done) cudaEventDestroy(l.done);
@@ -187,6 +203,12 @@ extern "C" long ndnet_b200_selftest_div(long n, unsigned seed) {
 }
 
 extern "C" long ndnet_b200_launch_count(void) { return ndt::launches(); }
+
+extern "C" int ndnet_b200_test_fail_next_reserve(ndnet_b200_ctx *c) {
+    if (!c) return -200;
+    c->ws.fail_next_reserve = true;
+    return 0;
+}
 
 extern "C" int ndnet_b200_stage_timing(ndnet_b200_ctx *c, int enable) {
     if (!c) return -200;
@@ -413,6 +435,7 @@ struct Session {
     NdToken nd{kMagicNd, nullptr};
     KlToken kl{kMagicKl, nullptr};
     bool nd_freed = false, kl_freed = false;
+    int device = 0;
     ndt::SessionState st;
 };
 
@@ -429,7 +452,7 @@ ndnet_b200_ctx *default_ctx() {
 }
 
 void maybe_delete(Session *s) {
-    if (s->nd_freed && s->kl_freed) { s->st.release(); delete s; }
+    if (s->nd_freed && s->kl_freed) { cudaSetDevice(s->device); s->st.release(); delete s; }
 }
 
 }  // namespace
@@ -466,6 +489,7 @@ extern "C" int ndt_downsample(double *point_cloud, unsigned short point_dim, uns
     if (voxel_size) *voxel_size = info.voxel_size;
     if (info.status != 0) {
         if (info.status == -3) fprintf(stderr, "Reached maximum number of iterations!\n");          // ndt.c:192
+        else if (info.status == -5) fprintf(stderr, "ndt_downsample: the point cloud holds NaN coordinates; refused\n");
         else fprintf(stderr, "Error allocating memory for normal distributions: grid too large\n");   // ndt.c:153
         return info.status;
     }
@@ -481,7 +505,7 @@ extern "C" int ndt_downsample(double *point_cloud, unsigned short point_dim, uns
     // retain the state for prune_nds / to_point_cloud
     Session *s = new (std::nothrow) Session();
     if (!s) return -202;
-    s->nd.owner = s; s->kl.owner = s;
+    s->nd.owner = s; s->kl.owner = s; s->device = c->device;
     cudaError_t e = s->st.capture(c->ws, 0, classes != nullptr);
     if (e != cudaSuccess) { s->st.release(); delete s; return fail(c, e, "session capture"); }
     if (nd_array) *nd_array = (struct normal_distribution_t *)&s->nd; else s->nd_freed = true;
@@ -502,12 +526,16 @@ extern "C" int prune_nds(struct normal_distribution_t *nd_array, unsigned int le
         return -200;
     }
     Session *s = t->owner;
-    if (num_valid_nds && num_desired_nds > *num_valid_nds) {
+    // the guard of ndt.c:36-39 on the library's own count: the caller's pointer may be NULL or stale, and an unsigned
+    // to_remove = valid - desired must never wrap
+    if (num_desired_nds > (unsigned long)s->st.n_valid || (num_valid_nds && num_desired_nds > *num_valid_nds)) {
         fprintf(stderr, "Number of desired normal distributions is greater than the number valid distributions!\n");  // ndt.c:37
         return -1;
     }
     unsigned valid = 0, nkl = 0; int ret = 0;
-    cudaError_t e = s->st.prune((unsigned long)num_desired_nds, &valid, &nkl, &ret);
+    cudaError_t e = cudaSetDevice(s->device);      // the session lives on the device that ran its ndt_downsample
+    if (e != cudaSuccess) return fail(g_ctx, e, "cudaSetDevice");
+    e = s->st.prune((unsigned long)num_desired_nds, &valid, &nkl, &ret);
     if (e != cudaSuccess) return fail(g_ctx, e, "session prune");
     if (num_valid_nds) *num_valid_nds = valid;
     if (num_kl_divergences) *num_kl_divergences = nkl;
@@ -529,7 +557,9 @@ extern "C" int to_point_cloud(struct normal_distribution_t *nd_array, unsigned i
     std::vector<double> feat;
     std::vector<uint16_t> lab;
     unsigned rows = 0;
-    cudaError_t e = s->st.output(feat, lab, &rows);
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e != cudaSuccess) return fail(g_ctx, e, "cudaSetDevice");
+    e = s->st.output(feat, lab, &rows);
     if (e != cudaSuccess) return fail(g_ctx, e, "session output");
     // The reference writes every surviving row; callers size buffers for the number they asked for,
     // which equals the survivor count unless a walk stopped early (A15).
@@ -597,6 +627,13 @@ extern "C" void ndnet_b200_model_destroy(ndnet_b200_model *m) {
     if (!m) return;
     m->m.release();
     delete m;
+}
+
+extern "C" long ndnet_b200_model_tap(ndnet_b200_ctx *c, ndnet_b200_model *m, const char *name, float *out, long cap, void *stream) {
+    if (!c || !m) return -200;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, e, "cudaSetDevice");
+    return m->m.tap(name, out, cap, (cudaStream_t)stream);
 }
 
 extern "C" int ndnet_b200_model_forward(ndnet_b200_ctx *c, ndnet_b200_model *m, const float *feat, int B, int D, float *out,

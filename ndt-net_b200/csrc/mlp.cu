@@ -235,6 +235,18 @@ __global__ void __launch_bounds__(256) k_softmax(const float *__restrict__ x, fl
     for (int i = threadIdx.x; i < n; i += blockDim.x) yo[i] = expf(xi[i] - mx) / sum;
 }
 
+// Inspection taps (Model::tap): an internal activation of the last forward as fp32.  src_kind 0 = fp32, 1 = bf16,
+// 2 = order-preserving encoded fp32 (the max-pool accumulators).
+__global__ void __launch_bounds__(256) k_tap(const void *__restrict__ src, int src_kind, long n, float *__restrict__ dst) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        float v;
+        if (src_kind == 0) v = ((const float *)src)[i];
+        else if (src_kind == 1) v = __bfloat162float(((const __nv_bfloat16 *)src)[i]);
+        else v = dec_f32(((const unsigned *)src)[i]);
+        dst[i] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -302,6 +314,9 @@ struct ModelImpl {
     // classification head
     float *k1_w = nullptr, *k1_b = nullptr, *k2_w = nullptr, *k2_b = nullptr, *k3_w = nullptr, *k3_b = nullptr;
     std::vector<void *> allocs;
+    // where the activations of the last forward live (Model::tap)
+    struct Tap { const void *ptr; int kind; long count; };
+    std::map<std::string, Tap> taps;
 };
 
 namespace {
@@ -420,6 +435,20 @@ int Model::build(int kind, int n_tensors, const char *const *names, const float 
 }
 
 int Model::input_dim() const { return impl ? impl->in_dim : 0; }
+
+long Model::tap(const char *name, float *out, long cap, cudaStream_t st) {
+    if (!impl || !name) return -300;
+    auto it = impl->taps.find(name);
+    if (it == impl->taps.end()) return -307;
+    const ModelImpl::Tap &t = it->second;
+    if (!out) return t.count;
+    if (cap < t.count) return -308;
+    long blocks = (t.count + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    k_tap<<<(unsigned)blocks, 256, 0, st>>>(t.ptr, t.kind, t.count, out);
+    ndt::count_launches(1);
+    return cudaGetLastError() == cudaSuccess ? t.count : -306;
+}
 
 void Model::release() {
     if (!impl) return;
@@ -575,6 +604,24 @@ int Model::forward(Scratch &scratch, const float *feat, int B, int D, float *out
         if (f.ok) k_softmax<<<B, 256, 0, st>>>(logit, out, m.ncls);
     }
     if (!f.ok) return -306;
+    {
+        const long Bl = B, Ml = (long)M;
+        m.taps.clear();
+        m.taps["t1"] = {T1, 0, Bl * td * td};                  // input transform  (ndtnet.py:132-133)   [B, d, d]
+        m.taps["t2"] = {T2, 0, Bl * 4096};                     // feature transform (ndtnet.py:152)        [B, 64, 64]
+        m.taps["t1.pool"] = {g1, 2, Bl * 1024};                // T-Net max-pools (ndtnet.py:50)           [B, 1024]
+        m.taps["t2.pool"] = {g2, 2, Bl * 1024};
+        m.taps["trunk.l1"] = {a1, 1, Ml * 64};                 // bn1(conv1([T p ; T Sigma]))  (ndtnet.py:149)  [B, N, 64]
+        m.taps["trunk.xt2"] = {xt2, 1, Ml * 64};               // x . T2  (ndtnet.py:153-155)              [B, N, 64]
+        m.taps["trunk.pool"] = {g3, 2, Bl * m.F};              // max over points of bn3(conv3(.))         [B, F]
+        if (m.kind == 1) {
+            m.taps["head.l1"] = {s1, 1, Ml * 512};             // segmentation head layers (ndtnet.py:231-233)
+            m.taps["head.l2"] = {s2, 1, Ml * 256};
+            m.taps["head.l3"] = {h128, 1, Ml * 128};
+        } else {
+            m.taps["trunk.l2"] = {h128, 1, Ml * 128};          // bn2(conv2(.)) survives when no head reuses the buffer
+        }
+    }
     ndt::count_launches(f.gemm_launches + 2 + (m.kind == 1 ? 7 : 10));   // + the small CUDA-core kernels
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return -100 - (int)e; }

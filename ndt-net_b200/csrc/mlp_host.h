@@ -21,6 +21,9 @@ struct Model {
     int forward(Scratch &scratch, const float *feat, int B, int D, float *out, cudaStream_t st, std::string &err);
     void release();
     int input_dim() const;
+    // inspection: copy one internal activation of the LAST forward (still in its scratch buffer) to `out` as fp32;
+    // returns the element count (out == nullptr: query only) or a negative error
+    long tap(const char *name, float *out, long cap, cudaStream_t st);
 };
 
 }  // namespace mlp

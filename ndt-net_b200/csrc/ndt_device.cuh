@@ -24,6 +24,8 @@ constexpr unsigned kSmemBitmapBits = 1u << 18; // grids up to this many cells ar
 constexpr int kCountPointsPerCta = 4096;
 constexpr int kRankTile = 2048;                // points per rank tile (one warp walks one tile in order)
 constexpr unsigned kDropped = 0xFFFFFFFFu;
+constexpr int kLimWords = 8;                   // per cloud: encoded max x,y,z, min x,y,z, NaN-seen flag, (pad)
+constexpr int kStatusNaNInput = -5;            // a coordinate is NaN: refused (the reference's behaviour is undefined, voxel.c:89-91)
 constexpr int kSortedStride = 4;               // voxel-sorted points are {x, y, z, label bits}: one 16-byte store per point
 constexpr int kSmemLabelBins = 64;
 constexpr unsigned kHeavyVoxel = 512;           // voxels with at least this many points get a warp each in k_stats

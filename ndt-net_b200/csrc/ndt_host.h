@@ -61,8 +61,11 @@ struct Workspace {
     // of the last run
     int last_B = 0; long last_N = 0; long last_D = 0;
 
+    bool fail_next_reserve = false;    // test hook (ndnet_b200_test_fail_next_reserve): the next growing reserve() fails
+
     cudaError_t reserve(int B, long N, long D, int bins);
-    void release();
+    void release();                    // frees the arrays, zeroes the capacities
+    void destroy();                    // release() + the side stream and its events
 };
 
 cudaError_t run_batch(Workspace &w, const void *pts, int dtype, const uint16_t *labels, int B, long N, int num_classes,

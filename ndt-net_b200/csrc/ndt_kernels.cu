@@ -40,9 +40,10 @@ __global__ void __launch_bounds__(256) k_limits(const T *__restrict__ pts, long 
     const int b = blockIdx.y;
     const T *p = pts + (size_t)b * N * 3;
     T mx[3], mn[3];
-    bool any = false;
+    bool any = false, nan = false;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
         const T x = p[i * 3 + 0], y = p[i * 3 + 1], z = p[i * 3 + 2];
+        nan = nan || x != x || y != y || z != z;
         if (!any) { mx[0] = mn[0] = x; mx[1] = mn[1] = y; mx[2] = mn[2] = z; any = true; }
         else {
             mx[0] = x > mx[0] ? x : mx[0]; mn[0] = x < mn[0] ? x : mn[0];
@@ -70,10 +71,13 @@ __global__ void __launch_bounds__(256) k_limits(const T *__restrict__ pts, long 
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            atomicMax(&lim_enc[b * 6 + a], e[a]);
-            atomicMin(&lim_enc[b * 6 + 3 + a], e[3 + a]);
+            atomicMax(&lim_enc[b * kLimWords + a], e[a]);
+            atomicMin(&lim_enc[b * kLimWords + 3 + a], e[3 + a]);
         }
     }
+    // a NaN coordinate is refused (status -5): the reference converts floor(NaN) to unsigned, which is undefined
+    // behaviour in C (voxel.c:89-91); silently voxelising such a point anywhere would not be parity with anything
+    if (__any_sync(0xffffffffu, nan) && (threadIdx.x & 31) == 0) lim_enc[b * kLimWords + 6] = 1ull;
 }
 
 // grid + risk flag for a guess (voxel.c:61-81); returns false when the grid cannot be held
@@ -119,9 +123,9 @@ __global__ void __launch_bounds__(256) k_decide(CloudState *__restrict__ states,
     if (phase == 0) {
         if (tid == 0) {
             for (int a = 0; a < 3; a++) {
-                const double m = dec_f64(lim_enc[b * 6 + a]);
+                const double m = dec_f64(lim_enc[b * kLimWords + a]);
                 s.lim[a] = m > DBL_MIN ? m : DBL_MIN;              // pointclouds.c:44-46,55-61 (A2)
-                const double n = dec_f64(lim_enc[b * 6 + 3 + a]);
+                const double n = dec_f64(lim_enc[b * kLimWords + 3 + a]);
                 s.lim[3 + a] = n < DBL_MAX ? n : DBL_MAX;
             }
             s.guess = (double)(kMaxVoxelGuess - kMinVoxelGuess) / 2.0;   // ndt.c:136
@@ -131,6 +135,7 @@ __global__ void __launch_bounds__(256) k_decide(CloudState *__restrict__ states,
             for (int w = 0; w < kWorkers; w++) s.fail[w] = kDropped;
             s.status = 1;
             if (!set_grid(s)) { s.status = -1; s.G = 0; s.nwords = 0; }
+            if (lim_enc[b * kLimWords + 6]) { s.status = kStatusNaNInput; s.G = 0; s.nwords = 0; }
             s_action = s.status == 1 ? 1 : 0;
         }
         __syncthreads();
@@ -1191,7 +1196,7 @@ cudaError_t selftest_div(long n, unsigned seed, unsigned long long *mismatches_h
 // ------------------------------------------------------------------------------------------------
 __global__ void k_init_limits(unsigned long long *lim_enc, int B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B * 6) lim_enc[i] = (i % 6) < 3 ? 0ull : ~0ull;
+    if (i < B * kLimWords) { const int w = i % kLimWords; lim_enc[i] = w < 3 ? 0ull : (w < 6 ? ~0ull : 0ull); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1216,7 +1221,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     StageTimer &tm = w.timer;
     if (tm.enabled && !tm.created) { for (auto &e : tm.ev) cudaEventCreate(&e); tm.created = true; }
     tm.mark(ST_LIMITS, st);
-    k_init_limits<<<(B * 6 + 127) / 128, 128, 0, st>>>(w.lim_enc, B);
+    k_init_limits<<<(B * kLimWords + 127) / 128, 128, 0, st>>>(w.lim_enc, B);
     {
         int chunks = (int)((N + 256 * 16 - 1) / (256 * 16));
         if (chunks < 1) chunks = 1;

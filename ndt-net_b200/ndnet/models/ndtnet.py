@@ -2,17 +2,31 @@
 signatures, outputs and - so that reference checkpoints load unchanged - the same parameter / buffer names
 (reference: ndtnet.py:17-30 TNet, :100-109 NDTNet, :177-179 classification head, :209-216 segmentation head).
 
-`forward` is the plain PyTorch fp32 definition of the network (it is what the parity tests compare the
-CUDA path against).  `forward_b200` runs the same network through libndnet_b200.so (tcgen05/TMA bf16 GEMMs
-with fused bias/BN/ReLU/max-pool epilogues) in eval mode, and through the fp32 training kernels (train.cu, with
-gradients) when the segmentation module is in training mode.
+`model(points, covariances)` - the call the reference's scripts make (tools/seg_viz.py:133, tools/train.py:69) - runs
+the network through libndnet_b200.so whenever the inputs are CUDA tensors: `forward` dispatches to `forward_b200`
+(tcgen05/TMA bf16 GEMMs with fused bias/BN/ReLU/max-pool epilogues in eval mode; the training kernels of train.cu, with
+gradients, when a segmentation module is in training mode).  `forward_torch` is the plain PyTorch fp32 definition of the
+same network: it is what the parity tests compare the CUDA path against, what CPU tensors get, and what a training-mode
+module without CUDA training kernels (the classification head) falls back to so that autograd keeps working.
+Set `module.b200 = False` (or NDNET_B200_FORWARD=torch in the environment) to force the PyTorch definition.
 """
 from __future__ import annotations
 
+import os
 from enum import Enum
 
 import torch
 from torch import nn
+
+
+def _use_library(module: nn.Module, x: torch.Tensor, has_training_kernels: bool) -> bool:
+    """Whether `module(x, ...)` runs through libndnet_b200.so: CUDA input, not opted out, and - in training mode - only
+    when the library has the backward of this head (otherwise autograd needs the PyTorch graph)."""
+    if not x.is_cuda or not getattr(module, "b200", True) or os.environ.get("NDNET_B200_FORWARD", "") == "torch":
+        return False
+    if not getattr(module, "_b200_supported", lambda: True)():
+        return False
+    return has_training_kernels or not module.training
 
 
 def _pointwise(n_in: int, n_out: int) -> nn.Conv1d:
@@ -85,8 +99,18 @@ def _state_stamp(module: nn.Module):
 
 
 class _B200Mixin:
-    """Builds (once) and runs the CUDA model for an eval-mode module."""
+    """Builds (once) and runs the CUDA model for an eval-mode module; `forward` = the reference's call signature."""
     _kind = 0
+    b200 = True
+
+    def _b200_supported(self) -> bool:
+        """Shapes the CUDA kernels are built for: xyz points + 3x3 covariances; at most 32 segmentation outputs."""
+        return self.point_dim == 3 and self.feature_extractor.extra_dim == 9 and (self._kind == 0 or self.num_classes + 1 <= 32)
+
+    def forward(self, points: torch.Tensor, covariances: torch.Tensor) -> torch.Tensor:
+        if _use_library(self, points, has_training_kernels=self._kind == 1):
+            return self.forward_b200(points, covariances)
+        return self.forward_torch(points, covariances)
 
     def forward_b200(self, points: torch.Tensor, covariances: torch.Tensor) -> torch.Tensor:
         from ndnet_b200.model import B200Model
@@ -109,7 +133,7 @@ class _B200Mixin:
         return m(feat)
 
 
-class NDTNetClassification(nn.Module, _B200Mixin):
+class NDTNetClassification(_B200Mixin, nn.Module):
     _kind = 0
 
     def __init__(self, point_dim: int = 3, num_classes: int = 512, feature_dim: int = 768) -> None:
@@ -118,7 +142,7 @@ class NDTNetClassification(nn.Module, _B200Mixin):
         self.feature_extractor = NDTNet(point_dim, feature_dim=feature_dim)
         self.conv1, self.conv2, self.conv3 = _pointwise(feature_dim, 512), _pointwise(512, 256), _pointwise(256, num_classes)
 
-    def forward(self, points: torch.Tensor, covariances: torch.Tensor) -> torch.Tensor:
+    def forward_torch(self, points: torch.Tensor, covariances: torch.Tensor) -> torch.Tensor:
         """-> (B, num_classes, 1) class probabilities"""
         x, _ = self.feature_extractor(points, covariances)
         x = x.amax(dim=2, keepdim=True)
@@ -127,7 +151,7 @@ class NDTNetClassification(nn.Module, _B200Mixin):
         return torch.softmax(self.conv3(x), dim=1)
 
 
-class NDTNetSegmentation(nn.Module, _B200Mixin):
+class NDTNetSegmentation(_B200Mixin, nn.Module):
     _kind = 1
 
     def __init__(self, point_dim: int = 3, num_classes: int = 16, feature_dim: int = 1024) -> None:
@@ -138,7 +162,7 @@ class NDTNetSegmentation(nn.Module, _B200Mixin):
         self.conv3, self.conv4 = _pointwise(256, 128), _pointwise(128, num_classes + 1)
         self.bn1, self.bn2, self.bn3 = nn.BatchNorm1d(512), nn.BatchNorm1d(256), nn.BatchNorm1d(128)
 
-    def forward(self, points: torch.Tensor, covariances: torch.Tensor) -> torch.Tensor:
+    def forward_torch(self, points: torch.Tensor, covariances: torch.Tensor) -> torch.Tensor:
         """-> (B, N, num_classes + 1) per-distribution log-probabilities"""
         x, x_t2 = self.feature_extractor(points, covariances)
         g = x.amax(dim=2, keepdim=True).expand(-1, -1, x_t2.shape[2])

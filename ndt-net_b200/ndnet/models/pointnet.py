@@ -1,13 +1,14 @@
 """Drop-in for the reference's ndnet/models/pointnet.py: PointNet without the covariance branch, for points of
 any width `point_dim` (e.g. the 12-D mean+covariance points of tools/train_pointnet.py).  Same classes,
 arguments, outputs and parameter names (reference: pointnet.py:65-98 PointNet, :137-149 classification head,
-:169-186 segmentation head).  `forward` is plain PyTorch fp32; `forward_b200` runs the CUDA path (eval mode)."""
+:169-186 segmentation head).  `model(points)` runs the CUDA path (`forward_b200`) for CUDA tensors in eval mode and the
+plain PyTorch fp32 definition (`forward_torch`) otherwise - see ndtnet.py."""
 from __future__ import annotations
 
 import torch
 from torch import nn
 
-from .ndtnet import TNet, _pointwise
+from .ndtnet import TNet, _pointwise, _use_library
 
 
 class PointNet(nn.Module):
@@ -30,6 +31,15 @@ class PointNet(nn.Module):
 
 class _B200PointMixin:
     _kind = 2
+    b200 = True
+
+    def _b200_supported(self) -> bool:
+        return 1 <= self.point_dim <= 16 and (self._kind == 2 or self.num_classes + 1 <= 32)
+
+    def forward(self, points: torch.Tensor) -> torch.Tensor:
+        if _use_library(self, points, has_training_kernels=False):
+            return self.forward_b200(points)
+        return self.forward_torch(points)
 
     def forward_b200(self, points: torch.Tensor) -> torch.Tensor:
         from ndnet_b200.model import B200Model
@@ -45,7 +55,7 @@ class _B200PointMixin:
         return m(points.float().contiguous())
 
 
-class PointNetClassification(nn.Module, _B200PointMixin):
+class PointNetClassification(_B200PointMixin, nn.Module):
     _kind = 2
 
     def __init__(self, point_dim: int = 3, num_classes: int = 512, feature_dim: int = 768) -> None:
@@ -54,14 +64,14 @@ class PointNetClassification(nn.Module, _B200PointMixin):
         self.feature_extractor = PointNet(point_dim=point_dim, feature_dim=feature_dim)
         self.conv1, self.conv2, self.conv3 = _pointwise(feature_dim, 512), _pointwise(512, 256), _pointwise(256, num_classes)
 
-    def forward(self, points: torch.Tensor) -> torch.Tensor:
+    def forward_torch(self, points: torch.Tensor) -> torch.Tensor:
         x, _ = self.feature_extractor(points)
         x = x.amax(dim=2, keepdim=True)
         x = torch.relu(self.conv2(torch.relu(self.conv1(x))))
         return torch.softmax(self.conv3(x), dim=1)
 
 
-class PointNetSegmentation(nn.Module, _B200PointMixin):
+class PointNetSegmentation(_B200PointMixin, nn.Module):
     _kind = 3
 
     def __init__(self, point_dim: int = 3, num_classes: int = 16, feature_dim: int = 768) -> None:
@@ -72,7 +82,7 @@ class PointNetSegmentation(nn.Module, _B200PointMixin):
         self.conv3, self.conv4 = _pointwise(256, 128), _pointwise(128, num_classes + 1)
         self.bn1, self.bn2, self.bn3 = nn.BatchNorm1d(512), nn.BatchNorm1d(256), nn.BatchNorm1d(128)
 
-    def forward(self, points: torch.Tensor) -> torch.Tensor:
+    def forward_torch(self, points: torch.Tensor) -> torch.Tensor:
         x, x_t2 = self.feature_extractor(points)
         g = x.amax(dim=2, keepdim=True).expand(-1, -1, x_t2.shape[2])
         x = torch.cat((x_t2, g), dim=1)

@@ -154,8 +154,8 @@ def smoke_forward(engine, feat: torch.Tensor) -> None:
     net = net.cuda().eval()
     f = torch.nan_to_num(feat.float(), nan=0.0, posinf=0.0, neginf=0.0)
     with torch.no_grad():
-        ref = net(f[:, :, :3], f[:, :, 3:])
-        got = net.forward_b200(f[:, :, :3], f[:, :, 3:])
+        ref = net.forward_torch(f[:, :, :3], f[:, :, 3:])
+        got = net(f[:, :, :3], f[:, :, 3:])                 # model(points, covs): dispatches to the CUDA path
     torch.cuda.synchronize()
     err = (got - ref).abs().max().item()
     scale = max(1.0, ref.abs().max().item())

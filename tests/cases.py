@@ -64,3 +64,14 @@ def medium_cases():
         ("lidar120k_d256", lidar_cloud(120000, 14), None, 0, 256),
         ("lidar120k_d1024", lidar_cloud(120000, 15), None, 0, 1024),
     ]
+
+
+# (cloud name, n_desired_nds, further prune targets): chains during which no prune walk passes over an already-removed
+# entry, i.e. the regime in which the reference's own retained-handle continuation is well defined.
+CLEAN_PRUNE_CHAINS = [
+    ("lidar16k_d1000", 881, [877, 873]),
+    ("lidar16k_d1000_labels", 888, [880, 866]),
+    ("modelnet2048_d512", 449, [430, 405]),
+    ("lidar8001_negative_axis", 265, [260, 256]),
+    ("modelnet3000_duplicates", 130, [120, 110]),
+]

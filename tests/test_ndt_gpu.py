@@ -283,3 +283,48 @@ def test_legacy_sampler_drop_in():
     bad.downsample(64)
     assert bad.status == -3
     bad.cleanup()
+
+
+def test_nan_coordinates_are_refused_not_voxelised(engine):
+    """A NaN coordinate makes the reference convert floor(NaN) to unsigned (undefined behaviour, voxel.c:89-91).  The
+    library refuses such a cloud (status -5, zero rows) and leaves the other clouds of the batch untouched; +-inf
+    coordinates cannot be held by any grid and end in -1."""
+    from ndnet_b200.synth import lidar_batch
+    pts = lidar_batch(4, 20000, seed0=910)
+    clean = engine.downsample(torch.from_numpy(pts).cuda(), 400, nan_to_num=False, want_f64=True, want_voxel=True)
+    bad = pts.copy()
+    bad[1, 12345, 2] = np.nan
+    bad[3, 7, 0] = np.inf
+    out = engine.downsample(torch.from_numpy(bad).cuda(), 400, nan_to_num=False, want_f64=True, want_voxel=True)
+    assert out.info["status"].tolist() == [0, -5, 0, -1]
+    for b in (1, 3):
+        assert out.info[b]["num_out"] == 0 and torch.all(out.feat64[b] == 0) and torch.all(out.voxel[b] == -1)
+    for b in (0, 2):
+        assert same_bits(out.feat64[b].cpu().numpy(), clean.feat64[b].cpu().numpy()) and torch.equal(out.voxel[b], clean.voxel[b])
+    # the legacy symbol reports it too
+    from ndnet.preprocessing.ndt_legacy import NDT_Sampler
+    s = NDT_Sampler(bad[1].astype(np.float64))
+    p, c, k = s.downsample(400)
+    assert s.status == -5 and np.all(p == 0) and np.all(c == 0)
+    s.cleanup()
+
+
+def test_failed_workspace_allocation_leaves_a_usable_context():
+    """A workspace allocation that fails must not leave capacities behind (the next call would run every kernel on
+    null buffers): the failing call returns the error, the next one allocates afresh and gives the usual result."""
+    from ndnet_b200 import _lib
+    from ndnet_b200.engine import NdtEngine
+    from ndnet_b200.synth import lidar_batch
+    e = NdtEngine(0)
+    pts = torch.from_numpy(lidar_batch(2, 16000, seed0=920)).cuda()
+    first = e.downsample(pts, 300, nan_to_num=False, want_f64=True)
+    assert _lib.lib().ndnet_b200_test_fail_next_reserve(e.handle) == 0
+    bigger = torch.from_numpy(lidar_batch(3, 16000, seed0=920)).cuda()          # needs a larger workspace -> reserve() runs
+    with pytest.raises(RuntimeError, match="workspace allocation"):
+        e.downsample(bigger, 300, nan_to_num=False, want_f64=True)
+    again = e.downsample(pts, 300, nan_to_num=False, want_f64=True)              # same shape as before the failure
+    torch.cuda.synchronize()
+    assert np.all(again.info["status"] == 0) and same_bits(again.feat64.cpu().numpy(), first.feat64.cpu().numpy())
+    third = e.downsample(bigger, 300, nan_to_num=False, want_f64=True)
+    assert same_bits(third.feat64[:2].cpu().numpy(), first.feat64.cpu().numpy())
+    e.close()

@@ -109,3 +109,28 @@ def test_oracle_matches_reference_live():
         occupied = r.nd["num_samples"] > 0
         assert np.array_equal(occupied, o.num_samples > 0)
         assert same_bits(r.nd["mean"][occupied], o.mean[occupied])
+
+
+@pytest.mark.skipif(not ref_ctypes.have_ref("det"), reason="reference build absent")
+@pytest.mark.parametrize("name,d,chain", cases.CLEAN_PRUNE_CHAINS, ids=[c[0] for c in cases.CLEAN_PRUNE_CHAINS])
+def test_prune_continuation_model_matches_reference_live(name, d, chain):
+    """Row f1: the list-walk restatement the GPU test uses (tests/prune_model.py::ListWalk on the oracle's sorted list)
+    against the reference build's own prune_nds / to_point_cloud on retained handles.  The reference's continuation is
+    only defined while no walk skipped an already-removed entry (its shifted list then reads past its end, SURVEY.md
+    A15); cases.CLEAN_PRUNE_CHAINS are (cloud, D, further targets) picked so that the whole chain stays in that regime."""
+    from tests.prune_model import ListWalk, RefHandles
+    _, pts, labels, ncls, _ = [c for c in cases.small_cases() if c[0] == name][0]
+    o = ndt_oracle.run(pts, d, labels, ncls)
+    walk = ListWalk(o)
+    assert walk.prune(d) == o.prune_ret == 0 and not walk.skipped
+    ref = RefHandles(pts, labels, ncls, d)
+    assert ref.ret == 0 and ref.n_valid.value == walk.n_valid and ref.n_kl.value == walk.num_kl
+    for d2 in chain:
+        assert walk.prune(d2) == 0 and not walk.skipped
+        rp, rc, rk = ref.prune(d2)
+        rows = walk.rows()
+        assert ref.n_valid.value == walk.n_valid == len(rows) == d2 and ref.n_kl.value == walk.num_kl
+        assert same_bits(rp, o.mean[rows]) and same_bits(rc, o.cov[rows])
+        if labels is not None:
+            assert np.array_equal(rk, o.cls[rows])
+    ref.close()

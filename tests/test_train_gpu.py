@@ -76,9 +76,9 @@ def test_forward_backward_match_torch_autograd(B, N, F, C, loss):
     net_64 = copy.deepcopy(net_a).double()
     pts, cov, gt = _batch(B * 1000 + N, B, N, C)
     fn = reference_loss if loss == "reference" else (lambda pred, gt: -(pred * gt).sum() / (B * N))
-    out_a = net_a(pts, cov)
+    out_a = net_a.forward_torch(pts, cov)
     fn(out_a, gt).backward()
-    out_64 = net_64(pts.double(), cov.double())
+    out_64 = net_64.forward_torch(pts.double(), cov.double())
     fn(out_64, gt.double()).backward()
     trainer = SegTrainer(net_b)
     out_b = trainer(pts, cov)
@@ -105,9 +105,9 @@ def test_forward_b200_in_training_mode_is_the_training_path_and_steps_like_torch
     losses = []
     for step in range(3):
         pts, cov, gt = _batch(100 + step, B, N, C)
-        la = reference_loss(net_a(pts, cov), gt)
+        la = reference_loss(net_a.forward_torch(pts, cov), gt)
         opt_a.zero_grad(); la.backward(); opt_a.step()
-        lb = reference_loss(net_b.forward_b200(pts, cov), gt)
+        lb = reference_loss(net_b(pts, cov), gt)      # tools/train.py:69: model(pcl, covs) in train() mode
         opt_b.zero_grad(); lb.backward(); opt_b.step()
         losses.append((la.item(), lb.item()))
         assert abs(la.item() - lb.item()) <= 2e-2 * abs(la.item()) + 1e-4, losses
@@ -301,8 +301,8 @@ def test_eval_after_training_uses_the_updated_running_statistics():
     reference_loss(net.forward_b200(pts, cov), gt).backward()
     net.eval()
     with torch.no_grad():
-        want = net(pts, cov)
-        got = net.forward_b200(pts, cov)
+        want = net.forward_torch(pts, cov)
+        got = net(pts, cov)
     assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
 
 
@@ -319,11 +319,11 @@ def test_eval_model_is_rebuilt_when_the_weights_change():
         opt.step()
         net.eval()
         with torch.no_grad():
-            want, got = net(pts, cov), net.forward_b200(pts, cov)
+            want, got = net.forward_torch(pts, cov), net.forward_b200(pts, cov)
         assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
     net.load_state_dict(deterministic_state_dict(net, 8))
     with torch.no_grad():
-        want, got = net(pts, cov), net.forward_b200(pts, cov)
+        want, got = net.forward_torch(pts, cov), net.forward_b200(pts, cov)
     assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
 
 

@@ -106,7 +106,7 @@ def main():
         def step(i):
             pcl, gt = sets[i % len(sets)]
             p, c, g = ndt_preprocessing(N_NDS, pcl, gt, N_CLASSES)      # :69
-            pred = net.forward_b200(p, c) if mode == "ours" else net(p, c)   # :71
+            pred = net(p, c) if mode == "ours" else net.forward_torch(p, c)   # :71
             loss = reference_loss(pred, g)                               # :74
             opt.zero_grad()
             loss.backward()                                              # :78

@@ -11,13 +11,13 @@ net = NDTNetSegmentation(num_classes=28, feature_dim=1024); net.load_state_dict(
 for (B, N, sc) in [(2, 200, 1.0), (2, 200, 0.05), (1, 1000, 0.05), (64, 1000, 0.05)]:
     p, c = inputs(3, B, N); p, c = torch.from_numpy(p).cuda() * sc, torch.from_numpy(c).cuda() * sc
     with torch.no_grad():
-        ref = net(p, c); got = net.forward_b200(p, c)
+        ref = net.forward_torch(p, c); got = net.forward_b200(p, c)
         torch.cuda.synchronize()
         t = time.time(); 
         for _ in range(5): got = net.forward_b200(p, c)
         torch.cuda.synchronize(); dt = (time.time() - t) / 5
         t = time.time()
-        for _ in range(5): ref = net(p, c)
+        for _ in range(5): ref = net.forward_torch(p, c)
         torch.cuda.synchronize(); dt2 = (time.time() - t) / 5
     d = (got - ref).abs()
     print("   ref absmax", ref.abs().max().item(), "rel err (max/absmax)", (d.max() / ref.abs().max()).item())
@@ -27,6 +27,6 @@ cls = NDTNetClassification(); cls.load_state_dict(deterministic_state_dict(cls, 
 for (B, N) in [(3, 130), (32, 512)]:
     p, c = inputs(4, B, N); p, c = torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda()
     with torch.no_grad():
-        ref = cls(p, c); got = cls.forward_b200(p, c)
+        ref = cls.forward_torch(p, c); got = cls.forward_b200(p, c)
     d = (got - ref).abs()
     print("cls", B, N, "max", d.max().item(), "ref max prob", ref.max().item(), "argmax agree", (got.argmax(1) == ref.argmax(1)).float().mean().item())
