@@ -111,6 +111,7 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     const long nN = N > N_cap ? N : N_cap;
     const long nD = D > D_cap ? D : D_cap;
     const int nbins = bins > bins_cap ? bins : bins_cap;
+    const bool inject_failure = fail_next_reserve;
     release();
     B_cap = nB; N_cap = nN; D_cap = nD; bins_cap = nbins;
     vcap = (unsigned)((double)nD * 1.2) + 2;
@@ -123,7 +124,7 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     // a failed allocation leaves NO capacity behind: release() frees what was obtained and zeroes the caps, so the next
     // call re-allocates instead of passing the early-out above with null or partial buffers
 #define A(ptr, count) if ((e = alloc(ptr, (size_t)(count))) != cudaSuccess) { release(); return e; }
-    if (fail_next_reserve) { fail_next_reserve = false; e = cudaErrorMemoryAllocation; release(); return e; }
+    if (inject_failure) { e = cudaErrorMemoryAllocation; release(); return e; }
     if ((e = cudaMalloc((void **)&states, cloud_state_size() * nB)) != cudaSuccess) { release(); return e; }
     A(lim_enc, (size_t)nB * 8);
     A(bitmap, (size_t)nB * bitmap_stride);

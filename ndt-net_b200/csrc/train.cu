@@ -24,6 +24,9 @@
 #include <string>
 #include <vector>
 
+namespace ndt { void count_launches(long n); long launches(); }
+
+
 namespace train {
 
 constexpr float kBnEps = 1e-5f;
@@ -319,6 +322,10 @@ struct Block {            // Linear (+ BatchNorm (+ ReLU)) over `rows` rows
     double *red_bias = nullptr;           // out doubles for the bias gradient
 };
 
+// every kernel launch of this file goes through the library-wide launch counter (bench.py's gpu_launches); under a CUDA
+// graph the capture pass counts once and each replay adds the number counted then (run_graphed)
+static inline void train_count() { ndt::count_launches(1); }
+
 struct TNet {
     int d = 0;
     Block c1, c2, c3, f1, f2, f3;
@@ -345,7 +352,7 @@ struct Trainer {
     // replayed; the first pass of a configuration runs eagerly (one-time attribute calls stay out of the capture)
     int use_graph = 0;
     cudaStream_t cap = nullptr;
-    struct GraphSlot { cudaGraphExec_t exec = nullptr; std::vector<const void *> key; int seen = 0; } gf, gb;
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; std::vector<const void *> key; int seen = 0; long kernels = 0; } gf, gb;
     float *feat_static = nullptr, *dlogp_static = nullptr, *flat_grad = nullptr;
     std::vector<long> grad_off;           // per tensor: offset (floats) of its gradient in the flat buffer, -1 for buffers
     long flat_elems = 0;
@@ -500,7 +507,7 @@ static void gemm(cudaStream_t st, const float *A, long sai, long sak, const floa
         else cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st);
     }
     dim3 grid(cdiv(N, kTile), cdiv(M, kTile), batch * splitk);
-    k_gemm32<<<grid, 256, 0, st>>>(p);
+    train_count(), k_gemm32<<<grid, 256, 0, st>>>(p);
 }
 
 // ---- tcgen05 / TF32 path (train_gemm.cuh) --------------------------------------------------------------------------
@@ -545,7 +552,7 @@ static bool launch_tf32(cudaStream_t st, const CUtensorMap &ma, const CUtensorMa
         if (cudaFuncSetAttribute(k_gemm_tf32<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
         attr_done[dev] = true;
     }
-    k_gemm_tf32<BN><<<grid, mlp::kGemmThreads, smem, st>>>(ma, mb, a);
+    train_count(), k_gemm_tf32<BN><<<grid, mlp::kGemmThreads, smem, st>>>(ma, mb, a);
     return true;
 }
 
@@ -594,14 +601,14 @@ __global__ void __launch_bounds__(256) k_transpose(const float *__restrict__ src
 }
 
 static void transpose(cudaStream_t st, const float *src, long lds, int rows, int cols, float *dst, long ldd) {
-    k_transpose<<<dim3(cdiv(cols, 32), cdiv(rows, 32)), 256, 0, st>>>(src, lds, rows, cols, dst, ldd);
+    train_count(), k_transpose<<<dim3(cdiv(cols, 32), cdiv(rows, 32)), 256, 0, st>>>(src, lds, rows, cols, dst, ldd);
 }
 
 template <int OP>
 static void colred(cudaStream_t st, RedP p, int batch) {
     const unsigned ysplit = p.rows >= 4096 ? 32 : p.rows >= 512 ? 8 : 1;
     dim3 grid(cdiv(p.cols, 32), ysplit, batch);
-    k_colred<OP><<<grid, 256, 0, st>>>(p);
+    train_count(), k_colred<OP><<<grid, 256, 0, st>>>(p);
 }
 
 struct Pass {
@@ -622,9 +629,9 @@ static void block_fwd(const Pass &ps, Block &k, const float *X, long ldx) {
     RedP r{};
     r.P = k.Y; r.ldp = out; r.rows = (int)k.rows; r.cols = out; r.s0 = k.red; r.s1 = k.red + out;
     colred<RED_STATS>(ps.st, r, 1);
-    k_bn_finalize<<<cdiv(out, 128), 128, 0, ps.st>>>(k.red, k.red + out, (int)k.rows, out, k.mean, k.rstd, ps.P(k.bn.rm), ps.P(k.bn.rv),
+    train_count(), k_bn_finalize<<<cdiv(out, 128), 128, 0, ps.st>>>(k.red, k.red + out, (int)k.rows, out, k.mean, k.rstd, ps.P(k.bn.rm), ps.P(k.bn.rv),
                                                      (long long *)ps.P(k.bn.nbt), ps.update_running);
-    k_bn_apply<<<cdiv(k.rows * out, 256), 256, 0, ps.st>>>(k.Y, k.rows, out, k.mean, k.rstd, ps.P(k.bn.g), ps.P(k.bn.be), k.relu ? 1 : 0, k.A);
+    train_count(), k_bn_apply<<<cdiv(k.rows * out, 256), 256, 0, ps.st>>>(k.Y, k.rows, out, k.mean, k.rstd, ps.P(k.bn.g), ps.P(k.bn.be), k.relu ? 1 : 0, k.A);
 }
 
 // k.dA holds dL/dA on entry; on return it holds dL/dY.  dX (optional) receives or accumulates dL/dX.
@@ -636,15 +643,15 @@ static void block_bwd(const Pass &ps, Block &k, const float *X, long ldx, float 
         r.P = k.dA; r.ldp = out; r.Y = k.Y; r.ldy = out; r.Aact = k.relu ? k.A : nullptr; r.lda = out; r.mean = k.mean; r.rstd = k.rstd;
         r.rows = (int)k.rows; r.cols = out; r.s0 = s0; r.s1 = s1;
         colred<RED_BNBWD>(ps.st, r, 1);
-        if (ps.Gr(k.bn.be) && ps.Gr(k.bn.g)) k_bnbwd_finalize<<<cdiv(out, 128), 128, 0, ps.st>>>(s0, s1, out, ps.Gr(k.bn.be), ps.Gr(k.bn.g));
-        k_bnbwd_apply<<<cdiv(k.rows * out, 256), 256, 0, ps.st>>>(k.dA, k.Y, k.relu ? k.A : nullptr, k.rows, out, k.mean, k.rstd, ps.P(k.bn.g), s0, s1);
+        if (ps.Gr(k.bn.be) && ps.Gr(k.bn.g)) train_count(), k_bnbwd_finalize<<<cdiv(out, 128), 128, 0, ps.st>>>(s0, s1, out, ps.Gr(k.bn.be), ps.Gr(k.bn.g));
+        train_count(), k_bnbwd_apply<<<cdiv(k.rows * out, 256), 256, 0, ps.st>>>(k.dA, k.Y, k.relu ? k.A : nullptr, k.rows, out, k.mean, k.rstd, ps.P(k.bn.g), s0, s1);
     }
     float *dY = k.dA;
     if (ps.Gr(k.lin.b)) {
         RedP r{};
         r.P = dY; r.ldp = out; r.rows = (int)k.rows; r.cols = out; r.s0 = k.red_bias;
         colred<RED_SUM>(ps.st, r, 1);
-        k_sum_finalize<<<cdiv(out, 128), 128, 0, ps.st>>>(k.red_bias, out, ps.Gr(k.lin.b));
+        train_count(), k_sum_finalize<<<cdiv(out, 128), 128, 0, ps.st>>>(k.red_bias, out, ps.Gr(k.lin.b));
     }
     Trainer &t = ps.t;
     const int rows = (int)k.rows;
@@ -672,12 +679,12 @@ static void tnet_fwd(const Pass &ps, TNet &n, const float *X, long ldx) {
     block_fwd(ps, n.c1, X, ldx);
     block_fwd(ps, n.c2, n.c1.A, 64);
     block_fwd(ps, n.c3, n.c2.A, 128);
-    k_maxpool_fwd<<<dim3(cdiv(1024, 32), t.B), 256, 0, ps.st>>>(n.c3.A, t.N, 1024, n.G, n.idx);
+    train_count(), k_maxpool_fwd<<<dim3(cdiv(1024, 32), t.B), 256, 0, ps.st>>>(n.c3.A, t.N, 1024, n.G, n.idx);
     block_fwd(ps, n.f1, n.G, 1024);
     block_fwd(ps, n.f2, n.f1.A, 512);
     block_fwd(ps, n.f3, n.f2.A, 256);
     cudaMemcpyAsync(n.T, n.f3.Y, sizeof(float) * t.B * n.d * n.d, cudaMemcpyDeviceToDevice, ps.st);
-    k_add_identity<<<cdiv((long)t.B * n.d, 128), 128, 0, ps.st>>>(n.T, t.B, n.d);
+    train_count(), k_add_identity<<<cdiv((long)t.B * n.d, 128), 128, 0, ps.st>>>(n.T, t.B, n.d);
 }
 
 // n.dT holds dL/dT on entry
@@ -688,7 +695,7 @@ static void tnet_bwd(const Pass &ps, TNet &n, const float *X, long ldx, float *d
     block_bwd(ps, n.f3, n.f2.A, 256, n.f2.dA, 256, false);
     block_bwd(ps, n.f2, n.f1.A, 512, n.f1.dA, 512, false);
     block_bwd(ps, n.f1, n.G, 1024, n.dG, 1024, false);
-    k_maxpool_bwd<<<cdiv(M * 1024, 256), 256, 0, ps.st>>>(n.dG, n.idx, t.N, 1024, M * 1024, n.c3.dA);
+    train_count(), k_maxpool_bwd<<<cdiv(M * 1024, 256), 256, 0, ps.st>>>(n.dG, n.idx, t.N, 1024, M * 1024, n.c3.dA);
     block_bwd(ps, n.c3, n.c2.A, 128, n.c2.dA, 128, false);
     block_bwd(ps, n.c2, n.c1.A, 64, n.c1.dA, 64, false);
     block_bwd(ps, n.c1, X, ldx, dX, lddx, accumulate_dx);
@@ -702,19 +709,19 @@ static int forward(Trainer &t, const float *feat, int B, int N, float *const *te
     t.feat = feat;
     cudaMemsetAsync(t.arena + t.zero_begin, 0, t.zero_end - t.zero_begin, st);
     tnet_fwd(ps, t.t1, feat, 12);                                                         // ndtnet.py:131-132
-    k_apply_t_fwd<<<cdiv(M, 128), 128, 0, st>>>(feat, t.t1.T, M, N, t.X12);              // :134-146
+    train_count(), k_apply_t_fwd<<<cdiv(M, 128), 128, 0, st>>>(feat, t.t1.T, M, N, t.X12);              // :134-146
     block_fwd(ps, t.c1, t.X12, 12);                                                       // :149
     tnet_fwd(ps, t.t2, t.c1.A, 64);                                                       // :152
     gemm(st, t.c1.A, 64, 1, t.t2.T, 1, 64, t.X2, 64, N, 64, 64, nullptr, false, B, (long)N * 64, 4096, (long)N * 64);   // :153-155
     block_fwd(ps, t.c2, t.X2, 64);                                                        // :160
     block_fwd(ps, t.c3, t.c2.A, 128);                                                     // :161
-    k_maxpool_fwd<<<dim3(cdiv(t.F, 32), B), 256, 0, st>>>(t.c3.A, N, t.F, t.Gf, t.idxf); // :224
-    k_concat_fwd<<<cdiv(M * (64 + t.F), 256), 256, 0, st>>>(t.X2, t.Gf, M, N, t.F, t.H0);   // :227-230
+    train_count(), k_maxpool_fwd<<<dim3(cdiv(t.F, 32), B), 256, 0, st>>>(t.c3.A, N, t.F, t.Gf, t.idxf); // :224
+    train_count(), k_concat_fwd<<<cdiv(M * (64 + t.F), 256), 256, 0, st>>>(t.X2, t.Gf, M, N, t.F, t.H0);   // :227-230
     block_fwd(ps, t.h1, t.H0, 64 + t.F);                                                  // :233
     block_fwd(ps, t.h2, t.h1.A, 512);
     block_fwd(ps, t.h3, t.h2.A, 256);
     block_fwd(ps, t.h4, t.h3.A, 128);                                                     // :236
-    k_logsm_fwd<<<cdiv(M, 128), 128, 0, st>>>(t.h4.Y, M, t.C, t.logp);                    // :239
+    train_count(), k_logsm_fwd<<<cdiv(M, 128), 128, 0, st>>>(t.h4.Y, M, t.C, t.logp);                    // :239
     if (out_logp) cudaMemcpyAsync(out_logp, t.logp, sizeof(float) * M * t.C, cudaMemcpyDeviceToDevice, st);
     e = cudaGetLastError();
     if (e != cudaSuccess) { t.err = std::string("forward: ") + cudaGetErrorString(e); return -100 - (int)e; }
@@ -729,7 +736,7 @@ static int backward(Trainer &t, const float *dlogp, float *const *tensors, float
     Pass ps{t, tensors, grads, st, 0};
     // the forward's column sums are already folded into mean/rstd: clear every accumulator for this pass
     cudaMemsetAsync(t.arena + t.zero_begin, 0, t.zero_end - t.zero_begin, st);
-    k_logsm_bwd<<<cdiv(M, 128), 128, 0, st>>>(dlogp, t.logp, M, t.C, t.h4.dA);
+    train_count(), k_logsm_bwd<<<cdiv(M, 128), 128, 0, st>>>(dlogp, t.logp, M, t.C, t.h4.dA);
     block_bwd(ps, t.h4, t.h3.A, 128, t.h3.dA, 128, false);
     block_bwd(ps, t.h3, t.h2.A, 256, t.h2.dA, 256, false);
     block_bwd(ps, t.h2, t.h1.A, 512, t.h1.dA, 512, false);
@@ -739,9 +746,9 @@ static int backward(Trainer &t, const float *dlogp, float *const *tensors, float
         RedP r{};
         r.P = t.dH0 + 64; r.ldp = W; r.rows = N; r.cols = t.F; r.batch_stride_rows = N; r.s0 = t.red_gf;
         colred<RED_SUM>(st, r, B);
-        k_sum_finalize<<<cdiv((long)B * t.F, 128), 128, 0, st>>>(t.red_gf, (long)B * t.F, t.dGf);
+        train_count(), k_sum_finalize<<<cdiv((long)B * t.F, 128), 128, 0, st>>>(t.red_gf, (long)B * t.F, t.dGf);
     }
-    k_maxpool_bwd<<<cdiv(M * t.F, 256), 256, 0, st>>>(t.dGf, t.idxf, N, t.F, M * t.F, t.c3.dA);
+    train_count(), k_maxpool_bwd<<<cdiv(M * t.F, 256), 256, 0, st>>>(t.dGf, t.idxf, N, t.F, M * t.F, t.c3.dA);
     block_bwd(ps, t.c3, t.c2.A, 128, t.c2.dA, 128, false);
     block_bwd(ps, t.c2, t.X2, 64, t.dH0, W, true);                     // dX2 lives in the first 64 columns of dH0
     // x2 = x1 . T2 per cloud:  dX1 = dX2 . T2^T ;  dT2 = X1^T . dX2
@@ -749,7 +756,7 @@ static int backward(Trainer &t, const float *dlogp, float *const *tensors, float
     gemm(st, t.c1.A, 1, 64, t.dH0, 1, W, t.t2.dT, 64, 64, 64, N, nullptr, false, B, (long)N * 64, (long)N * W, 4096);
     tnet_bwd(ps, t.t2, t.c1.A, 64, t.c1.dA, 64, true);
     block_bwd(ps, t.c1, t.X12, 12, t.dX12, 12, false);
-    k_apply_t_bwd<<<B, 256, 0, st>>>(t.feat, t.dX12, N, t.t1.dT);
+    train_count(), k_apply_t_bwd<<<B, 256, 0, st>>>(t.feat, t.dX12, N, t.t1.dT);
     tnet_bwd(ps, t.t1, t.feat, 12, nullptr, 0, false);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { t.err = std::string("backward: ") + cudaGetErrorString(e); return -100 - (int)e; }
@@ -768,13 +775,17 @@ static int run_graphed(Trainer &t, Trainer::GraphSlot &g, const std::vector<cons
         if (!t.cap && cudaStreamCreateWithFlags(&t.cap, cudaStreamNonBlocking) != cudaSuccess) return body(st);
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(t.cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return body(st); }
+        const long before = ndt::launches();
         const int rc = body(t.cap);
+        g.kernels = ndt::launches() - before;
         cudaError_t e = cudaStreamEndCapture(t.cap, &graph);
         if (rc != 0 || e != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); g.seen = 0; return rc != 0 ? rc : body(st); }
         e = cudaGraphInstantiate(&g.exec, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; g.seen = 0; return body(st); }
         g.seen = 2;
+    } else {
+        ndt::count_launches(g.kernels);
     }
     const cudaError_t e = cudaGraphLaunch(g.exec, st);
     if (e != cudaSuccess) { t.err = std::string("graph launch: ") + cudaGetErrorString(e); return -100 - (int)e; }
