@@ -40,24 +40,23 @@ NDT_HD unsigned cell_exact64(double p, double off, double vs, double rv) {
 
 // fp32 prefilter for fp32 inputs: the offset is the minimum of fp32 values, hence itself an fp32 value, so
 // q32 = RN32(RN32(p - off) * RN32(1/vs)) differs from the reference's fp64 quotient by less than 2e-7 q.  When q32
-// is further than 4e-7 q from an integer the two have the same floor (returns true, cell set); otherwise (about 1e-5 of
-// the points) the caller takes the exact path.  The floor itself is taken with the 2^23 magic-number add (FADD/integer
+// is further than 4e-7 q from the nearest integer the two have the same floor (returns true, cell set); otherwise (about
+// 1e-5 of the points) the caller takes the exact path.  The integer is taken with the 2^23 magic-number add (FADD/integer
 // pipes): the conversion instructions (F2F/FRND/F2I) all issue on the quarter-rate XU pipe, which is what bounded k_count.
+// Ten instructions per axis: FADD, FMUL, FADD, IADD, FADD, FADD, FMUL, two FSETP, one predicated IADD.
+//   * rn = RN(q) exactly while q < 2^22; beyond 1.25e6 the margin eps = 4e-7 q exceeds 0.5 >= |q - rn|, so large, infinite
+//     and NaN quotients never decide (no range test needed);
+//   * d >= 0 (off is the minimum), so q >= 0 and a quotient below 1/2 is in cell 0 whatever its distance from 0:
+//     flat ground at the minimum z puts most of a scan exactly there.
 NDT_HD bool cell_prefilter32(float p, float off32, float rv32, unsigned &cell) {
     const float d = p - off32;
     const float q = d * rv32;
-    if (q >= 0.0f && q < 4194304.0f) {
-        const float m = q + 8388608.0f;                       // RN(q) in the low mantissa bits
-        int ri = float_bits(m) - 0x4B000000;
-        float rf = m - 8388608.0f;
-        if (rf > q) { ri -= 1; rf -= 1.0f; }                  // nearest -> floor
-        const float t = q - rf;
-        const float eps = q * 4e-7f;
-        // d >= 0 (off is the minimum, an fp32 value), so cell 0 has no lower-boundary ambiguity: flat ground at
-        // the minimum z puts most of a scan exactly there
-        if ((t > eps || ri == 0) && (1.0f - t) > eps) { cell = (unsigned)ri; return true; }
-    }
-    return false;
+    const float m = q + 8388608.0f;                           // RN(q) in the low mantissa bits
+    const int ri = float_bits(m) - 0x4B000000;
+    const float t = q - (m - 8388608.0f);                     // signed distance from the nearest integer, |t| <= 1/2
+    const float eps = q * 4e-7f;
+    cell = (unsigned)(t < 0.0f ? ri - 1 : ri);                // nearest -> floor
+    return fabsf(t) > eps || q < 0.5f;
 }
 
 }  // namespace ndt

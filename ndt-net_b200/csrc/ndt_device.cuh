@@ -269,6 +269,17 @@ template <> __device__ __forceinline__ void load_sorted<double>(const double *p,
     const double2 v = *reinterpret_cast<const double2 *>(p);
     x = v.x; y = v.y; z = p[2];
 }
+// the whole record: coordinates and the label lane
+template <typename T> __device__ __forceinline__ void load_sorted_rec(const T *p, T &x, T &y, T &z, unsigned &label);
+template <> __device__ __forceinline__ void load_sorted_rec<float>(const float *p, float &x, float &y, float &z, unsigned &label) {
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    x = v.x; y = v.y; z = v.z; label = __float_as_uint(v.w);
+}
+template <> __device__ __forceinline__ void load_sorted_rec<double>(const double *p, double &x, double &y, double &z, unsigned &label) {
+    const double2 v = *reinterpret_cast<const double2 *>(p);
+    const double2 w = *reinterpret_cast<const double2 *>(p + 2);
+    x = v.x; y = v.y; z = w.x; label = (unsigned)__double_as_longlong(w.y);
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ unsigned sorted_label(const float *p) { return __float_as_uint(p[3]); }
 __device__ __forceinline__ unsigned sorted_label(const double *p) { return (unsigned)__double_as_longlong(p[3]); }

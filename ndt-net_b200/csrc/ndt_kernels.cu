@@ -13,7 +13,7 @@
 #include <cstring>
 
 #ifndef NDT_STATS_WARPS
-#define NDT_STATS_WARPS 2
+#define NDT_STATS_WARPS 4
 #endif
 #ifndef NDT_STATS_MIN_BLOCKS
 #define NDT_STATS_MIN_BLOCKS 4
@@ -477,14 +477,41 @@ __device__ __forceinline__ double div_by_count(double d, double cnt) {
     return d / cnt;
 }
 
+// Shared memory of one warp of k_stats.  Dimension-major rows of 33 doubles: lane k (phase B, staging) touches word 2k of
+// a row, chain / accumulator lane l (phase A) touches row l at a common k; rows are 66 words apart, so both patterns are
+// bank-conflict free.
+struct StatsWarpSmem {
+    double x[kQ][3][33];        // this round's points
+    double mu[kQ][3][33];       // means: [.][0] before the round's first point, [.][k+1] after point k
+    double t[kQ][6][33];        // terms of the round: m2 x3, c01, c02, c12 (phase A of the next round adds them)
+    double2 r[32];              // 1 / count as an unevaluated sum {rh, rl} (~106 bits), shared by the voxels
+    unsigned h[kQ][kSmemLabelBins];   // label histograms
+};
+
+// Label vote of kQ voxels from a warp's shared-memory histograms (normal_distributions.c:107-121): most frequent class,
+// lowest index on ties, 0 when nothing was counted.  Every lane returns the class of voxel q.
+__device__ __forceinline__ unsigned vote_from_hist(const unsigned *h, int nbins, int lane) {
+    unsigned best = 0; int bc = 0x7fffffff;
+    for (int j = lane; j < nbins; j += 32) { const unsigned x = h[j]; if (x > best) { best = x; bc = j; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+        if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
+    }
+    return best > 0 ? (unsigned)bc : 0u;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
                                                const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                                const unsigned *__restrict__ vox_order,
-                                               double *__restrict__ mean, double *__restrict__ cov) {
+                                               double *__restrict__ mean, double *__restrict__ cov,
+                                               uint16_t *__restrict__ cls, int vote_bins) {
     // Each warp runs kQ heavy voxels (neighbours in the size-ordered list, so of similar length) in lockstep: the
     // three mean chains of voxel q sit on lanes 3q..3q+2, its six running sums on lanes 6q..6q+5, so the paced
-    // instruction stream (phase A) is shared by all of them.
+    // instruction stream (phase A) is shared by all of them.  vote_bins > 0: the label vote is taken here too, from
+    // the label lane of the same records (shared-memory histogram per voxel, <= kSmemLabelBins classes).
     const int b = blockIdx.x;
     const CloudState &s = states[b];
     if (s.status != 0) return;
@@ -504,40 +531,44 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
         } else { vv[q] = 0; nn[q] = 0; pp[q] = sorted; }
     }
 
-    // point-major layouts: in phase A the chain lanes (accumulator lanes) read consecutive banks and every other
-    // lane reads the same word as a neighbour (broadcast): no bank conflicts on the paced path
-    __shared__ double2 s_x[kStatsWarps][kQ][32][3];      // per voxel, point, dimension: {x, x * rl}
-    __shared__ double2 s_r[kStatsWarps][32];            // 1 / count as an unevaluated sum {rh, rl} (~106 bits), shared by both voxels
-    __shared__ double s_mu[kStatsWarps][kQ][33][3];      // means: [0][.] before the round's first point, [k+1][.] after point k
-    __shared__ double s_t[kStatsWarps][2][kQ][32][6];    // [buffer][voxel] terms of the round: m2 x3, c01, c02, c12
-    double2 *rs = s_r[warp];
+    // one StatsWarpSmem per warp (dynamic shared memory: 4 warps x 14 KB exceeds the static limit)
+    extern __shared__ __align__(16) unsigned char s_stats_raw[];
+    StatsWarpSmem &sm = reinterpret_cast<StatsWarpSmem *>(s_stats_raw)[warp];
+    double2 *rs = sm.r;
 
     const int cq = lane < 3 * kQ ? lane / 3 : kQ - 1, cj = lane < 3 * kQ ? lane % 3 : 2;     // chain lane -> (voxel, dimension)
     const int aq = lane < 6 * kQ ? lane / 6 : kQ - 1, at = lane < 6 * kQ ? lane % 6 : 5;     // accumulator lane -> (voxel, term)
     const bool chain_lane = lane < 3 * kQ, acc_lane = lane < 6 * kQ, cov_lane = acc_lane && at >= 3;
+    const double *xs = sm.x[cq][cj];
+    double *mus = sm.mu[cq][cj];
+    const double *tp = sm.t[aq][at];
     double mu = 0.0, acc = 0.0;
-    if (chain_lane) s_mu[warp][cq][0][cj] = 0.0;
+    if (chain_lane) mus[0] = 0.0;
+    if (vote_bins > 0) {
+#pragma unroll
+        for (int q = 0; q < kQ; q++)
+            for (int j = lane; j < kSmemLabelBins; j += 32) sm.h[q][j] = 0u;
+    }
     unsigned nmax = 0;
     int prev_m[kQ];
 #pragma unroll
     for (int q = 0; q < kQ; q++) { nmax = nn[q] > nmax ? nn[q] : nmax; prev_m[q] = 0; }
-    int buf = 0;
     bool prev_chk = false;                 // previous round produced a non-finite term: add with the NaN rule
     bool fin_mu = false, fin_acc = false;  // this lane's voxel is finished: its result is parked in mu_fin / acc_fin
     double mu_fin = 0.0, acc_fin = 0.0;    // (the straight-line rounds of the longer voxel keep clobbering mu / acc)
     T nx[kQ][3];                           // the next round's point of this lane (per voxel), fetched one round ahead
+    unsigned nl[kQ];                       // ... and its label
 #pragma unroll
     for (int q = 0; q < kQ; q++)
     {
-        nx[q][0] = nx[q][1] = nx[q][2] = 0;
-        if ((unsigned)lane < nn[q]) load_sorted<T>(pp[q] + lane * kSortedStride, nx[q][0], nx[q][1], nx[q][2]);
+        nx[q][0] = nx[q][1] = nx[q][2] = 0; nl[q] = 0;
+        if ((unsigned)lane < nn[q]) load_sorted_rec<T>(pp[q] + lane * kSortedStride, nx[q][0], nx[q][1], nx[q][2], nl[q]);
         if ((unsigned)lane + 32u < nn[q]) prefetch_l2(pp[q] + (size_t)(lane + 32) * kSortedStride);
         if ((unsigned)lane + 64u < nn[q]) prefetch_l2(pp[q] + (size_t)(lane + 64) * kSortedStride);
     }
 
     for (unsigned base = 0; base < nmax; base += 32) {
         int m[kQ];
-        double x[kQ][3];
 #pragma unroll
         for (int q = 0; q < kQ; q++) m[q] = base >= nn[q] ? 0 : (int)(nn[q] - base < 32u ? nn[q] - base : 32u);
         const double c = (double)(base + lane + 1);
@@ -546,16 +577,15 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
         rs[lane] = make_double2(rh, rl);
 #pragma unroll
         for (int q = 0; q < kQ; q++) {
-#pragma unroll
-            for (int j = 0; j < 3; j++) x[q][j] = (double)nx[q][j];
             if (lane < m[q]) {
 #pragma unroll
-                for (int j = 0; j < 3; j++) s_x[warp][q][lane][j] = make_double2(x[q][j], x[q][j] * rl);
+                for (int j = 0; j < 3; j++) sm.x[q][j][lane] = (double)nx[q][j];
+                if (vote_bins > 0 && nl[q] < (unsigned)vote_bins) atomicAdd(&sm.h[q][nl[q]], 1u);
             }
-            // a round lasts ~800 cycles, about one DRAM round trip: pull the records of the round after the next two into L2 now
+            // a round lasts about one DRAM round trip: pull the records of the round after the next two into L2 now
             if (base + 96 + lane < nn[q]) prefetch_l2(pp[q] + (size_t)(base + 96 + lane) * kSortedStride);
             if (base + 32 + lane < nn[q]) {      // issue the next round's global loads now; they land during phase A
-                load_sorted<T>(pp[q] + (size_t)(base + 32 + lane) * kSortedStride, nx[q][0], nx[q][1], nx[q][2]);
+                load_sorted_rec<T>(pp[q] + (size_t)(base + 32 + lane) * kSortedStride, nx[q][0], nx[q][1], nx[q][2], nl[q]);
             }
         }
         __syncwarp();
@@ -565,9 +595,6 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
         //      why the quotient is exact; the cancellation in t is harmless while |d| >= 2^-22 |x|).  Whether every
         //      operand of the round was inside the proven range is checked afterwards, in parallel, by phase B; if
         //      not, the round is redone with the IEEE division.
-        const double2(*xs)[3] = s_x[warp][cq];
-        double(*mus)[3] = s_mu[warp][cq];
-        const double(*tp)[6] = s_t[warp][buf ^ 1][aq];
         const double mu_start = mu;
         const int my_m = m[cq], my_pm = prev_m[aq];
         if (!fin_mu && m[cq] == 0) { fin_mu = true; mu_fin = mu; }
@@ -576,39 +603,41 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
 #pragma unroll
         for (int q = 0; q < kQ; q++) straight = straight && ((m[q] == 32 && prev_m[q] == 32) || (m[q] == 0 && prev_m[q] == 0));
         if (straight) {
-            // full rounds: straight-line, no per-step predicates, operands of the next four points are fetched
-            // while the current four are on the chain
-            double2 xv[4], rv[4], xn[4], rn[4];
-            double tv[4], tn[4];
+            // full rounds: straight-line, no per-step predicates; the operands of the next two points are fetched while
+            // the current two are on the chain
+            double xv[2], tv[2], xn[2], tn[2];
+            double2 rv[2], rn[2];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { xv[j] = xs[j][cj]; rv[j] = rs[j]; tv[j] = tp[j][at]; }
+            for (int j = 0; j < 2; j++) { xv[j] = xs[j]; rv[j] = rs[j]; tv[j] = tp[j]; }
 #pragma unroll
-            for (int k0 = 0; k0 < 32; k0 += 4) {
-                if (k0 + 4 < 32) {
+            for (int k0 = 0; k0 < 32; k0 += 2) {
+                if (k0 + 2 < 32) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { xn[j] = xs[k0 + 4 + j][cj]; rn[j] = rs[k0 + 4 + j]; tn[j] = tp[k0 + 4 + j][at]; }
+                    for (int j = 0; j < 2; j++) { xn[j] = xs[k0 + 2 + j]; rn[j] = rs[k0 + 2 + j]; tn[j] = tp[k0 + 2 + j]; }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const double d = xv[j].x - mu;
-                    const double t = fma(-mu, rv[j].y, xv[j].y);
+                for (int j = 0; j < 2; j++) {
+                    const double d = xv[j] - mu;
+                    const double t = fma(-mu, rv[j].y, xv[j] * rv[j].y);
                     mu = mu + fma(d, rv[j].x, t);
-                    if (chain_lane) mus[k0 + j + 1][cj] = mu;
+                    if (chain_lane) mus[k0 + j + 1] = mu;
                     acc += tv[j];
                 }
 #pragma unroll
-                for (int j = 0; j < 4; j++) { xv[j] = xn[j]; rv[j] = rn[j]; tv[j] = tn[j]; }
+                for (int j = 0; j < 2; j++) { xv[j] = xn[j]; rv[j] = rn[j]; tv[j] = tn[j]; }
             }
         } else {
             // first / last rounds of a voxel, or a round after non-finite terms: per-lane predicates
             for (int k = 0; k < 32; k++) {
                 if (k < my_m) {
-                    const double d = xs[k][cj].x - mu;
-                    mu = mu + fma(d, rs[k].x, fma(-mu, rs[k].y, xs[k][cj].y));
-                    if (chain_lane) mus[k + 1][cj] = mu;
+                    const double xk = xs[k];
+                    const double2 r = rs[k];
+                    const double d = xk - mu;
+                    mu = mu + fma(d, r.x, fma(-mu, r.y, xk * r.y));
+                    if (chain_lane) mus[k + 1] = mu;
                 }
                 if (k < my_pm) {
-                    const double a2 = acc + tp[k][at];
+                    const double a2 = acc + tp[k];
                     acc = (prev_chk && cov_lane && a2 != a2) ? 0.0 : a2;          // NaN -> 0 (normal_distributions.c:98-100)
                 }
             }
@@ -622,16 +651,16 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
             while (true) {
                 bool bad = false;
                 if (lane < m[q]) {
-                    const double(*mq)[3] = s_mu[warp][q];
-                    const double o0 = mq[lane][0], o1 = mq[lane][1], o2 = mq[lane][2];
-                    const double n0 = mq[lane + 1][0], n1 = mq[lane + 1][1], n2 = mq[lane + 1][2];
-                    const double x0 = x[q][0], x1 = x[q][1], x2 = x[q][2];
+                    const double(*mq)[33] = sm.mu[q];
+                    const double o0 = mq[0][lane], o1 = mq[1][lane], o2 = mq[2][lane];
+                    const double n0 = mq[0][lane + 1], n1 = mq[1][lane + 1], n2 = mq[2][lane + 1];
+                    const double x0 = sm.x[q][0][lane], x1 = sm.x[q][1][lane], x2 = sm.x[q][2][lane];
                     const double d0 = x0 - o0, d1 = x1 - o1, d2 = x2 - o2;          // the chain's d, bit for bit
                     const double a0 = fabs(d0), a1 = fabs(d1), a2 = fabs(d2);
                     bad = !(a0 > 1e-250 && a0 < 1e290 && a0 * 4194304.0 >= fabs(x0)) ||
                           !(a1 > 1e-250 && a1 < 1e290 && a1 * 4194304.0 >= fabs(x1)) ||
                           !(a2 > 1e-250 && a2 < 1e290 && a2 * 4194304.0 >= fabs(x2));
-                    double(*t)[6] = s_t[warp][buf][q];
+                    double(*t)[33] = sm.t[q];
                     const double e0 = x0 - n0, e1 = x1 - n1;
                     const double t0 = d0 * e0, t1 = d1 * e1, t2 = d2 * (x2 - n2);
                     // (x_j - new_j)(x_k - old_k) / count: mu_k (k > j) is not yet updated when dimension j runs
@@ -642,7 +671,7 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
                         const bool ok = b0 > 1e-250 && b0 < 1e290 && b1 > 1e-250 && b1 < 1e290 && b2 > 1e-250 && b2 < 1e290;
                         if (!ok) { q01 = p01 / c; q02 = p02 / c; q12 = p12 / c; }     // zeros, tiny or huge products: IEEE division
                     }
-                    t[lane][0] = t0; t[lane][1] = t1; t[lane][2] = t2; t[lane][3] = q01; t[lane][4] = q02; t[lane][5] = q12;
+                    t[0][lane] = t0; t[1][lane] = t1; t[2][lane] = t2; t[3][lane] = q01; t[4][lane] = q02; t[5][lane] = q12;
                     const double big = 1.7976931348623157e308;
                     nonfinite |= !(fabs(t0) <= big && fabs(t1) <= big && fabs(t2) <= big && fabs(q01) <= big && fabs(q02) <= big && fabs(q12) <= big);
                 }
@@ -652,8 +681,8 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
                     mu = mu_start;
                     for (int k = 0; k < m[q]; k++) {
                         const double cnt = (double)(base + k + 1);
-                        mu = mu + (s_x[warp][q][k][cj].x - mu) / cnt;
-                        s_mu[warp][q][k + 1][cj] = mu;
+                        mu = mu + (xs[k] - mu) / cnt;
+                        mus[k + 1] = mu;
                     }
                 }
                 redone = true;
@@ -662,17 +691,15 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
         }
         prev_chk = __any_sync(0xffffffffu, nonfinite);
         __syncwarp();
-        if (chain_lane && my_m > 0) s_mu[warp][cq][0][cj] = s_mu[warp][cq][my_m][cj];
+        if (chain_lane && my_m > 0) mus[0] = mus[my_m];
 #pragma unroll
         for (int q = 0; q < kQ; q++) prev_m[q] = m[q];
-        buf ^= 1;
         __syncwarp();
     }
     {   // C for the last round of each voxel (a shorter voxel's last terms were already added: its prev_m became 0)
-        const double(*tp)[6] = s_t[warp][buf ^ 1][aq];
         const int my_pm = prev_m[aq];
         for (int k = 0; k < my_pm; k++) {
-            const double a2 = acc + tp[k][at];
+            const double a2 = acc + tp[k];
             acc = (cov_lane && a2 != a2) ? 0.0 : a2;
         }
     }
@@ -689,11 +716,14 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
         const double v0 = __shfl_sync(0xffffffffu, out, q * 6 + 0), v1 = __shfl_sync(0xffffffffu, out, q * 6 + 1), v2 = __shfl_sync(0xffffffffu, out, q * 6 + 2);
         const double c01 = __shfl_sync(0xffffffffu, out, q * 6 + 3), c02 = __shfl_sync(0xffffffffu, out, q * 6 + 4), c12 = __shfl_sync(0xffffffffu, out, q * 6 + 5);
         const double m0 = __shfl_sync(0xffffffffu, mu, q * 3 + 0), m1 = __shfl_sync(0xffffffffu, mu, q * 3 + 1), m2 = __shfl_sync(0xffffffffu, mu, q * 3 + 2);
+        unsigned label = 0;
+        if (vote_bins > 0) label = vote_from_hist(sm.h[q], vote_bins, lane);
         if (lane == 0) {
             double *mo = mean + ((size_t)b * vcap + vv[q]) * 3;
             mo[0] = m0; mo[1] = m1; mo[2] = m2;
             double *co = cov + ((size_t)b * vcap + vv[q]) * 9;
             co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
+            if (vote_bins > 0) cls[(size_t)b * vcap + vv[q]] = (uint16_t)label;
         }
     }
 }
@@ -701,17 +731,46 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
 // Statistics of the light voxels (fewer than kHeavyVoxel points: about 1040 of a scan's 1060 voxels, half of its
 // points): one THREAD per voxel runs the literal recurrence of normal_distributions.c:76-104, so a warp advances 32
 // voxels per instruction instead of one.  vox_order is bucketed by size, so the voxels of a warp have similar
-// lengths.  The divisions by the running count share one reciprocal per point (see div_by_count).
-// grid (ceil(vcap/128), B), block 128.
+// lengths.  The divisions by the running count share one reciprocal pair per count, tabulated once per CTA (every thread
+// of a warp is at the same count; see div_by_count for why the reciprocal form is the correctly rounded quotient).
+// vote_bins > 0: the label vote (normal_distributions.c:107-121) is taken here too, in per-thread 16-bit counters.
+// grid (ceil(vcap/128), B), block 128, dynamic smem vote_bins * 128 * 2 bytes.
+__device__ __forceinline__ bool in_recip_range(double u) {
+    // 2^-830 <= |u| < 2^963: inside the range (1e-250, 1e290) for which div_by_count's reciprocal form is proven
+    const unsigned h = (unsigned)__double2hiint(u) & 0x7fffffffu;
+    return h - 0x0C100000u < 0x70100000u;
+}
+__device__ __forceinline__ bool exp_all_ones(double u) { return ((unsigned)__double2hiint(u) & 0x7ff00000u) == 0x7ff00000u; }
+
 template <typename T>
 __global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restrict__ states, unsigned vcap, long N,
                                                      const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                                      const unsigned *__restrict__ vox_order,
-                                                     double *__restrict__ mean, double *__restrict__ cov) {
+                                                     double *__restrict__ mean, double *__restrict__ cov,
+                                                     uint16_t *__restrict__ cls, int vote_bins) {
+    extern __shared__ unsigned short s_votes[];          // [vote_bins][128]
+    __shared__ double2 s_rc[kHeavyVoxel];                // {rh, rl} ~ 1 / (k + 1)
     const int b = blockIdx.y;
     const CloudState &s = states[b];
     if (s.status != 0) return;
-    const unsigned idx = s.n_heavy + blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned first = s.n_heavy + blockIdx.x * blockDim.x;
+    if (first >= s.V) return;
+    const int tid = threadIdx.x;
+    {
+        // vox_order lists the voxels heaviest bucket first, so the first voxel of the CTA bounds every count it will see
+        const unsigned v0 = vox_order[(size_t)b * vcap + first];
+        const unsigned n0 = vox_start[(size_t)b * (vcap + 1) + v0 + 1] - vox_start[(size_t)b * (vcap + 1) + v0];
+        unsigned bound = 1u << (32 - __clz(n0 | 1u));                       // counts of this bucket are < bound
+        if (bound > kHeavyVoxel) bound = kHeavyVoxel;
+        for (unsigned k = tid; k < bound; k += blockDim.x) {
+            const double c = (double)(k + 1);
+            const double rh = 1.0 / c;
+            s_rc[k] = make_double2(rh, fma(-c, rh, 1.0) * rh);
+        }
+        for (int j = 0; j < vote_bins; j++) s_votes[j * 128 + tid] = 0;
+    }
+    __syncthreads();
+    const unsigned idx = first + tid;
     if (idx >= s.V) return;
     const unsigned v = vox_order[(size_t)b * vcap + idx];
     const unsigned st = vox_start[(size_t)b * (vcap + 1) + v], en = vox_start[(size_t)b * (vcap + 1) + v + 1];
@@ -719,32 +778,35 @@ __global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restric
     double mu0 = 0, mu1 = 0, mu2 = 0, m20 = 0, m21 = 0, m22 = 0, c01 = 0, c02 = 0, c12 = 0;
     const unsigned n = en - st;
     T a0 = 0, a1 = 0, a2 = 0;
-    if (n > 0) load_sorted<T>(p, a0, a1, a2);
+    unsigned lab = 0;
+    if (n > 0) load_sorted_rec<T>(p, a0, a1, a2, lab);
     for (unsigned k = 0; k < n; k++) {
         const double x0 = (double)a0, x1 = (double)a1, x2 = (double)a2;
-        if (k + 1 < n) load_sorted<T>(p + (size_t)(k + 1) * kSortedStride, a0, a1, a2);   // overlaps this point's chain
-        const double c = (double)(k + 1);
-        const double rh = 1.0 / c;
-        const double rl = fma(-c, rh, 1.0) * rh;
+        if (vote_bins > 0 && lab < (unsigned)vote_bins) s_votes[lab * 128 + tid]++;
+        if ((k & 7u) == 0 && k + 8 < n) prefetch_l2(p + (size_t)(k + 8) * kSortedStride);   // the next 128-byte line of this voxel
+        if (k + 1 < n) load_sorted_rec<T>(p + (size_t)(k + 1) * kSortedStride, a0, a1, a2, lab);   // overlaps this point's chain
+        const double2 r = s_rc[k];
+        const double rh = r.x, rl = r.y;
         // RN(u / c): reciprocal form inside its proven range, IEEE division otherwise
-#define QDIV(u) ((fabs(u) > 1e-250 && fabs(u) < 1e290) ? fma((u), rh, (u) * rl) : (u) / c)
+#define QDIV(u) (in_recip_range(u) ? fma((u), rh, (u) * rl) : (u) / (double)(k + 1))
         // j = 0
         const double d0 = x0 - mu0;
         const double o0 = mu0;
         mu0 = mu0 + QDIV(d0);
-        m20 += (x0 - o0) * (x0 - mu0);
-        { const double u = (x0 - mu0) * (x1 - mu1); c01 += QDIV(u); if (c01 != c01) c01 = 0.0; }   // mu1, mu2 still old
-        { const double u = (x0 - mu0) * (x2 - mu2); c02 += QDIV(u); if (c02 != c02) c02 = 0.0; }
+        const double e0 = x0 - mu0;
+        m20 += (x0 - o0) * e0;
+        const double f1 = x1 - mu1, f2 = x2 - mu2;                                                  // mu1, mu2 still old
+        { const double u = e0 * f1; c01 += QDIV(u); if (exp_all_ones(c01) && c01 != c01) c01 = 0.0; }
+        { const double u = e0 * f2; c02 += QDIV(u); if (exp_all_ones(c02) && c02 != c02) c02 = 0.0; }
         // j = 1
-        const double d1 = x1 - mu1;
         const double o1 = mu1;
-        mu1 = mu1 + QDIV(d1);
-        m21 += (x1 - o1) * (x1 - mu1);
-        { const double u = (x1 - mu1) * (x2 - mu2); c12 += QDIV(u); if (c12 != c12) c12 = 0.0; }
+        mu1 = mu1 + QDIV(f1);
+        const double e1 = x1 - mu1;
+        m21 += (x1 - o1) * e1;
+        { const double u = e1 * f2; c12 += QDIV(u); if (exp_all_ones(c12) && c12 != c12) c12 = 0.0; }
         // j = 2
-        const double d2 = x2 - mu2;
         const double o2 = mu2;
-        mu2 = mu2 + QDIV(d2);
+        mu2 = mu2 + QDIV(f2);
         m22 += (x2 - o2) * (x2 - mu2);
 #undef QDIV
     }
@@ -757,6 +819,11 @@ __global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restric
     mo[0] = mu0; mo[1] = mu1; mo[2] = mu2;
     double *co = cov + ((size_t)b * vcap + v) * 9;
     co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
+    if (vote_bins > 0) {
+        unsigned best = 0, bc = 0;
+        for (int j = 0; j < vote_bins; j++) { const unsigned x = s_votes[j * 128 + tid]; if (x > best) { best = x; bc = (unsigned)j; } }
+        cls[(size_t)b * vcap + v] = (uint16_t)(best > 0 ? bc : 0u);
+    }
 }
 
 // Label vote (normal_distributions.c:107-121): most frequent class of the voxel, lowest index on ties.  One warp
@@ -1267,14 +1334,25 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         CK(cudaEventRecord(w.ev_fork, st));
         CK(cudaStreamWaitEvent(w.side, w.ev_fork, 0));
         const unsigned max_pairs = (max_heavy + kQ - 1) / kQ;
-        k_stats<T><<<dim3(B, (max_pairs + kStatsWarps - 1) / kStatsWarps), 32 * kStatsWarps, 0, st>>>(
-            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov);
+        // label vote: taken inside the statistics kernels from the label lane of the records they read anyway when the
+        // class count fits their shared-memory counters; wide label sets were counted by k_scatter's global atomics
+        const int vote_bins = labels && !wide_labels ? nbins : 0;
+        constexpr size_t stats_smem = sizeof(StatsWarpSmem) * kStatsWarps;
+        {
+            static bool attr_set[64] = {};   // function attributes are per device
+            int dev = 0; cudaGetDevice(&dev);
+            if (!attr_set[dev & 63]) {
+                CK(cudaFuncSetAttribute(k_stats<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_smem));
+                attr_set[dev & 63] = true;
+            }
+        }
+        k_stats<T><<<dim3(B, (max_pairs + kStatsWarps - 1) / kStatsWarps), 32 * kStatsWarps, stats_smem, st>>>(
+            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
         DBG("k_stats");
-        k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, 0, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start,
-                                                                         w.vox_order, w.mean, w.cov);
-        if (labels) {
-            k_votes<T><<<dim3(B, (vcap + 3) / 4), 128, 0, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start,
-                                                                wide_labels ? w.hist : nullptr, nbins, w.cls);
+        k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, (size_t)vote_bins * 128 * sizeof(unsigned short), w.side>>>(
+            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
+        if (wide_labels) {
+            k_votes<T><<<dim3(B, (vcap + 3) / 4), 128, 0, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.hist, nbins, w.cls);
         }
         CK(cudaEventRecord(w.ev_join, w.side));
         CK(cudaStreamWaitEvent(st, w.ev_join, 0));
@@ -1302,7 +1380,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     }
     DBG("end");
     tm.mark(ST_COUNT, st);
-    count_launches(3 + 2 * kMaxGuessIterations + (N > 0 ? 2 : 0) + 5 + (labels ? 1 : 0));
+    count_launches(3 + 2 * kMaxGuessIterations + (N > 0 ? 2 : 0) + 5 + (wide_labels ? 1 : 0));
     if (tm.enabled) {
         CK(cudaEventSynchronize(tm.ev[ST_COUNT]));
         for (int i = 0; i < ST_COUNT; i++) { float ms = 0; cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]); tm.ms[i] += ms; }
