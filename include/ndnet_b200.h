@@ -74,6 +74,8 @@ typedef struct ndnet_b200_ctx ndnet_b200_ctx;
 
 /* flags for ndnet_b200_downsample_batch */
 #define NDNET_B200_NAN_TO_NUM 1u /* NaN/+-inf -> 0 in the f32 features (ndtnet_preprocessing.py:66-69) */
+#define NDNET_B200_LABELS_U8 2u  /* `labels` holds one BYTE per point instead of the reference's uint16 (num_classes <= 255):
+                                    fewer bytes to move when the scans come from the host */
 
 /* Per-cloud record written by ndnet_b200_downsample_batch (device memory, one per cloud). */
 typedef struct ndnet_b200_cloud_info {
@@ -187,6 +189,10 @@ long ndnet_b200_model_tap(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const ch
 int ndnet_b200_infer_host(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const void *points, int dtype,
                           const uint16_t *labels, int B, long N, int num_classes, long num_desired, float *out_host,
                           long out_elems_per_cloud, void *stream);
+/* Same with one byte per point label (13 instead of 14 bytes per point cross PCIe; num_classes <= 255). */
+int ndnet_b200_infer_host_u8(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const void *points, int dtype,
+                             const uint8_t *labels, int B, long N, int num_classes, long num_desired, float *out_host,
+                             long out_elems_per_cloud, void *stream);
 /* Same with DEVICE buffers in and out, asynchronous (the caller's stream waits for the result). */
 int ndnet_b200_infer_device(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const void *points, int dtype,
                             const uint16_t *labels, int B, long N, int num_classes, long num_desired, float *out_dev,

@@ -237,6 +237,7 @@ extern "C" int ndnet_b200_downsample_batch(ndnet_b200_ctx *c, const void *points
                                            double *out_feat64, uint16_t *out_labels, int32_t *out_voxel,
                                            ndnet_b200_cloud_info *info, void *stream) {
     if (!c || !points || B <= 0 || N < 0 || D <= 0 || (dtype != 0 && dtype != 1) || num_classes < 0) return -200;
+    if ((flags & NDNET_B200_LABELS_U8) && num_classes > 255) return -200;
     cudaError_t e = cudaSetDevice(c->device);
     if (e != cudaSuccess) return fail(c, e, "cudaSetDevice");
     e = c->ws.reserve(B, N, D, num_classes + 1);
@@ -260,7 +261,8 @@ extern "C" int ndnet_b200_downsample_batch_host(ndnet_b200_ctx *c, const void *p
     const size_t pbytes = (size_t)B * N * 3 * esz;
 #define G(ptr, have, need) if ((e = grow(ptr, have, need)) != cudaSuccess) return fail(c, e, "staging allocation")
     G(c->d_points, c->d_points_bytes, pbytes);
-    if (labels) G(c->d_labels, c->d_labels_bytes, (size_t)B * N * 2);
+    const size_t lsz = (flags & NDNET_B200_LABELS_U8) ? 1 : 2;
+    if (labels) G(c->d_labels, c->d_labels_bytes, (size_t)B * N * lsz);
     if (out_feat) G(c->d_feat, c->d_feat_bytes, (size_t)B * D * 12 * 4);
     if (out_feat64) G(c->d_feat64, c->d_feat64_bytes, (size_t)B * D * 12 * 8);
     if (out_labels) G(c->d_olab, c->d_olab_bytes, (size_t)B * D * 2);
@@ -268,7 +270,7 @@ extern "C" int ndnet_b200_downsample_batch_host(ndnet_b200_ctx *c, const void *p
     if (info) G(c->d_info, c->d_info_bytes, (size_t)B * sizeof(NdtCloudInfo));
 #undef G
     if ((e = cudaMemcpyAsync(c->d_points, points, pbytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(c, e, "H2D points");
-    if (labels && (e = cudaMemcpyAsync(c->d_labels, labels, (size_t)B * N * 2, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    if (labels && (e = cudaMemcpyAsync(c->d_labels, labels, (size_t)B * N * lsz, cudaMemcpyHostToDevice, st)) != cudaSuccess)
         return fail(c, e, "H2D labels");
     int r = ndnet_b200_downsample_batch(c, c->d_points, dtype, labels ? c->d_labels : nullptr, B, N, num_classes, D, flags,
                                         out_feat ? c->d_feat : nullptr, out_feat64 ? c->d_feat64 : nullptr,
@@ -302,7 +304,8 @@ extern "C" int ndnet_b200_set_device_chunk(ndnet_b200_ctx *c, int chunk) {
 
 static int infer_pipelined(ndnet_b200_ctx *c, ndnet_b200_model *model, const void *points, int dtype, const uint16_t *labels,
                            int B, long N, int num_classes, long D, float *out, long out_elems_per_cloud, cudaStream_t user,
-                           bool host_io) {
+                           bool host_io, unsigned label_flags = 0) {
+    const size_t lsz = (label_flags & NDNET_B200_LABELS_U8) ? 1 : 2;      // bytes per point label
     cudaError_t e = cudaSetDevice(c->device);
     if (e != cudaSuccess) return fail(c, e, "cudaSetDevice");
     if (c->lanes.empty()) {
@@ -327,21 +330,21 @@ static int infer_pipelined(ndnet_b200_ctx *c, ndnet_b200_model *model, const voi
         ndnet_b200_ctx::Lane &l = c->lanes[lane_i];
         if ((e = cudaStreamWaitEvent(l.stream, c->start_ev, 0)) != cudaSuccess) return fail(c, e, "stream wait");
         const char *psrc = (const char *)points + (size_t)b0 * N * 3 * esz;
-        const uint16_t *lsrc = labels ? labels + (size_t)b0 * N : nullptr;
+        const uint16_t *lsrc = labels ? (const uint16_t *)((const char *)labels + (size_t)b0 * N * lsz) : nullptr;
         float *odst = out + (size_t)b0 * out_elems_per_cloud;
         const void *dp = psrc; const uint16_t *dl = lsrc; float *dout = odst;
         if ((e = grow(l.d_feat, l.d_feat_bytes, (size_t)nb * D * 12 * 4)) != cudaSuccess) return fail(c, e, "lane allocation");
         if (host_io) {
             if ((e = grow(l.d_points, l.d_points_bytes, (size_t)nb * N * 3 * esz)) != cudaSuccess) return fail(c, e, "lane allocation");
-            if (labels && (e = grow(l.d_labels, l.d_labels_bytes, (size_t)nb * N * 2)) != cudaSuccess) return fail(c, e, "lane allocation");
+            if (labels && (e = grow(l.d_labels, l.d_labels_bytes, (size_t)nb * N * lsz)) != cudaSuccess) return fail(c, e, "lane allocation");
             if ((e = grow(l.d_logits, l.d_logits_bytes, (size_t)nb * out_elems_per_cloud * 4)) != cudaSuccess) return fail(c, e, "lane allocation");
             if ((e = cudaMemcpyAsync(l.d_points, psrc, (size_t)nb * N * 3 * esz, cudaMemcpyHostToDevice, l.stream)) != cudaSuccess) return fail(c, e, "H2D points");
-            if (labels && (e = cudaMemcpyAsync(l.d_labels, lsrc, (size_t)nb * N * 2, cudaMemcpyHostToDevice, l.stream)) != cudaSuccess) return fail(c, e, "H2D labels");
+            if (labels && (e = cudaMemcpyAsync(l.d_labels, lsrc, (size_t)nb * N * lsz, cudaMemcpyHostToDevice, l.stream)) != cudaSuccess) return fail(c, e, "H2D labels");
             dp = l.d_points; dl = labels ? l.d_labels : nullptr; dout = l.d_logits;
         }
         if ((e = l.ws.reserve(nb, N, D, num_classes + 1)) != cudaSuccess) return fail(c, e, "lane workspace allocation");
         l.ws.last_B = nb; l.ws.last_N = N; l.ws.last_D = D;
-        if ((e = ndt::run_batch(l.ws, dp, dtype, dl, nb, N, num_classes, D, NDNET_B200_NAN_TO_NUM, l.d_feat, nullptr, nullptr, nullptr,
+        if ((e = ndt::run_batch(l.ws, dp, dtype, dl, nb, N, num_classes, D, NDNET_B200_NAN_TO_NUM | label_flags, l.d_feat, nullptr, nullptr, nullptr,
                                 nullptr, l.stream)) != cudaSuccess) return fail(c, e, "ndt::run_batch");
         std::string err;
         int r = model->m.forward(l.scratch, l.d_feat, nb, (int)D, dout, l.stream, err);
@@ -364,6 +367,15 @@ extern "C" int ndnet_b200_infer_host(ndnet_b200_ctx *c, ndnet_b200_model *model,
                                      long out_elems_per_cloud, void *stream) {
     if (!c || !model || !points || !out_host || B <= 0 || N < 0 || D <= 0 || (dtype != 0 && dtype != 1)) return -200;
     return infer_pipelined(c, model, points, dtype, labels, B, N, num_classes, D, out_host, out_elems_per_cloud, (cudaStream_t)stream, true);
+}
+
+// The same call with one BYTE per point label (num_classes <= 255): 13 instead of 14 bytes per point cross PCIe.
+extern "C" int ndnet_b200_infer_host_u8(ndnet_b200_ctx *c, ndnet_b200_model *model, const void *points, int dtype,
+                                        const uint8_t *labels, int B, long N, int num_classes, long D, float *out_host,
+                                        long out_elems_per_cloud, void *stream) {
+    if (!c || !model || !points || !out_host || B <= 0 || N < 0 || D <= 0 || (dtype != 0 && dtype != 1) || num_classes > 255) return -200;
+    return infer_pipelined(c, model, points, dtype, (const uint16_t *)labels, B, N, num_classes, D, out_host, out_elems_per_cloud,
+                           (cudaStream_t)stream, true, NDNET_B200_LABELS_U8);
 }
 
 // Same from/to DEVICE buffers; asynchronous: on return the caller's stream waits for the result.

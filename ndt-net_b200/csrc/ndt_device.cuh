@@ -20,8 +20,9 @@ constexpr int kWorkers = 8;                 // normal_distributions.h:39
 constexpr int kDirs = 6;                    // voxel.h:35-43  X+,X-,Y+,Y-,Z+,Z-
 
 constexpr unsigned kMaxGridCells = 1u << 25;   // cells per cloud the bitmap workspace can hold
-constexpr unsigned kSmemBitmapBits = 1u << 18; // grids up to this many cells are counted in shared memory
+constexpr unsigned kSmemBitmapBits = 1u << 17; // grids up to this many cells are counted in shared memory (16 KB: 8 CTAs of k_count per SM)
 constexpr int kCountPointsPerCta = 4096;
+constexpr int kCountCtasPerCloud = 8;          // CTAs of k_count per cloud (each walks N / 8 consecutive points)
 constexpr int kRankTile = 2048;                // points per rank tile (one warp walks one tile in order)
 constexpr unsigned kDropped = 0xFFFFFFFFu;
 constexpr int kLimWords = 8;                   // per cloud: encoded max x,y,z, min x,y,z, NaN-seen flag, (pad)
@@ -92,6 +93,9 @@ __device__ __forceinline__ GridCtx make_grid_ctx(const CloudState &s) {
     g.vs = s.guess; g.rv = 1.0 / s.guess; g.rv32 = (float)g.rv;
 #pragma unroll
     for (int a = 0; a < 3; a++) { g.off[a] = s.off[a]; g.len[a] = s.len[a]; g.off32[a] = (float)s.off[a]; }
+    // keep the fp32 copies in registers: left alone, the compiler re-converts the doubles at every use, and F2F issues on
+    // the quarter-rate XU pipe (two per point in k_count's inner loop)
+    asm volatile("" : "+f"(g.off32[0]), "+f"(g.off32[1]), "+f"(g.off32[2]), "+f"(g.rv32));
     return g;
 }
 

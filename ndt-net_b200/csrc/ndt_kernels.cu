@@ -35,28 +35,56 @@ namespace ndt {
 // ------------------------------------------------------------------------------------------------
 // K1  bounding box (pointclouds.c:40-66).  grid (chunks, B), block 256.
 // ------------------------------------------------------------------------------------------------
+template <typename T> struct LimAcc {
+    T mx[3], mn[3];
+    bool nan;
+    __device__ __forceinline__ void init() { nan = false; for (int a = 0; a < 3; a++) { mx[a] = -INFINITY; mn[a] = INFINITY; } }
+    __device__ __forceinline__ void add(int a, T v) {
+        nan = nan || v != v;
+        mx[a] = v > mx[a] ? v : mx[a];          // NaN never wins a comparison (a NaN cloud is refused anyway)
+        mn[a] = v < mn[a] ? v : mn[a];
+    }
+};
+
+// whether cloud b of a [B][N][3] fp32 array starts on a 16-byte boundary (then 4 points = 3 aligned float4)
+template <typename T> __device__ __forceinline__ bool cloud_vectorizable(const T *) { return false; }
+template <> __device__ __forceinline__ bool cloud_vectorizable<float>(const float *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// four consecutive points with three coalesced 16-byte loads (p: the 16-byte aligned first coordinate of the group)
+__device__ __forceinline__ void load_points4(const float *p, float x[4], float y[4], float z[4]) {
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    const float4 a = q[0], b = q[1], c = q[2];
+    x[0] = a.x; y[0] = a.y; z[0] = a.z; x[1] = a.w; y[1] = b.x; z[1] = b.y;
+    x[2] = b.z; y[2] = b.w; z[2] = c.x; x[3] = c.y; y[3] = c.z; z[3] = c.w;
+}
+__device__ __forceinline__ void load_points4(const double *, double *, double *, double *) {}   // never taken (cloud_vectorizable<double> is false)
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_limits(const T *__restrict__ pts, long N, unsigned long long *__restrict__ lim_enc) {
     const int b = blockIdx.y;
     const T *p = pts + (size_t)b * N * 3;
-    T mx[3], mn[3];
-    bool any = false, nan = false;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long)gridDim.x * blockDim.x) {
-        const T x = p[i * 3 + 0], y = p[i * 3 + 1], z = p[i * 3 + 2];
-        nan = nan || x != x || y != y || z != z;
-        if (!any) { mx[0] = mn[0] = x; mx[1] = mn[1] = y; mx[2] = mn[2] = z; any = true; }
-        else {
-            mx[0] = x > mx[0] ? x : mx[0]; mn[0] = x < mn[0] ? x : mn[0];
-            mx[1] = y > mx[1] ? y : mx[1]; mn[1] = y < mn[1] ? y : mn[1];
-            mx[2] = z > mx[2] ? z : mx[2]; mn[2] = z < mn[2] ? z : mn[2];
+    LimAcc<T> acc;
+    acc.init();
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long)gridDim.x * blockDim.x;
+    if (cloud_vectorizable<T>(p)) {
+        const long groups = N / 4;
+        for (long g = tid; g < groups; g += nthreads) {
+            T x[4], y[4], z[4];
+            load_points4(p + g * 12, x, y, z);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { acc.add(0, x[k]); acc.add(1, y[k]); acc.add(2, z[k]); }
         }
+        for (long i = groups * 4 + tid; i < N; i += nthreads) { acc.add(0, p[i * 3 + 0]); acc.add(1, p[i * 3 + 1]); acc.add(2, p[i * 3 + 2]); }
+    } else {
+        for (long i = tid; i < N; i += nthreads) { acc.add(0, p[i * 3 + 0]); acc.add(1, p[i * 3 + 1]); acc.add(2, p[i * 3 + 2]); }
     }
-    // warp reduce through the order-preserving encoding, then one atomic per warp
+    // warp reduce through the order-preserving encoding, then one atomic per warp (the +-inf of a thread that saw no
+    // point is the identity of the reduction)
     unsigned long long e[6];
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        e[a] = any ? enc_f64((double)mx[a]) : 0ull;
-        e[3 + a] = any ? enc_f64((double)mn[a]) : ~0ull;
+        e[a] = enc_f64((double)acc.mx[a]);
+        e[3 + a] = enc_f64((double)acc.mn[a]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -77,7 +105,7 @@ __global__ void __launch_bounds__(256) k_limits(const T *__restrict__ pts, long 
     }
     // a NaN coordinate is refused (status -5): the reference converts floor(NaN) to unsigned, which is undefined
     // behaviour in C (voxel.c:89-91); silently voxelising such a point anywhere would not be parity with anything
-    if (__any_sync(0xffffffffu, nan) && (threadIdx.x & 31) == 0) lim_enc[b * kLimWords + 6] = 1ull;
+    if (__any_sync(0xffffffffu, acc.nan) && (threadIdx.x & 31) == 0) lim_enc[b * kLimWords + 6] = 1ull;
 }
 
 // grid + risk flag for a guess (voxel.c:61-81); returns false when the grid cannot be held
@@ -101,6 +129,21 @@ __device__ bool set_grid(CloudState &s) {
     s.nwords = (s.G + 31u) >> 5;
     s.risky = risky ? 1 : 0;
     return true;
+}
+
+// A grid with fewer cells than D cannot hold D occupied voxels: whatever the points are, the pass would count
+// num_nds <= G < D and take the branch of ndt.c:171 (hi = guess).  Take it without reading the points; the evaluation
+// still counts (the reference runs it), so `evaluations` and the 15-guess limit are unchanged.  A degenerate axis
+// (G == 0, A3) goes the same way down to -3.
+__device__ void skip_small_grids(CloudState &s, unsigned long D) {
+    while (s.status == 1 && (unsigned long)s.G < D) {
+        s.evals++;
+        s.hi = s.guess;                                                                                    // ndt.c:171
+        s.guess = s.lo + (s.hi - s.lo) / 2.0;                                                              // ndt.c:183
+        s.iter++;
+        if (s.iter >= kMaxGuessIterations) { s.status = -3; break; }                                       // ndt.c:187-194
+        if (!set_grid(s)) { s.status = -1; break; }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -136,6 +179,7 @@ __global__ void __launch_bounds__(256) k_decide(CloudState *__restrict__ states,
             s.status = 1;
             if (!set_grid(s)) { s.status = -1; s.G = 0; s.nwords = 0; }
             if (lim_enc[b * kLimWords + 6]) { s.status = kStatusNaNInput; s.G = 0; s.nwords = 0; }
+            skip_small_grids(s, (unsigned long)num_desired);
             s_action = s.status == 1 ? 1 : 0;
         }
         __syncthreads();
@@ -165,6 +209,7 @@ __global__ void __launch_bounds__(256) k_decide(CloudState *__restrict__ states,
                 else {
                     for (int w = 0; w < kWorkers; w++) s.fail[w] = kDropped;
                     if (!set_grid(s)) { s.status = -1; s_action = 0; }
+                    else { skip_small_grids(s, D); if (s.status != 1) s_action = 0; }
                 }
             }
         }
@@ -221,12 +266,58 @@ __device__ __forceinline__ void load_point(const T *p, long i, double &x, double
     x = (double)p[i * 3 + 0]; y = (double)p[i * 3 + 1]; z = (double)p[i * 3 + 2];
 }
 
+// cell id of an fp32 point of a NON-risky grid: the fp32 prefilter per axis, the exact fp64 path (out of line) for the
+// ~1e-5 of the points it does not decide.  No bound test: floor((p - off) / vs) < ceil((max - min) / vs) for every
+// p <= max when that quotient is not an integer, which is what "not risky" means (set_grid).
+static __device__ __noinline__ unsigned cell_id_exact(float x, float y, float z, const GridCtx &g) {
+    const unsigned vx = axis_cell((double)x, g.off[0], g.vs, g.rv), vy = axis_cell((double)y, g.off[1], g.vs, g.rv),
+                   vz = axis_cell((double)z, g.off[2], g.vs, g.rv);
+    return vz * (unsigned)g.len[0] * (unsigned)g.len[1] + vy * (unsigned)g.len[0] + vx;
+}
+__device__ __forceinline__ unsigned cell_id_fast(float x, float y, float z, const GridCtx &g, unsigned lxly) {
+    unsigned vx, vy, vz;
+    const bool ok = cell_prefilter32(x, g.off32[0], g.rv32, vx) & cell_prefilter32(y, g.off32[1], g.rv32, vy) &
+                    cell_prefilter32(z, g.off32[2], g.rv32, vz);
+    if (ok) return vz * lxly + vy * (unsigned)g.len[0] + vx;
+    return cell_id_exact(x, y, z, g);
+}
+
+// marks the cells of the points [begin, end) of a non-risky grid in the CTA's shared-memory bitmap (kSmem) or straight in
+// the global one.  Test before set: only ~V of the G cells are occupied, so after the first few hundred points of the CTA
+// nearly every bit is already there and the (serialising) atomic is skipped.
+template <typename T, bool kSmem>
+__device__ __forceinline__ void count_span(const T *__restrict__ p, long begin, long end, const GridCtx &gc, unsigned *s_bits, uint2 *bm) {
+    auto mark = [&](unsigned id) {
+        if (kSmem) { if (!((s_bits[id >> 5] >> (id & 31)) & 1u)) atomicOr(&s_bits[id >> 5], 1u << (id & 31)); }
+        else if (!((bm[id >> 5].x >> (id & 31)) & 1u)) atomicOr(&bm[id >> 5].x, 1u << (id & 31));
+    };
+    if (cloud_vectorizable<T>(p)) {
+        const unsigned lxly = (unsigned)gc.len[0] * (unsigned)gc.len[1];
+        const long vend = begin + (end - begin) / 4 * 4;
+        for (long i = begin + threadIdx.x * 4; i < vend; i += blockDim.x * 4) {
+            T x[4], y[4], z[4];
+            load_points4(p + i * 3, x, y, z);
+#pragma unroll
+            for (int k = 0; k < 4; k++) mark(cell_id_fast((float)x[k], (float)y[k], (float)z[k], gc, lxly));
+        }
+        for (long i = vend + threadIdx.x; i < end; i += blockDim.x) {
+            unsigned id;
+            if (point_cell<T>(p, i, gc, id)) mark(id);
+        }
+    } else {
+        for (long i = begin + threadIdx.x; i < end; i += blockDim.x) {
+            unsigned id;
+            if (point_cell<T>(p, i, gc, id)) mark(id);
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N, CloudState *__restrict__ states,
                                                uint2 *__restrict__ bitmap, size_t bitmap_stride) {
     const int b = blockIdx.y;
     CloudState &s = states[b];
-    if (s.status != 1) return;
+    if (s.status != 1) return;                           // converged or failed clouds cost one exiting CTA per launch slot
     __shared__ unsigned s_bits[kSmemBitmapBits / 32];
     __shared__ unsigned s_fail[kWorkers];
     const T *p = pts + (size_t)b * N * 3;
@@ -266,28 +357,26 @@ __global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N
         return;
     }
 
-    const long begin = (long)blockIdx.x * kCountPointsPerCta;
+    // this CTA's contiguous span of the cloud (a multiple of 4 * 256 points, so every thread's groups of four are
+    // 16-byte aligned when the cloud is)
+    long per = (n_used + gridDim.x - 1) / gridDim.x;
+    per = (per + 1023) / 1024 * 1024;
+    const long begin = (long)blockIdx.x * per;
     if (begin >= n_used) return;
     const GridCtx gc = make_grid_ctx(s);
-    const long end = begin + kCountPointsPerCta < n_used ? begin + kCountPointsPerCta : n_used;
+    const long end = begin + per < n_used ? begin + per : n_used;
     if (use_smem) {
         for (unsigned w = threadIdx.x; w < nwords; w += blockDim.x) s_bits[w] = 0u;
         __syncthreads();
-        for (long i = begin + threadIdx.x; i < end; i += blockDim.x) {
-            unsigned id;
-            // test before set: only ~V of the G cells are occupied, so after the first few hundred points of the
-            // CTA nearly every bit is already there and the (serialising) shared-memory atomic is skipped
-            if (point_cell<T>(p, i, gc, id) && !((s_bits[id >> 5] >> (id & 31)) & 1u)) atomicOr(&s_bits[id >> 5], 1u << (id & 31));
-        }
+        count_span<T, true>(p, begin, end, gc, s_bits, bm);
+    } else {
+        count_span<T, false>(p, begin, end, gc, s_bits, bm);
+    }
+    if (use_smem) {
         __syncthreads();
         for (unsigned w = threadIdx.x; w < nwords; w += blockDim.x) {
             const unsigned v = s_bits[w];
             if (v) atomicOr(&bm[w].x, v);
-        }
-    } else {
-        for (long i = begin + threadIdx.x; i < end; i += blockDim.x) {
-            unsigned id;
-            if (point_cell<T>(p, i, gc, id) && !((bm[id >> 5].x >> (id & 31)) & 1u)) atomicOr(&bm[id >> 5].x, 1u << (id & 31));
         }
     }
 }
@@ -297,12 +386,19 @@ __global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N
 // order and gives each point (slot, rank among earlier points of the tile in the same slot).
 // grid (ceil(tiles/4), B), block 128 (4 warps = 4 tiles); dynamic smem 4 * vcap u16 counters.
 // ------------------------------------------------------------------------------------------------
+// slot of a cell in the accepted grid's directory (bitmap word = {occupancy bits, occupied cells before the word})
+__device__ __forceinline__ unsigned slot_of_cell(const uint2 *__restrict__ bm, unsigned id) {
+    const uint2 w = bm[id >> 5];
+    return w.y + __popc(w.x & ((1u << (id & 31)) - 1u));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N, const CloudState *__restrict__ states,
                                               const uint2 *__restrict__ bitmap, size_t bitmap_stride, unsigned vcap,
                                               int ntiles, unsigned *__restrict__ slot_rank, unsigned *__restrict__ tile_cnt,
                                               int *__restrict__ point_voxel) {
     extern __shared__ unsigned short s_cnt_all[];
+    __shared__ __align__(16) unsigned s_slot[4][128], s_cell[4][128];     // per warp: slots / cells of 128 consecutive points
     const int b = blockIdx.y;
     const CloudState &s = states[b];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -326,18 +422,9 @@ __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N,
     const long n_used = chunk * kWorkers;
     const GridCtx gc = make_grid_ctx(s);
     const bool risky = s.risky != 0;
-    for (long base = begin; base < tend; base += 32) {
+    // ranks the 32 points [base, base + 32) in order: rank among earlier points of the tile in the same slot
+    auto rank32 = [&](long base, unsigned slot, unsigned id) {
         const long i = base + lane;
-        unsigned slot = kDropped;
-        unsigned id = 0;
-        bool live = i < n_used;
-        if (live && risky) live = (unsigned)i < s.fail[(unsigned long)i / (unsigned long)chunk];   // A4: only risky grids drop points
-        if (live) {
-            if (point_cell<T>(p, i, gc, id)) {
-                const uint2 w = bm[id >> 5];
-                slot = w.y + __popc(w.x & ((1u << (id & 31)) - 1u));
-            }
-        }
         const unsigned peers = __match_any_sync(0xffffffffu, slot);
         unsigned packed = kDropped;
         if (slot != kDropped) {
@@ -349,6 +436,44 @@ __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N,
         }
         __syncwarp();
         if (i < tend) { sr[i] = packed; if (pv) pv[i] = slot != kDropped ? (int)id : -1; }
+    };
+    if (cloud_vectorizable<T>(p) && !risky) {
+        // 128 points per step: every lane takes four consecutive points (three 16-byte loads), the slots go through
+        // shared memory so that the ranking still walks the points in index order, 32 at a time
+        const unsigned lxly = (unsigned)gc.len[0] * (unsigned)gc.len[1];
+        for (long base = begin; base < tend; base += 128) {
+            const long i0 = base + 4 * lane;
+            unsigned sl[4] = {kDropped, kDropped, kDropped, kDropped}, id[4] = {0u, 0u, 0u, 0u};
+            if (i0 + 3 < n_used) {
+                T x[4], y[4], z[4];
+                load_points4(p + i0 * 3, x, y, z);
+#pragma unroll
+                for (int k = 0; k < 4; k++) { id[k] = cell_id_fast((float)x[k], (float)y[k], (float)z[k], gc, lxly); sl[k] = slot_of_cell(bm, id[k]); }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (i0 + k < n_used && point_cell<T>(p, i0 + k, gc, id[k])) sl[k] = slot_of_cell(bm, id[k]);
+            }
+            *reinterpret_cast<uint4 *>(&s_slot[wid][4 * lane]) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
+            if (pv) *reinterpret_cast<uint4 *>(&s_cell[wid][4 * lane]) = make_uint4(id[0], id[1], id[2], id[3]);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (base + 32 * j >= tend) break;
+                rank32(base + 32 * j, s_slot[wid][32 * j + lane], pv ? s_cell[wid][32 * j + lane] : 0u);
+            }
+            __syncwarp();
+        }
+    } else {
+        for (long base = begin; base < tend; base += 32) {
+            const long i = base + lane;
+            unsigned slot = kDropped;
+            unsigned id = 0;
+            bool live = i < n_used;
+            if (live && risky) live = (unsigned)i < s.fail[(unsigned long)i / (unsigned long)chunk];   // A4: only risky grids drop points
+            if (live && point_cell<T>(p, i, gc, id)) slot = slot_of_cell(bm, id);
+            rank32(base, slot, id);
+        }
     }
     __syncwarp();
     unsigned *tc = tile_cnt + ((size_t)b * ntiles + tile) * vcap;
@@ -356,11 +481,37 @@ __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N,
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5  stable voxel assignment, step 2: per slot, turn the per-tile counts into exclusive prefixes and
-// the slot totals into segment starts.  grid B, block 1024.
+// K5  stable voxel assignment, step 2: per slot, turn the per-tile counts into exclusive prefixes (k_tile_prefix, the
+// part that moves data: ntiles x V counters per cloud, spread over ceil(V/256) CTAs per cloud) and the slot totals into
+// segment starts (k_offsets, one CTA per cloud over V values).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_offsets(CloudState *__restrict__ states, unsigned vcap, int ntiles,
-                                                  unsigned *__restrict__ tile_cnt, unsigned *__restrict__ vox_n,
+// step 2a: thread per slot, exclusive prefix of its per-tile counts in place and the slot total.  grid (ceil(vcap/256), B).
+__global__ void __launch_bounds__(256) k_tile_prefix(const CloudState *__restrict__ states, unsigned vcap, int ntiles,
+                                                     unsigned *__restrict__ tile_cnt, unsigned *__restrict__ vox_n) {
+    const int b = blockIdx.y;
+    const CloudState &s = states[b];
+    if (s.status != 0) return;
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= s.V) return;
+    unsigned *tc = tile_cnt + (size_t)b * ntiles * vcap;
+    unsigned acc = 0;
+    // 8 independent loads in flight per thread (the running sum is the only dependency)
+    for (int t0 = 0; t0 < ntiles; t0 += 8) {
+        unsigned c[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) c[j] = t0 + j < ntiles ? tc[(size_t)(t0 + j) * vcap + v] : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (t0 + j < ntiles) tc[(size_t)(t0 + j) * vcap + v] = acc;
+            acc += c[j];
+        }
+    }
+    vox_n[(size_t)b * vcap + v] = acc;
+}
+
+// step 2b: slot totals -> segment starts, heaviest-first processing order, heavy/light split.  grid B, block 1024.
+__global__ void __launch_bounds__(1024) k_offsets(CloudState *__restrict__ states, unsigned vcap,
+                                                  const unsigned *__restrict__ vox_n,
                                                   unsigned *__restrict__ vox_start, unsigned *__restrict__ vox_order) {
     const int b = blockIdx.x;
     CloudState &s = states[b];
@@ -371,24 +522,9 @@ __global__ void __launch_bounds__(1024) k_offsets(CloudState *__restrict__ state
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    unsigned *tc = tile_cnt + (size_t)b * ntiles * vcap;
     for (unsigned base = 0; base < V; base += blockDim.x) {
         const unsigned v = base + tid;
-        unsigned acc = 0;
-        if (v < V) {
-            // 8 independent loads in flight per thread (the running sum is the only dependency)
-            for (int t0 = 0; t0 < ntiles; t0 += 8) {
-                unsigned c[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) c[j] = t0 + j < ntiles ? tc[(size_t)(t0 + j) * vcap + v] : 0u;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if (t0 + j < ntiles) tc[(size_t)(t0 + j) * vcap + v] = acc;
-                    acc += c[j];
-                }
-            }
-            vox_n[(size_t)b * vcap + v] = acc;
-        }
+        const unsigned acc = v < V ? vox_n[(size_t)b * vcap + v] : 0u;
         unsigned inc = acc;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
@@ -426,7 +562,7 @@ __global__ void __launch_bounds__(1024) k_offsets(CloudState *__restrict__ state
 // vote labels into the per-voxel histogram.  grid (chunks, B), block 256.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) k_scatter(const T *__restrict__ pts, const uint16_t *__restrict__ labels, long N,
+__global__ void __launch_bounds__(256) k_scatter(const T *__restrict__ pts, const uint16_t *__restrict__ labels, int label_bytes, long N,
                                                  const CloudState *__restrict__ states, unsigned vcap, int ntiles,
                                                  const unsigned *__restrict__ slot_rank, const unsigned *__restrict__ tile_cnt,
                                                  const unsigned *__restrict__ vox_start, T *__restrict__ sorted,
@@ -441,7 +577,9 @@ __global__ void __launch_bounds__(256) k_scatter(const T *__restrict__ pts, cons
     const int tile = (int)(i / kRankTile);
     const unsigned pos = vox_start[(size_t)b * (vcap + 1) + slot] + tile_cnt[((size_t)b * ntiles + tile) * vcap + slot] + rank;
     const T *p = pts + ((size_t)b * N + i) * 3;
-    const unsigned l = labels ? labels[(size_t)b * N + i] : 0u;
+    // labels: uint16 per point (the reference's dtype) or, with NDNET_B200_LABELS_U8, one byte per point
+    const unsigned l = !labels ? 0u : (label_bytes == 1 ? (unsigned)reinterpret_cast<const uint8_t *>(labels)[(size_t)b * N + i]
+                                                        : (unsigned)labels[(size_t)b * N + i]);
     store_sorted<T>(sorted + ((size_t)b * N + pos) * kSortedStride, p[0], p[1], p[2], l);
     // wide label sets (> kSmemLabelBins classes) vote through global atomics; small ones are counted by k_votes
     if (labels && hist && l < (unsigned)nbins) atomicAdd(&hist[((size_t)b * vcap + slot) * nbins + l], 1u);
@@ -1297,7 +1435,10 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     k_decide<<<B, 256, 0, st>>>(w.states, w.lim_enc, w.bitmap, w.bitmap_stride, w.vox_cell, vcap, D, 0); DBG("k_decide");
     tm.mark(ST_SEARCH, st);
     {
+        // a few CTAs per cloud, each walking a long contiguous span: a launch for clouds that are done is one wave of exiting
+        // CTAs, and a live CTA merges its shared-memory bitmap into the global one once per ~15 k points
         int chunks = (int)((N + kCountPointsPerCta - 1) / kCountPointsPerCta);
+        if (chunks > kCountCtasPerCloud) chunks = kCountCtasPerCloud;
         if (chunks < 1) chunks = 1;
         for (int it = 0; it < kMaxGuessIterations; it++) {
             k_count<T><<<dim3(chunks, B), 256, 0, st>>>(pts, N, w.states, w.bitmap, w.bitmap_stride); DBG("k_count");
@@ -1313,13 +1454,14 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         DBG("k_rank");
     }
     tm.mark(ST_OFFSETS, st);
-    k_offsets<<<B, 1024, 0, st>>>(w.states, vcap, ntiles, w.tile_cnt, w.vox_n, w.vox_start, w.vox_order); DBG("k_offsets");
+    k_tile_prefix<<<dim3((vcap + 255) / 256, B), 256, 0, st>>>(w.states, vcap, ntiles, w.tile_cnt, w.vox_n); DBG("k_tile_prefix");
+    k_offsets<<<B, 1024, 0, st>>>(w.states, vcap, w.vox_n, w.vox_start, w.vox_order); DBG("k_offsets");
     tm.mark(ST_SCATTER, st);
     const bool wide_labels = labels && nbins > kSmemLabelBins;
     if (wide_labels) CK(cudaMemsetAsync(w.hist, 0, (size_t)B * vcap * nbins * sizeof(unsigned), st));
     if (N > 0) {
         k_scatter<T><<<dim3((unsigned)((N + 255) / 256), B), 256, 0, st>>>(
-            pts, labels, N, w.states, vcap, ntiles, w.slot_rank, w.tile_cnt, w.vox_start, (T *)w.sorted,
+            pts, labels, (flags & 2u) ? 1 : 2, N, w.states, vcap, ntiles, w.slot_rank, w.tile_cnt, w.vox_start, (T *)w.sorted,
             wide_labels ? w.hist : nullptr, nbins);
         DBG("k_scatter");
     }
@@ -1380,7 +1522,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     }
     DBG("end");
     tm.mark(ST_COUNT, st);
-    count_launches(3 + 2 * kMaxGuessIterations + (N > 0 ? 2 : 0) + 5 + (wide_labels ? 1 : 0));
+    count_launches(3 + 2 * kMaxGuessIterations + (N > 0 ? 2 : 0) + 6 + (wide_labels ? 1 : 0));
     if (tm.enabled) {
         CK(cudaEventSynchronize(tm.ev[ST_COUNT]));
         for (int i = 0; i < ST_COUNT; i++) { float ms = 0; cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]); tm.ms[i] += ms; }

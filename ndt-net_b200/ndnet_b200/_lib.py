@@ -23,6 +23,7 @@ assert INFO_DTYPE.itemsize == 128
 
 F32, F64 = 0, 1
 NAN_TO_NUM = 1
+LABELS_U8 = 2
 
 _lib = None
 
@@ -78,6 +79,8 @@ def lib() -> C.CDLL:
     L.ndnet_b200_test_fail_next_reserve.argtypes = [vp]
     L.ndnet_b200_infer_host.restype = i
     L.ndnet_b200_infer_host.argtypes = [vp, vp, vp, i, vp, i, l, i, l, vp, l, vp]
+    L.ndnet_b200_infer_host_u8.restype = i
+    L.ndnet_b200_infer_host_u8.argtypes = [vp, vp, vp, i, vp, i, l, i, l, vp, l, vp]
     L.ndnet_b200_infer_device.restype = i
     L.ndnet_b200_infer_device.argtypes = [vp, vp, vp, i, vp, i, l, i, l, vp, l, vp]
     L.ndnet_b200_set_pipeline.restype = i
@@ -126,7 +129,7 @@ EXPORTED = [
     "ndnet_b200_last_kl_list", "ndnet_b200_selftest_div", "ndnet_b200_launch_count", "ndnet_b200_stage_timing", "ndnet_b200_stage_times",
     "ndnet_b200_model_create", "ndnet_b200_model_input_dim", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
     "ndnet_b200_model_tap", "ndnet_b200_test_fail_next_reserve",
-    "ndnet_b200_infer_host", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline", "ndnet_b200_set_device_chunk",
+    "ndnet_b200_infer_host", "ndnet_b200_infer_host_u8", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline", "ndnet_b200_set_device_chunk",
     "ndnet_b200_ply_load", "ndnet_b200_ply_num_points", "ndnet_b200_ply_sample", "ndnet_b200_ply_free",
     "ndnet_b200_trainer_create", "ndnet_b200_trainer_forward", "ndnet_b200_trainer_backward", "ndnet_b200_trainer_last_error",
     "ndnet_b200_trainer_backward_flat", "ndnet_b200_trainer_grad_layout", "ndnet_b200_trainer_set_graph",

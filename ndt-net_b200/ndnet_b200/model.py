@@ -97,13 +97,19 @@ class B200Model:
 
     def infer_host(self, points: torch.Tensor, num_desired: int, labels: torch.Tensor | None, num_classes: int,
                    out: torch.Tensor) -> torch.Tensor:
-        """HOST tensors in (pinned for speed), HOST tensor out: H2D + NDT + forward + D2H + sync in one C call."""
+        """HOST tensors in (pinned for speed), HOST tensor out: H2D + NDT + forward + D2H + sync in one C call.
+        labels: int16/uint16 [B, N] (the reference's dtype) or uint8 [B, N] (one byte per point, num_classes <= 255)."""
         assert not points.is_cuda and points.is_contiguous() and not out.is_cuda
         B, N, _ = points.shape
         per_cloud = out.numel() // B
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        fn = self._L.ndnet_b200_infer_host
+        if labels is not None:
+            assert labels.is_contiguous() and labels.dtype in (torch.int16, torch.uint16, torch.uint8)
+            if labels.dtype == torch.uint8:
+                fn = self._L.ndnet_b200_infer_host_u8
         with torch.cuda.device(self.device):
-            rc = self._L.ndnet_b200_infer_host(
+            rc = fn(
                 self.engine.handle, self._h, points.data_ptr(), _lib.F32 if points.dtype == torch.float32 else _lib.F64,
                 labels.data_ptr() if labels is not None else None, B, N, int(num_classes), int(num_desired),
                 out.data_ptr(), per_cloud, stream)
