@@ -36,6 +36,8 @@ import torch  # noqa: E402
 N_POINTS, N_NDS, N_CLASSES, FEATURE_DIM = 120_000, 1000, 28, 1024
 WORKLOAD = "config4: segmentation head (seg_viz path), 120k-point synthetic LiDAR scans, n_desired_nds=1000, 29 classes, F=1024"
 STAGES = ["limits", "search", "rank", "offsets", "scatter", "stats", "kl", "select"]
+DOMINANT_KERNEL = {"limits": "k_limits", "rank": "k_rank", "offsets": "k_tile_prefix + k_offsets", "scatter": "k_scatter",
+                   "stats": "k_stats (heavy voxels) || k_stats_light (side stream)", "kl": "k_kl", "select": "k_select"}
 ALGO_BYTES_PER_CLOUD = N_POINTS * 12 + N_POINTS * 2 + N_NDS * 48 + N_NDS * 2     # SURVEY.md §8(d), with labels
 
 
@@ -122,11 +124,18 @@ def build_network(device):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
+def ref_workers(threads: int) -> int:
+    """Concurrent ndt_downsample calls that fill the host: the reference's core uses a fixed 8 pthreads per call
+    (normal_distributions.h:39) and ctypes releases the GIL, so threads // 8 calls run side by side."""
+    return max(1, threads // 8)
+
+
 def cpu_reference(n_clouds: int, seed0: int, threads: int, variant: str = "threaded"):
     """The reference path on the host: per-cloud ndt_downsample of the reference's own C core (8 pthreads inside,
     oracle/_ref/libndnet_ref.so = unmodified core_legacy sources, -O0 as its CMake builds them) through the same
     marshalling as ndnet/preprocessing/ndt_legacy.py, float32 + nan_to_num as ndtnet_preprocessing.py:60-69, then the
-    fp32 torch network on all host threads.  Returns (seconds, kind)."""
+    fp32 torch network on all host threads.  The reference's loop is serial over scans (ndtnet_preprocessing.py:27); to
+    give it every host core, threads // 8 scans are in flight at once.  Returns (seconds, kind)."""
     from oracle import ref_ctypes
     torch.set_num_threads(threads)
     if ref_ctypes.have_ref(variant):
@@ -143,11 +152,16 @@ def cpu_reference(n_clouds: int, seed0: int, threads: int, variant: str = "threa
     t0 = time.perf_counter()
     means = np.zeros((n_clouds, N_NDS, 3), np.float32)
     covs = np.zeros((n_clouds, N_NDS, 9), np.float32)
-    for b in range(n_clouds):
+
+    def one(b):
         r = run(pts[b].astype(np.float64), lab[b])
         m, c = unpack(r)
         means[b, : len(m)] = m
         covs[b, : len(c)] = c
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=ref_workers(threads)) as pool:
+        list(pool.map(one, range(n_clouds)))
     with torch.no_grad():
         m = torch.nan_to_num(torch.from_numpy(means), nan=0.0, posinf=0.0, neginf=0.0)
         c = torch.nan_to_num(torch.from_numpy(covs), nan=0.0, posinf=0.0, neginf=0.0)
@@ -176,10 +190,13 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "clouds_per_step": per_step, "points": N_POINTS, "n_desired_nds": N_NDS,
-                   "parallelism": "host CPU only (rank 0); NDT core uses its fixed 8 pthreads, torch all host threads"},
+                   "parallelism": f"host CPU only (ONE process on rank 0, whatever --gpus is); {ref_workers(threads)} scans in flight x the NDT "
+                                  f"core's fixed 8 pthreads, then torch on all {threads} host threads"},
         "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": threads, "kind": kind,
-                         "sample": f"{per_step} scans per step x {args.steps} steps; NDT = reference C core (8 pthreads, -O0, GSL shim) "
-                                   f"serial over scans, network = torch fp32 on {threads} threads"},
+                         "sample": f"{per_step} scans per step x {args.steps} steps; NDT = reference C core (8 pthreads per scan, "
+                                   f"{ref_workers(threads)} scans in flight, -O0, GSL shim), network = this repo's torch mirror of ndtnet.py "
+                                   f"(pinned to the reference modules by tests/test_model_cpu.py; /root/reference does not exist on the "
+                                   f"GPU box) in fp32 on {threads} threads"},
         "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -211,9 +228,9 @@ def run_ours(args):
     for s in range(n_sets):
         p, l = make_scans(B, seed0=ndist_seed(rank, B, s))
         hp = torch.from_numpy(p).pin_memory()
-        hl = torch.from_numpy(l.astype(np.int16)).pin_memory()
+        hl = torch.from_numpy(l.astype(np.uint8)).pin_memory()       # 29 classes fit one byte per point: 13 B/point cross PCIe
         host_pts.append(hp); host_lab.append(hl)
-        dev_pts.append(hp.to(dev)); dev_lab.append(hl.to(dev))
+        dev_pts.append(hp.to(dev)); dev_lab.append(torch.from_numpy(l.astype(np.int16)).to(dev))
     eng = NdtEngine(local)
     net = build_network(dev)
     model = B200Model(net, KIND_SEG, dev)
@@ -248,6 +265,36 @@ def run_ours(args):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
+    def h2d_ceiling(steps):
+        """Bare pinned host -> device copies of exactly the bytes a step of the e2e path moves, on `lanes` streams in the
+        same chunks, no kernels: the PCIe ceiling the e2e number is measured against (max over ranks)."""
+        lanes = [torch.cuda.Stream(dev) for _ in range(args.lanes)]
+        chunk = min(args.chunk, (B + args.lanes - 1) // args.lanes)
+        dst_p = [torch.empty((chunk, N_POINTS, 3), dtype=torch.float32, device=dev) for _ in lanes]
+        dst_l = [torch.empty((chunk, N_POINTS), dtype=torch.uint8, device=dev) for _ in lanes]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def run(n):
+            for i in range(n):
+                hp, hl = host_pts[i % n_sets], host_lab[i % n_sets]
+                for k, b0 in enumerate(range(0, B, chunk)):
+                    nb = min(chunk, B - b0)
+                    ln = lanes[k % len(lanes)]
+                    with torch.cuda.stream(ln):
+                        dst_p[k % len(lanes)][:nb].copy_(hp[b0:b0 + nb], non_blocking=True)
+                        dst_l[k % len(lanes)][:nb].copy_(hl[b0:b0 + nb], non_blocking=True)
+        run(2)
+        barrier()
+        e0.record(stream)
+        for ln in lanes:
+            ln.wait_stream(stream)
+        run(steps)
+        for ln in lanes:
+            stream.wait_stream(ln)
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
     # correctness guard of the measured configuration: every scan converged to N_NDS distributions
     chk = eng.downsample(dev_pts[0], N_NDS, dev_lab[0], N_CLASSES)
     assert np.all(chk.info["status"] == 0) and np.all(chk.info["num_out"] == N_NDS), "workload did not converge"
@@ -269,6 +316,7 @@ def run_ours(args):
     launches = L.ndnet_b200_launch_count() - launches0
     ms_e2e = timed(step_host, args.steps)
     clocks = sampler.stop()
+    ms_h2d = h2d_ceiling(args.steps)
 
     # per-stage CUDA-event times of the NDT kernels (same K steps, events on the launching stream) and of the network
     L.ndnet_b200_stage_timing(eng.handle, 1)
@@ -280,6 +328,9 @@ def run_ours(args):
     runs = np.zeros(1, np.int64)
     L.ndnet_b200_stage_times(eng.handle, st.ctypes.data, 8, runs.ctypes.data)
     L.ndnet_b200_stage_timing(eng.handle, 0)
+    import ctypes
+    passes, evals = ctypes.c_double(0), ctypes.c_double(0)
+    L.ndnet_b200_last_search_passes(eng.handle, ctypes.byref(passes), ctypes.byref(evals))
     stage_ms = {n: float(st[i]) / max(int(runs[0]), 1) for i, n in enumerate(STAGES)}
     feat = eng.downsample(dev_pts[0], N_NDS, dev_lab[0], N_CLASSES, want_info=False).feat
     model(feat)                               # sizes the single-stream scratch outside the timed loop
@@ -301,8 +352,8 @@ def run_ours(args):
     e2e_value = clouds / (ms_e2e * 1e-3)
     peak, peak_src = peaks()
     dom = max(STAGES, key=lambda n: stage_ms[n])
-    # the `search` stage is up to 15 k_count launches; each launch that does work reads every point once
-    launches_in_dom = {"search": 5}.get(dom, 1)
+    # the `search` stage is 15 k_count launches; the ones that do work (mean over the scans) read every point once
+    launches_in_dom = {"search": max(passes.value, 1.0)}.get(dom, 1)
     dom_ms = stage_ms[dom] / launches_in_dom
     achieved = ALGO_BYTES_PER_CLOUD * B / (dom_ms * 1e-3) / 1e9
     line = {
@@ -314,22 +365,31 @@ def run_ours(args):
                    "pipeline": f"{args.lanes} lanes; chunks of {args.device_chunk} scans (device buffers, `value`) / {args.chunk} scans (host buffers, `e2e`)",
                    "l2": f"inputs rotate over {n_sets} resident batches ({n_sets * B * ALGO_BYTES_PER_CLOUD / 1e6:.0f} MB vs 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": "clouds/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": B * N_POINTS * 14, "d2h_bytes_per_step": B * N_NDS * (N_CLASSES + 1) * 4},
+                "h2d_bytes_per_step": B * N_POINTS * 13, "d2h_bytes_per_step": B * N_NDS * (N_CLASSES + 1) * 4,
+                "labels": "uint8 (29 classes; ndnet_b200_infer_host_u8)",
+                # the same bytes, same chunks and lanes, copies only: what PCIe gives this rank count on this box
+                "h2d_ceiling_ms": ms_h2d / args.steps,
+                "h2d_gbs_aggregate": world * B * N_POINTS * 13 / (ms_h2d / args.steps * 1e-3) / 1e9,
+                "fraction_of_h2d_ceiling": (ms_h2d / args.steps) / (ms_e2e / args.steps)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": {"limits": "k_limits", "search": "k_count (x5 launches that do work, of 15)",
-                                                "rank": "k_rank", "offsets": "k_offsets", "scatter": "k_scatter", "stats": "k_stats",
-                                                "kl": "k_kl", "select": "k_select"}[dom],
+        "roofline": {"bound": "hbm",
+                     "kernel": dict(DOMINANT_KERNEL, search=f"k_count (x{passes.value:.2f} launches that do work, of 15; "
+                                                            f"{evals.value:.2f} guesses evaluated per scan)")[dom],
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic({"search": "k_count"}.get(dom, "k_" + dom), B),
+                     "traffic": ncu_traffic({"search": "k_count", "offsets": "k_tile_prefix"}.get(dom, "k_" + dom), B),
+                     # the whole NDT path against the same algorithmic bytes: sum of its stage times
+                     "ndt_pipeline": {"ms_per_step": sum(stage_ms[n] for n in STAGES),
+                                      "achieved": ALGO_BYTES_PER_CLOUD * B / (sum(stage_ms[n] for n in STAGES) * 1e-3) / 1e9,
+                                      "frac": ALGO_BYTES_PER_CLOUD * B / (sum(stage_ms[n] for n in STAGES) * 1e-3) / 1e9 / peak},
                      "peak_source": peak_src, "stage_ms_per_step": stage_ms},
     }
     if world == 1 and not args.no_cpu_baseline:
         n = args.cpu_clouds
         dt, kind = cpu_reference(n, 500_000, os.cpu_count() or 1)
         line["cpu_baseline"] = {"value": n / dt, "unit": "clouds/s", "cores": os.cpu_count() or 1, "kind": kind,
-                                "sample": f"{n} scans of the same workload; NDT = reference C core (8 pthreads, -O0, GSL shim) serial over "
-                                          f"scans, network = torch fp32 on all host threads"}
+                                "sample": f"{n} scans of the same workload; NDT = reference C core (8 pthreads per scan, "
+                                          f"{ref_workers(os.cpu_count() or 1)} scans in flight, -O0, GSL shim), network = torch fp32 on all host threads"}
         # courtesy number: the same reference sources compiled with -O2
         dt2, kind2 = cpu_reference(n, 500_000, os.cpu_count() or 1, variant="O2")
         if kind2 == "reference":

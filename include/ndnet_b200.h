@@ -148,6 +148,10 @@ long ndnet_b200_selftest_div(long n, unsigned seed);
  * triggers it returns the allocation error; the one after must allocate afresh and succeed). */
 int ndnet_b200_test_fail_next_reserve(ndnet_b200_ctx *ctx);
 int ndnet_b200_stage_timing(ndnet_b200_ctx *ctx, int enable);
+/* Of the last ndnet_b200_downsample_batch on this context, averaged over its clouds: how many voxel-size guesses needed a
+ * pass over the points, and how many guesses were evaluated in all (a grid with fewer cells than num_desired is decided
+ * without reading the points).  Synchronises the device.  bench.py divides the search stage by the former. */
+int ndnet_b200_last_search_passes(ndnet_b200_ctx *ctx, double *mean_passes, double *mean_evaluations);
 int ndnet_b200_stage_times(ndnet_b200_ctx *ctx, double *ms, int cap, long *runs);
 
 /* ---- PointNet / NDT-Net forward (ndnet/models/ndtnet.py:33-62,112-164,181-196,218-243) ------------ */

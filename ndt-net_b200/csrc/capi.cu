@@ -118,7 +118,7 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     // Bitmap words per cloud: enough for kMaxGridCells when the batch is small, never less than 64K
     // cells; the search answers -1 (as the reference does when malloc fails) beyond what is held.
     bitmap_stride = (size_t)(1u << 25) / 32;
-    ntiles_cap = (int)((nN + 2047) / 2048);
+    ntiles_cap = (int)((nN + 2047) / 2048);   // >= ceil(N / kRankTile)
     const size_t kcap = (size_t)vcap * 6;
     cudaError_t e;
     // a failed allocation leaves NO capacity behind: release() frees what was obtained and zeroes the caps, so the next
@@ -224,6 +224,22 @@ extern "C" int ndnet_b200_stage_times(ndnet_b200_ctx *c, double *ms, int cap, lo
     for (int i = 0; i < cap && i < (int)ndt::ST_COUNT; i++) ms[i] = c->ws.timer.ms[i];
     if (runs) *runs = c->ws.timer.runs;
     return (int)ndt::ST_COUNT;
+}
+
+extern "C" int ndnet_b200_last_search_passes(ndnet_b200_ctx *c, double *mean_passes, double *mean_evaluations) {
+    if (!c || c->ws.last_B <= 0) return -200;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail(c, e, "synchronise");
+    double p = 0, v = 0;
+    for (int b = 0; b < c->ws.last_B; b++) {
+        ndt::CloudSummary cs;
+        if ((e = ndt::read_cloud_summary(c->ws, b, &cs)) != cudaSuccess) return fail(c, e, "read state");
+        p += cs.passes; v += cs.evals;
+    }
+    if (mean_passes) *mean_passes = p / c->ws.last_B;
+    if (mean_evaluations) *mean_evaluations = v / c->ws.last_B;
+    return 0;
 }
 
 extern "C" const char *ndnet_b200_last_error(const ndnet_b200_ctx *c) { return c ? c->err.c_str() : "null context"; }

@@ -23,7 +23,7 @@ constexpr unsigned kMaxGridCells = 1u << 25;   // cells per cloud the bitmap wor
 constexpr unsigned kSmemBitmapBits = 1u << 17; // grids up to this many cells are counted in shared memory (16 KB: 8 CTAs of k_count per SM)
 constexpr int kCountPointsPerCta = 4096;
 constexpr int kCountCtasPerCloud = 8;          // CTAs of k_count per cloud (each walks N / 8 consecutive points)
-constexpr int kRankTile = 2048;                // points per rank tile (one warp walks one tile in order)
+constexpr int kRankTile = 4096;                // points per rank tile (one warp walks one tile in order)
 constexpr unsigned kDropped = 0xFFFFFFFFu;
 constexpr int kLimWords = 8;                   // per cloud: encoded max x,y,z, min x,y,z, NaN-seen flag, (pad)
 constexpr int kStatusNaNInput = -5;            // a coordinate is NaN: refused (the reference's behaviour is undefined, voxel.c:89-91)
@@ -52,6 +52,7 @@ struct CloudState {
     unsigned n_survivors;
     unsigned fail[kWorkers]; // first point of each worker chunk that left the grid (A4), else 0xFFFFFFFF
     unsigned n_heavy;     // voxels with >= kHeavyVoxel points (first n_heavy entries of vox_order)
+    int passes;           // guesses that needed a pass over the points (the others were decided by skip_small_grids)
 };
 
 // Order-preserving map double <-> uint64 for atomicMin/atomicMax.

@@ -76,7 +76,7 @@ size_t cloud_state_size();
 cudaError_t selftest_div(long n, unsigned seed, unsigned long long *mismatches_host);
 
 // host copy of the scalar results of one cloud of the last batch
-struct CloudSummary { int status; int len[3]; unsigned V, K, n_valid, walk; int prune_ret; };
+struct CloudSummary { int status; int len[3]; unsigned V, K, n_valid, walk; int prune_ret; int passes, evals; };
 cudaError_t read_cloud_summary(const Workspace &w, int b, CloudSummary *out);
 
 // Device-resident state one legacy ndt_downsample call retains for prune_nds / to_point_cloud

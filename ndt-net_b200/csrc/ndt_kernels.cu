@@ -19,6 +19,10 @@
 #define NDT_STATS_MIN_BLOCKS 4
 #endif
 constexpr int kStatsWarps = NDT_STATS_WARPS;   // warps per CTA of k_stats
+constexpr int kSelectThreads = 512;             // k_select: three 512-thread CTAs per SM overlap one another's barriers
+#ifndef NDT_RANK_MATCH_ANY
+#define NDT_RANK_MATCH_ANY 0
+#endif
 #ifndef NDT_STATS_Q
 #define NDT_STATS_Q 4
 #endif
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(256) k_decide(CloudState *__restrict__ states,
             }
             s.guess = (double)(kMaxVoxelGuess - kMinVoxelGuess) / 2.0;   // ndt.c:136
             s.lo = kMinVoxelGuess; s.hi = kMaxVoxelGuess;
-            s.iter = 0; s.evals = 0; s.V = 0; s.K = 0; s.n_valid = 0; s.walk = 0; s.prune_ret = 0; s.n_out = 0;
+            s.iter = 0; s.evals = 0; s.passes = 0; s.V = 0; s.K = 0; s.n_valid = 0; s.walk = 0; s.prune_ret = 0; s.n_out = 0;
             s.n_survivors = 0;
             for (int w = 0; w < kWorkers; w++) s.fail[w] = kDropped;
             s.status = 1;
@@ -197,6 +201,7 @@ __global__ void __launch_bounds__(256) k_decide(CloudState *__restrict__ states,
             for (int w = 0; w < 8; w++) total += s_part[w];
             s_total = total;
             s.evals++;
+            s.passes++;
             const unsigned long num_nds = total;
             const unsigned long D = (unsigned long)num_desired;
             if ((double)num_nds > (double)D * (1 + kUpperThreshold)) { s.lo = s.guess; s_action = 1; }      // ndt.c:169
@@ -425,15 +430,25 @@ __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N,
     // ranks the 32 points [base, base + 32) in order: rank among earlier points of the tile in the same slot
     auto rank32 = [&](long base, unsigned slot, unsigned id) {
         const long i = base + lane;
+        // lanes of the group that hold the same slot.  32 broadcast-and-compare steps: independent, fully pipelined
+        // instructions (3 per point), where MATCH.ANY iterates over the distinct values of the warp - about 31 of them
+        // for a scan in random point order.
+#if NDT_RANK_MATCH_ANY
         const unsigned peers = __match_any_sync(0xffffffffu, slot);
+#else
+        unsigned peers = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) peers |= (__shfl_sync(0xffffffffu, slot, j) == slot ? 1u : 0u) << j;
+#endif
         unsigned packed = kDropped;
+        unsigned basec = 0;
         if (slot != kDropped) {
             const unsigned before = __popc(peers & ((1u << lane) - 1u));
-            const unsigned basec = cnt[slot];
+            basec = cnt[slot];
             packed = slot * (unsigned)kRankTile + basec + before;
-            __syncwarp(peers);
-            if (lane == 31 - __clz(peers)) cnt[slot] = (unsigned short)(basec + __popc(peers));
         }
+        __syncwarp();
+        if (slot != kDropped && lane == 31 - __clz(peers)) cnt[slot] = (unsigned short)(basec + __popc(peers));
         __syncwarp();
         if (i < tend) { sr[i] = packed; if (pv) pv[i] = slot != kDropped ? (int)id : -1; }
     };
@@ -495,13 +510,14 @@ __global__ void __launch_bounds__(256) k_tile_prefix(const CloudState *__restric
     if (v >= s.V) return;
     unsigned *tc = tile_cnt + (size_t)b * ntiles * vcap;
     unsigned acc = 0;
-    // 8 independent loads in flight per thread (the running sum is the only dependency)
-    for (int t0 = 0; t0 < ntiles; t0 += 8) {
-        unsigned c[8];
+    // the kernel is a chain of memory round trips per thread: issue 32 loads before the first dependent store (the running
+    // sum is the only dependency), so that a 59-tile scan is two round trips instead of eight
+    for (int t0 = 0; t0 < ntiles; t0 += 32) {
+        unsigned c[32];
 #pragma unroll
-        for (int j = 0; j < 8; j++) c[j] = t0 + j < ntiles ? tc[(size_t)(t0 + j) * vcap + v] : 0u;
+        for (int j = 0; j < 32; j++) c[j] = t0 + j < ntiles ? tc[(size_t)(t0 + j) * vcap + v] : 0u;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < 32; j++) {
             if (t0 + j < ntiles) tc[(size_t)(t0 + j) * vcap + v] = acc;
             acc += c[j];
         }
@@ -1128,8 +1144,8 @@ __device__ __forceinline__ unsigned long long desc_key(double d) {
 }
 
 __device__ __forceinline__ unsigned block_scan_step(unsigned val, unsigned *s_warp, unsigned &total) {
-    // inclusive scan over a 1024-thread block; returns exclusive prefix of this thread, total of block
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // inclusive scan over the block (up to 1024 threads); returns exclusive prefix of this thread, total of block
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     unsigned inc = val;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
@@ -1137,11 +1153,11 @@ __device__ __forceinline__ unsigned block_scan_step(unsigned val, unsigned *s_wa
     if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
     unsigned woff = 0; total = 0;
-    for (int k = 0; k < 32; k++) { const unsigned x = s_warp[k]; if (k < wid) woff += x; total += x; }
+    for (int k = 0; k < nwarps; k++) { const unsigned x = s_warp[k]; if (k < wid) woff += x; total += x; }
     return woff + inc - val;
 }
 
-__global__ void __launch_bounds__(1024) k_select(CloudState *__restrict__ states, unsigned vcap, long num_desired,
+__global__ void __launch_bounds__(kSelectThreads, 3) k_select(CloudState *__restrict__ states, unsigned vcap, long num_desired,
                                                  const unsigned *__restrict__ vox_cell, const unsigned *__restrict__ vox_n,
                                                  const double *__restrict__ mean, const double *__restrict__ cov_final,
                                                  const uint16_t *__restrict__ cls, int has_labels,
@@ -1212,7 +1228,7 @@ __global__ void __launch_bounds__(1024) k_select(CloudState *__restrict__ states
         __syncthreads();
         double wpre = s_cmin;
         double blockmin = s_cmin;
-        for (int k = 0; k < 32; k++) { const double x = s_wmin[k]; if (k < wid) wpre = x < wpre ? x : wpre; blockmin = x < blockmin ? x : blockmin; }
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) { const double x = s_wmin[k]; if (k < wid) wpre = x < wpre ? x : wpre; blockmin = x < blockmin ? x : blockmin; }
         excl = wpre < excl ? wpre : excl;
         if (present) {
             const unsigned pos = s_carry + pos_in;
@@ -1299,7 +1315,7 @@ __global__ void __launch_bounds__(1024) k_select(CloudState *__restrict__ states
         __syncthreads();
         if (tid == 0) {
             unsigned wm = 0;
-            for (int k = 0; k < 32; k++) wm = s_warp[k] > wm ? s_warp[k] : wm;
+            for (int k = 0; k < (int)(blockDim.x >> 5); k++) wm = s_warp[k] > wm ? s_warp[k] : wm;
             const unsigned n_removed = total;
             s.K = K;
             s.n_valid = V - n_removed;
@@ -1515,7 +1531,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         static bool attr_set[64] = {};   // function attributes are per device
         int dev = 0; cudaGetDevice(&dev);
         if (!attr_set[dev & 63]) { CK(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn)); attr_set[dev & 63] = true; }
-        k_select<<<B, 1024, bytes, st>>>(w.states, vcap, D, w.vox_cell, w.vox_n, w.mean, w.cov_final, w.cls, labels ? 1 : 0,
+        k_select<<<B, kSelectThreads, bytes, st>>>(w.states, vcap, D, w.vox_cell, w.vox_n, w.mean, w.cov_final, w.cls, labels ? 1 : 0,
                                          w.kl_div, w.kl_flag, w.key, w.seq, kcap, smem_cap, w.firstpos, w.removed, flags,
                                          out_feat, out_feat64, out_labels, out_voxel, w.list_div, w.list_seq, info);
         DBG("k_select");

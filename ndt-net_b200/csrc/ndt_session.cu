@@ -21,6 +21,7 @@ cudaError_t read_cloud_summary(const Workspace &w, int b, CloudSummary *out) {
     out->status = s.status;
     for (int a = 0; a < 3; a++) out->len[a] = s.len[a];
     out->V = s.V; out->K = s.K; out->n_valid = s.n_valid; out->walk = s.walk; out->prune_ret = s.prune_ret;
+    out->passes = s.passes; out->evals = s.evals;
     return cudaSuccess;
 }
 

@@ -62,6 +62,8 @@ def lib() -> C.CDLL:
     L.ndnet_b200_launch_count.argtypes = []
     L.ndnet_b200_stage_timing.restype = i
     L.ndnet_b200_stage_timing.argtypes = [vp, i]
+    L.ndnet_b200_last_search_passes.restype = i
+    L.ndnet_b200_last_search_passes.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ndnet_b200_stage_times.restype = i
     L.ndnet_b200_stage_times.argtypes = [vp, vp, i, vp]
     L.ndnet_b200_model_create.restype = i
@@ -127,6 +129,7 @@ EXPORTED = [
     "ndnet_b200_create", "ndnet_b200_destroy", "ndnet_b200_last_error", "ndnet_b200_version",
     "ndnet_b200_downsample_batch", "ndnet_b200_downsample_batch_host", "ndnet_b200_keep_point_voxels", "ndnet_b200_last_point_voxels",
     "ndnet_b200_last_kl_list", "ndnet_b200_selftest_div", "ndnet_b200_launch_count", "ndnet_b200_stage_timing", "ndnet_b200_stage_times",
+    "ndnet_b200_last_search_passes",
     "ndnet_b200_model_create", "ndnet_b200_model_input_dim", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
     "ndnet_b200_model_tap", "ndnet_b200_test_fail_next_reserve",
     "ndnet_b200_infer_host", "ndnet_b200_infer_host_u8", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline", "ndnet_b200_set_device_chunk",
