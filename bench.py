@@ -265,13 +265,15 @@ def run_ours(args):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
-    def h2d_ceiling(steps):
+    def h2d_ceiling(steps, with_d2h=False):
         """Bare pinned host -> device copies of exactly the bytes a step of the e2e path moves, on `lanes` streams in the
-        same chunks, no kernels: the PCIe ceiling the e2e number is measured against (max over ranks)."""
+        same chunks, no kernels: the PCIe ceiling the e2e number is measured against (max over ranks).  with_d2h: each
+        chunk's result bytes also travel back (the e2e path's device -> host read), as they do in the real step."""
         lanes = [torch.cuda.Stream(dev) for _ in range(args.lanes)]
         chunk = min(args.chunk, (B + args.lanes - 1) // args.lanes)
         dst_p = [torch.empty((chunk, N_POINTS, 3), dtype=torch.float32, device=dev) for _ in lanes]
         dst_l = [torch.empty((chunk, N_POINTS), dtype=torch.uint8, device=dev) for _ in lanes]
+        src_o = [torch.empty((chunk, N_NDS, N_CLASSES + 1), dtype=torch.float32, device=dev) for _ in lanes]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
         def run(n):
@@ -283,6 +285,8 @@ def run_ours(args):
                     with torch.cuda.stream(ln):
                         dst_p[k % len(lanes)][:nb].copy_(hp[b0:b0 + nb], non_blocking=True)
                         dst_l[k % len(lanes)][:nb].copy_(hl[b0:b0 + nb], non_blocking=True)
+                        if with_d2h:
+                            out_host[b0:b0 + nb].copy_(src_o[k % len(lanes)][:nb], non_blocking=True)
         run(2)
         barrier()
         e0.record(stream)
@@ -317,6 +321,7 @@ def run_ours(args):
     ms_e2e = timed(step_host, args.steps)
     clocks = sampler.stop()
     ms_h2d = h2d_ceiling(args.steps)
+    ms_copies = h2d_ceiling(args.steps, with_d2h=True)
 
     # per-stage CUDA-event times of the NDT kernels (same K steps, events on the launching stream) and of the network
     L.ndnet_b200_stage_timing(eng.handle, 1)
@@ -370,7 +375,10 @@ def run_ours(args):
                 # the same bytes, same chunks and lanes, copies only: what PCIe gives this rank count on this box
                 "h2d_ceiling_ms": ms_h2d / args.steps,
                 "h2d_gbs_aggregate": world * B * N_POINTS * 13 / (ms_h2d / args.steps * 1e-3) / 1e9,
-                "fraction_of_h2d_ceiling": (ms_h2d / args.steps) / (ms_e2e / args.steps)},
+                "fraction_of_h2d_ceiling": (ms_h2d / args.steps) / (ms_e2e / args.steps),
+                # ... and with the result bytes going back at the same time, as in the real step
+                "copies_ceiling_ms": ms_copies / args.steps,
+                "fraction_of_copies_ceiling": (ms_copies / args.steps) / (ms_e2e / args.steps)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm",

@@ -87,7 +87,7 @@ void Workspace::release() {
     cudaStream_t keep_side = side; cudaEvent_t keep_fork = ev_fork, keep_join = ev_join;
     const StageTimer keep_timer = timer;
     void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, vox_order, slot_rank, tile_cnt, hist, point_voxel, sorted,
-                    mean, cov, cov_final, cls, kl_div, kl_flag, key, seq, firstpos, removed, list_div, list_seq};
+                    mean, cov, cov_final, cls, kl_div, kl_flag, key, seq, firstpos, removed, list_div, list_seq, recip};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = Workspace();
     keep_point_voxels = keep;
@@ -150,6 +150,8 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     A(removed, (size_t)nB * vcap);
     A(list_div, (size_t)nB * kcap);
     A(list_seq, (size_t)nB * kcap);
+    A(recip, (size_t)(nN > 0 ? nN : 1));
+    if ((e = fill_recip_table(recip, nN)) != cudaSuccess) { release(); return e; }
 #undef A
     return cudaSuccess;
 }

@@ -52,6 +52,7 @@ struct CloudState {
     unsigned n_survivors;
     unsigned fail[kWorkers]; // first point of each worker chunk that left the grid (A4), else 0xFFFFFFFF
     unsigned n_heavy;     // voxels with >= kHeavyVoxel points (first n_heavy entries of vox_order)
+    unsigned next_heavy;  // k_stats: next entry of vox_order nobody has taken yet
     int passes;           // guesses that needed a pass over the points (the others were decided by skip_small_grids)
 };
 

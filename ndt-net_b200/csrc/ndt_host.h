@@ -50,6 +50,7 @@ struct Workspace {
     void *sorted = nullptr;
     bool keep_point_voxels = false;   // inspection only: k_rank also records every point's voxel id
     double *mean = nullptr, *cov = nullptr, *cov_final = nullptr;
+    double2 *recip = nullptr;         // {RN(1/c), residual} for c = 1..N_cap (k_stats' divisions by the running count)
     uint16_t *cls = nullptr;
     double *kl_div = nullptr; unsigned char *kl_flag = nullptr;
     unsigned long long *key = nullptr; unsigned *seq = nullptr;
@@ -74,6 +75,7 @@ cudaError_t run_batch(Workspace &w, const void *pts, int dtype, const uint16_t *
 
 size_t cloud_state_size();
 cudaError_t selftest_div(long n, unsigned seed, unsigned long long *mismatches_host);
+cudaError_t fill_recip_table(double2 *tab, long n);
 
 // host copy of the scalar results of one cloud of the last batch
 struct CloudSummary { int status; int len[3]; unsigned V, K, n_valid, walk; int prune_ret; int passes, evals; };

@@ -12,13 +12,10 @@
 #include <cstdlib>
 #include <cstring>
 
-#ifndef NDT_STATS_WARPS
-#define NDT_STATS_WARPS 4
+#ifndef NDT_STATS_WARPS_PER_CLOUD
+#define NDT_STATS_WARPS_PER_CLOUD 3
 #endif
-#ifndef NDT_STATS_MIN_BLOCKS
-#define NDT_STATS_MIN_BLOCKS 4
-#endif
-constexpr int kStatsWarps = NDT_STATS_WARPS;   // warps per CTA of k_stats
+constexpr int kStatsWarpsPerCloud = NDT_STATS_WARPS_PER_CLOUD;   // one-warp CTAs of k_stats that share a cloud's queue of heavy voxels
 constexpr int kSelectThreads = 512;             // k_select: three 512-thread CTAs per SM overlap one another's barriers
 #ifndef NDT_RANK_MATCH_ANY
 #define NDT_RANK_MATCH_ANY 0
@@ -565,6 +562,7 @@ __global__ void __launch_bounds__(1024) k_offsets(CloudState *__restrict__ state
         unsigned run = 0;
         for (int k = 0; k < 32; k++) { const unsigned c = s_hist[k]; s_hist[k] = run; run += c; }
         s.n_heavy = s_hist[__clz(kHeavyVoxel) + 1];      // keys 0..clz(kHeavyVoxel) hold the voxels with n >= kHeavyVoxel
+        s.next_heavy = 0;                                // k_stats' queue of heavy voxels
     }
     __syncthreads();
     for (unsigned v = tid; v < V; v += blockDim.x) {
@@ -632,18 +630,18 @@ __device__ __forceinline__ double div_by_count(double d, double cnt) {
 }
 
 // Shared memory of one warp of k_stats.  Dimension-major rows of 33 doubles: lane k (phase B, staging) touches word 2k of
-// a row, chain / accumulator lane l (phase A) touches row l at a common k; rows are 66 words apart, so both patterns are
-// bank-conflict free.
+// a row, chain / accumulator lane l (phase A) touches row l at a common k; rows are 66 words apart (132 for the reciprocal
+// pairs), so both patterns are bank-conflict free.
 struct StatsWarpSmem {
     double x[kQ][3][33];        // this round's points
     double mu[kQ][3][33];       // means: [.][0] before the round's first point, [.][k+1] after point k
     double t[kQ][6][33];        // terms of the round: m2 x3, c01, c02, c12 (phase A of the next round adds them)
-    double2 r[32];              // 1 / count as an unevaluated sum {rh, rl} (~106 bits), shared by the voxels
+    double2 r[kQ][33];          // 1 / count of this round's points as an unevaluated sum {rh, rl} (~106 bits), per slot
     unsigned h[kQ][kSmemLabelBins];   // label histograms
 };
 
-// Label vote of kQ voxels from a warp's shared-memory histograms (normal_distributions.c:107-121): most frequent class,
-// lowest index on ties, 0 when nothing was counted.  Every lane returns the class of voxel q.
+// Label vote of a voxel from a warp's shared-memory histogram (normal_distributions.c:107-121): most frequent class,
+// lowest index on ties, 0 when nothing was counted.  Every lane returns the class.
 __device__ __forceinline__ unsigned vote_from_hist(const unsigned *h, int nbins, int lane) {
     unsigned best = 0; int bc = 0x7fffffff;
     for (int j = lane; j < nbins; j += 32) { const unsigned x = h[j]; if (x > best) { best = x; bc = j; } }
@@ -656,90 +654,119 @@ __device__ __forceinline__ unsigned vote_from_hist(const unsigned *h, int nbins,
     return best > 0 ? (unsigned)bc : 0u;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
-                                               const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
-                                               const unsigned *__restrict__ vox_order,
-                                               double *__restrict__ mean, double *__restrict__ cov,
-                                               uint16_t *__restrict__ cls, int vote_bins) {
-    // Each warp runs kQ heavy voxels (neighbours in the size-ordered list, so of similar length) in lockstep: the
-    // three mean chains of voxel q sit on lanes 3q..3q+2, its six running sums on lanes 6q..6q+5, so the paced
-    // instruction stream (phase A) is shared by all of them.  vote_bins > 0: the label vote is taken here too, from
-    // the label lane of the same records (shared-memory histogram per voxel, <= kSmemLabelBins classes).
-    const int b = blockIdx.x;
-    const CloudState &s = states[b];
-    if (s.status != 0) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned pair = blockIdx.y * kStatsWarps + warp;
-    if (pair * kQ >= s.n_heavy) return;            // lighter voxels: k_stats_light
-    unsigned vv[kQ], nn[kQ];
-    const T *pp[kQ];
-#pragma unroll
-    for (int q = 0; q < kQ; q++) {
-        const unsigned idx = pair * kQ + q;
-        if (idx < s.n_heavy) {
-            vv[q] = vox_order[(size_t)b * vcap + idx];
-            const unsigned st = vox_start[(size_t)b * (vcap + 1) + vv[q]], en = vox_start[(size_t)b * (vcap + 1) + vv[q] + 1];
-            nn[q] = en - st;
-            pp[q] = sorted + ((size_t)b * N + st) * kSortedStride;
-        } else { vv[q] = 0; nn[q] = 0; pp[q] = sorted; }
+// magnitude tests on the high word (exponent and top mantissa bits) of a double: integer pipe, no fp64 compare
+__device__ __forceinline__ unsigned hi_abs(double u) { return (unsigned)__double2hiint(u) & 0x7fffffffu; }
+__device__ __forceinline__ bool in_recip_range(double u) {
+    // 2^-830 <= |u| < 2^963: inside the range (1e-250, 1e290) for which div_by_count's reciprocal form is proven
+    return hi_abs(u) - 0x0C100000u < 0x70100000u;
+}
+__device__ __forceinline__ bool exp_all_ones(double u) { return (hi_abs(u) & 0x7ff00000u) == 0x7ff00000u; }
+
+// {RN(1/c), RN((1 - c RN(1/c)) RN(1/c))} for c = 1 .. n (index c - 1): the reciprocal pairs of div_by_count, tabulated
+// once per workspace (every voxel of every cloud divides by the same running counts)
+__global__ void k_fill_recip(double2 *__restrict__ tab, long n) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const double c = (double)(i + 1);
+        const double rh = 1.0 / c;
+        tab[i] = make_double2(rh, fma(-c, rh, 1.0) * rh);
     }
+}
 
-    // one StatsWarpSmem per warp (dynamic shared memory: 4 warps x 14 KB exceeds the static limit)
-    extern __shared__ __align__(16) unsigned char s_stats_raw[];
-    StatsWarpSmem &sm = reinterpret_cast<StatsWarpSmem *>(s_stats_raw)[warp];
-    double2 *rs = sm.r;
+// K7 (heavy voxels).  One warp per CTA; the warps of a cloud share a queue of its heavy voxels (vox_order, heaviest first)
+// and each runs kQ of them at a time in lockstep: the three mean chains of slot q sit on lanes 3q..3q+2, its six running
+// sums on lanes 6q..6q+5, so the paced instruction stream (phase A) is shared.  The slots advance independently (each at
+// its own count, reciprocals from the table) and a slot that finishes its voxel pulls the next one from the queue, so the
+// lanes stay busy whatever the spread of voxel sizes.  vote_bins > 0: the label vote is taken here too, from the label
+// lane of the same records (shared-memory histogram per slot, <= kSmemLabelBins classes).
+// grid (B, warps per cloud), block 32.
+template <typename T>
+__global__ void __launch_bounds__(32) k_stats(CloudState *__restrict__ states, unsigned vcap, long N,
+                                              const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
+                                              const unsigned *__restrict__ vox_order, const double2 *__restrict__ recip,
+                                              double *__restrict__ mean, double *__restrict__ cov,
+                                              uint16_t *__restrict__ cls, int vote_bins) {
+    const int b = blockIdx.x;
+    CloudState &s = states[b];
+    if (s.status != 0) return;
+    const unsigned n_heavy = s.n_heavy;
+    if (blockIdx.y * kQ >= n_heavy) return;              // fewer heavy voxels than this warp's first slot: nothing to pull
+    const int lane = threadIdx.x;
+    __shared__ __align__(16) StatsWarpSmem sm;
 
-    const int cq = lane < 3 * kQ ? lane / 3 : kQ - 1, cj = lane < 3 * kQ ? lane % 3 : 2;     // chain lane -> (voxel, dimension)
-    const int aq = lane < 6 * kQ ? lane / 6 : kQ - 1, at = lane < 6 * kQ ? lane % 6 : 5;     // accumulator lane -> (voxel, term)
+    const int cq = lane < 3 * kQ ? lane / 3 : kQ - 1, cj = lane < 3 * kQ ? lane % 3 : 2;     // chain lane -> (slot, dimension)
+    const int aq = lane < 6 * kQ ? lane / 6 : kQ - 1, at = lane < 6 * kQ ? lane % 6 : 5;     // accumulator lane -> (slot, term)
     const bool chain_lane = lane < 3 * kQ, acc_lane = lane < 6 * kQ, cov_lane = acc_lane && at >= 3;
     const double *xs = sm.x[cq][cj];
     double *mus = sm.mu[cq][cj];
     const double *tp = sm.t[aq][at];
+    const double2 *rs = sm.r[cq];
     double mu = 0.0, acc = 0.0;
-    if (chain_lane) mus[0] = 0.0;
-    if (vote_bins > 0) {
-#pragma unroll
-        for (int q = 0; q < kQ; q++)
-            for (int j = lane; j < kSmemLabelBins; j += 32) sm.h[q][j] = 0u;
-    }
-    unsigned nmax = 0;
-    int prev_m[kQ];
-#pragma unroll
-    for (int q = 0; q < kQ; q++) { nmax = nn[q] > nmax ? nn[q] : nmax; prev_m[q] = 0; }
-    bool prev_chk = false;                 // previous round produced a non-finite term: add with the NaN rule
-    bool fin_mu = false, fin_acc = false;  // this lane's voxel is finished: its result is parked in mu_fin / acc_fin
-    double mu_fin = 0.0, acc_fin = 0.0;    // (the straight-line rounds of the longer voxel keep clobbering mu / acc)
-    T nx[kQ][3];                           // the next round's point of this lane (per voxel), fetched one round ahead
-    unsigned nl[kQ];                       // ... and its label
-#pragma unroll
-    for (int q = 0; q < kQ; q++)
-    {
-        nx[q][0] = nx[q][1] = nx[q][2] = 0; nl[q] = 0;
-        if ((unsigned)lane < nn[q]) load_sorted_rec<T>(pp[q] + lane * kSortedStride, nx[q][0], nx[q][1], nx[q][2], nl[q]);
-        if ((unsigned)lane + 32u < nn[q]) prefetch_l2(pp[q] + (size_t)(lane + 32) * kSortedStride);
-        if ((unsigned)lane + 64u < nn[q]) prefetch_l2(pp[q] + (size_t)(lane + 64) * kSortedStride);
-    }
 
-    for (unsigned base = 0; base < nmax; base += 32) {
-        int m[kQ];
+    // per-slot state, identical in every lane
+    unsigned vv[kQ], nn[kQ], base[kQ];
+    const T *pp[kQ];
+    int prev_m[kQ];
+    bool live[kQ];
+    T nx[kQ][3];                           // the next round's point of this lane (per slot), fetched one round ahead
+    unsigned nl[kQ];                       // ... its label
+    double2 nr[kQ];                        // ... and the reciprocal pair of its count
 #pragma unroll
-        for (int q = 0; q < kQ; q++) m[q] = base >= nn[q] ? 0 : (int)(nn[q] - base < 32u ? nn[q] - base : 32u);
-        const double c = (double)(base + lane + 1);
-        const double rh = 1.0 / c;
-        const double rl = fma(-c, rh, 1.0) * rh;
-        rs[lane] = make_double2(rh, rl);
+    for (int q = 0; q < kQ; q++) { vv[q] = 0; nn[q] = 0; base[q] = 0; pp[q] = sorted; prev_m[q] = 0; live[q] = false;
+                                   nx[q][0] = nx[q][1] = nx[q][2] = 0; nl[q] = 0; nr[q] = make_double2(0.0, 0.0); }
+    bool queue_empty = false;
+    bool prev_chk = false;                 // previous round produced a non-finite term: add with the NaN rule
+
+    while (true) {
+        // ---- refill: an idle slot takes the next heavy voxel of the cloud
+        bool any_live = false;
 #pragma unroll
         for (int q = 0; q < kQ; q++) {
+            if (!live[q] && !queue_empty) {
+                unsigned idx = 0;
+                if (lane == 0) idx = atomicAdd(&s.next_heavy, 1u);
+                idx = __shfl_sync(0xffffffffu, idx, 0);
+                if (idx >= n_heavy) queue_empty = true;
+                else {
+                    vv[q] = vox_order[(size_t)b * vcap + idx];
+                    const unsigned st = vox_start[(size_t)b * (vcap + 1) + vv[q]], en = vox_start[(size_t)b * (vcap + 1) + vv[q] + 1];
+                    nn[q] = en - st; base[q] = 0;
+                    pp[q] = sorted + ((size_t)b * N + st) * kSortedStride;
+                    live[q] = true;
+                    // the slot's first round adds 32 zero terms, so that it can take the straight path like any full round
+                    prev_m[q] = 32;
+#pragma unroll
+                    for (int t = 0; t < 6; t++) sm.t[q][t][lane] = 0.0;
+                    if (chain_lane && cq == q) { mu = 0.0; mus[0] = 0.0; }
+                    if (acc_lane && aq == q) acc = 0.0;
+                    if (vote_bins > 0) for (int j = lane; j < kSmemLabelBins; j += 32) sm.h[q][j] = 0u;
+                    nx[q][0] = nx[q][1] = nx[q][2] = 0; nl[q] = 0;
+                    if ((unsigned)lane < nn[q]) { load_sorted_rec<T>(pp[q] + lane * kSortedStride, nx[q][0], nx[q][1], nx[q][2], nl[q]); nr[q] = recip[lane]; }
+                    if ((unsigned)lane + 32u < nn[q]) prefetch_l2(pp[q] + (size_t)(lane + 32) * kSortedStride);
+                    if ((unsigned)lane + 64u < nn[q]) prefetch_l2(pp[q] + (size_t)(lane + 64) * kSortedStride);
+                }
+            }
+            any_live = any_live || live[q];
+        }
+        if (!any_live) break;
+
+        // ---- staging: this round's points, reciprocal pairs and labels; the next round's loads are issued now
+        int m[kQ];
+        double2 rq[kQ];                    // reciprocal pair of this lane's point (phase B)
+#pragma unroll
+        for (int q = 0; q < kQ; q++) {
+            m[q] = live[q] ? (int)(nn[q] - base[q] < 32u ? nn[q] - base[q] : 32u) : 0;
+            rq[q] = nr[q];
             if (lane < m[q]) {
 #pragma unroll
                 for (int j = 0; j < 3; j++) sm.x[q][j][lane] = (double)nx[q][j];
+                sm.r[q][lane] = rq[q];
                 if (vote_bins > 0 && nl[q] < (unsigned)vote_bins) atomicAdd(&sm.h[q][nl[q]], 1u);
             }
             // a round lasts about one DRAM round trip: pull the records of the round after the next two into L2 now
-            if (base + 96 + lane < nn[q]) prefetch_l2(pp[q] + (size_t)(base + 96 + lane) * kSortedStride);
-            if (base + 32 + lane < nn[q]) {      // issue the next round's global loads now; they land during phase A
-                load_sorted_rec<T>(pp[q] + (size_t)(base + 32 + lane) * kSortedStride, nx[q][0], nx[q][1], nx[q][2], nl[q]);
+            if (live[q] && base[q] + 96 + lane < nn[q]) prefetch_l2(pp[q] + (size_t)(base[q] + 96 + lane) * kSortedStride);
+            if (live[q] && base[q] + 32 + lane < nn[q]) {
+                load_sorted_rec<T>(pp[q] + (size_t)(base[q] + 32 + lane) * kSortedStride, nx[q][0], nx[q][1], nx[q][2], nl[q]);
+                nr[q] = recip[base[q] + 32 + lane];
             }
         }
         __syncwarp();
@@ -751,14 +778,12 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
         //      not, the round is redone with the IEEE division.
         const double mu_start = mu;
         const int my_m = m[cq], my_pm = prev_m[aq];
-        if (!fin_mu && m[cq] == 0) { fin_mu = true; mu_fin = mu; }
-        if (!fin_acc && m[aq] == 0 && prev_m[aq] == 0) { fin_acc = true; acc_fin = acc; }
-        bool straight = !prev_chk;             // every voxel is either in a full round after a full round, or finished
+        bool straight = !prev_chk;             // every slot is in a full round after a full round, or idle
 #pragma unroll
         for (int q = 0; q < kQ; q++) straight = straight && ((m[q] == 32 && prev_m[q] == 32) || (m[q] == 0 && prev_m[q] == 0));
         if (straight) {
             // full rounds: straight-line, no per-step predicates; the operands of the next two points are fetched while
-            // the current two are on the chain
+            // the current two are on the chain (an idle slot's lanes compute on stale rows; they are reset at refill)
             double xv[2], tv[2], xn[2], tn[2];
             double2 rv[2], rn[2];
 #pragma unroll
@@ -781,7 +806,8 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
                 for (int j = 0; j < 2; j++) { xv[j] = xn[j]; rv[j] = rn[j]; tv[j] = tn[j]; }
             }
         } else {
-            // first / last rounds of a voxel, or a round after non-finite terms: per-lane predicates
+            // last (partial) round of a voxel, the round after it (only the sums move), or a round after non-finite
+            // terms: per-lane predicates
             for (int k = 0; k < 32; k++) {
                 if (k < my_m) {
                     const double xk = xs[k];
@@ -797,11 +823,13 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
             }
         }
         __syncwarp();
-        // ---- B: per-point terms, all lanes in parallel, one voxel after the other; also validates the operands
+        // ---- B: per-point terms, all lanes in parallel, one slot after the other; also validates the operands
         bool nonfinite = false;
 #pragma unroll
         for (int q = 0; q < kQ; q++) {
+            if (m[q] == 0) continue;
             bool redone = false;
+            const double rh = rq[q].x, rl = rq[q].y;
             while (true) {
                 bool bad = false;
                 if (lane < m[q]) {
@@ -810,31 +838,32 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
                     const double n0 = mq[0][lane + 1], n1 = mq[1][lane + 1], n2 = mq[2][lane + 1];
                     const double x0 = sm.x[q][0][lane], x1 = sm.x[q][1][lane], x2 = sm.x[q][2][lane];
                     const double d0 = x0 - o0, d1 = x1 - o1, d2 = x2 - o2;          // the chain's d, bit for bit
-                    const double a0 = fabs(d0), a1 = fabs(d1), a2 = fabs(d2);
-                    bad = !(a0 > 1e-250 && a0 < 1e290 && a0 * 4194304.0 >= fabs(x0)) ||
-                          !(a1 > 1e-250 && a1 < 1e290 && a1 * 4194304.0 >= fabs(x1)) ||
-                          !(a2 > 1e-250 && a2 < 1e290 && a2 * 4194304.0 >= fabs(x2));
+                    // the chain's reciprocal form needs |d| inside its proven range and |d| 2^22 >= |x| (on the high words:
+                    // a strict inequality there implies the real one; the few equal cases just take the redo)
+                    bad = !(in_recip_range(d0) && hi_abs(d0) + 0x01600000u > hi_abs(x0)) ||
+                          !(in_recip_range(d1) && hi_abs(d1) + 0x01600000u > hi_abs(x1)) ||
+                          !(in_recip_range(d2) && hi_abs(d2) + 0x01600000u > hi_abs(x2));
                     double(*t)[33] = sm.t[q];
                     const double e0 = x0 - n0, e1 = x1 - n1;
                     const double t0 = d0 * e0, t1 = d1 * e1, t2 = d2 * (x2 - n2);
                     // (x_j - new_j)(x_k - old_k) / count: mu_k (k > j) is not yet updated when dimension j runs
                     const double p01 = e0 * d1, p02 = e0 * d2, p12 = e1 * d2;
                     double q01 = fma(p01, rh, p01 * rl), q02 = fma(p02, rh, p02 * rl), q12 = fma(p12, rh, p12 * rl);
-                    {
-                        const double b0 = fabs(p01), b1 = fabs(p02), b2 = fabs(p12);
-                        const bool ok = b0 > 1e-250 && b0 < 1e290 && b1 > 1e-250 && b1 < 1e290 && b2 > 1e-250 && b2 < 1e290;
-                        if (!ok) { q01 = p01 / c; q02 = p02 / c; q12 = p12 / c; }     // zeros, tiny or huge products: IEEE division
+                    if (!(in_recip_range(p01) && in_recip_range(p02) && in_recip_range(p12))) {
+                        const double c = (double)(base[q] + lane + 1);
+                        q01 = p01 / c; q02 = p02 / c; q12 = p12 / c;                   // zeros, tiny or huge products: IEEE division
                     }
                     t[0][lane] = t0; t[1][lane] = t1; t[2][lane] = t2; t[3][lane] = q01; t[4][lane] = q02; t[5][lane] = q12;
-                    const double big = 1.7976931348623157e308;
-                    nonfinite |= !(fabs(t0) <= big && fabs(t1) <= big && fabs(t2) <= big && fabs(q01) <= big && fabs(q02) <= big && fabs(q12) <= big);
+                    unsigned hm = hi_abs(t0);
+                    hm = max(hm, hi_abs(t1)); hm = max(hm, hi_abs(t2)); hm = max(hm, hi_abs(q01)); hm = max(hm, hi_abs(q02)); hm = max(hm, hi_abs(q12));
+                    nonfinite |= hm >= 0x7ff00000u;
                 }
                 if (redone || !__any_sync(0xffffffffu, bad)) break;
-                // rare: redo this voxel's round with the IEEE division on its three chain lanes, then its terms
+                // rare: redo this slot's round with the IEEE division on its three chain lanes, then its terms
                 if (chain_lane && cq == q) {
                     mu = mu_start;
                     for (int k = 0; k < m[q]; k++) {
-                        const double cnt = (double)(base + k + 1);
+                        const double cnt = (double)(base[q] + k + 1);
                         mu = mu + (xs[k] - mu) / cnt;
                         mus[k + 1] = mu;
                     }
@@ -845,40 +874,32 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
         }
         prev_chk = __any_sync(0xffffffffu, nonfinite);
         __syncwarp();
+        // ---- advance the slots; a slot whose last terms were just added writes its voxel out
         if (chain_lane && my_m > 0) mus[0] = mus[my_m];
 #pragma unroll
-        for (int q = 0; q < kQ; q++) prev_m[q] = m[q];
+        for (int q = 0; q < kQ; q++) {
+            if (!live[q]) continue;
+            if (m[q] > 0) { base[q] += (unsigned)m[q]; prev_m[q] = m[q]; continue; }
+            // variances m2 / n (normal_distributions.c:86-89), NaN -> 0
+            const double cntn = (double)nn[q];
+            double var = acc / cntn;
+            if (var != var) var = 0.0;
+            const double out = (acc_lane && at < 3) ? var : acc;
+            const double v0 = __shfl_sync(0xffffffffu, out, q * 6 + 0), v1 = __shfl_sync(0xffffffffu, out, q * 6 + 1), v2 = __shfl_sync(0xffffffffu, out, q * 6 + 2);
+            const double c01 = __shfl_sync(0xffffffffu, out, q * 6 + 3), c02 = __shfl_sync(0xffffffffu, out, q * 6 + 4), c12 = __shfl_sync(0xffffffffu, out, q * 6 + 5);
+            const double m0 = __shfl_sync(0xffffffffu, mu, q * 3 + 0), m1 = __shfl_sync(0xffffffffu, mu, q * 3 + 1), m2 = __shfl_sync(0xffffffffu, mu, q * 3 + 2);
+            unsigned label = 0;
+            if (vote_bins > 0) label = vote_from_hist(sm.h[q], vote_bins, lane);
+            if (lane == 0) {
+                double *mo = mean + ((size_t)b * vcap + vv[q]) * 3;
+                mo[0] = m0; mo[1] = m1; mo[2] = m2;
+                double *co = cov + ((size_t)b * vcap + vv[q]) * 9;
+                co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
+                if (vote_bins > 0) cls[(size_t)b * vcap + vv[q]] = (uint16_t)label;
+            }
+            live[q] = false; prev_m[q] = 0;
+        }
         __syncwarp();
-    }
-    {   // C for the last round of each voxel (a shorter voxel's last terms were already added: its prev_m became 0)
-        const int my_pm = prev_m[aq];
-        for (int k = 0; k < my_pm; k++) {
-            const double a2 = acc + tp[k];
-            acc = (cov_lane && a2 != a2) ? 0.0 : a2;
-        }
-    }
-    if (fin_mu) mu = mu_fin;
-    if (fin_acc) acc = acc_fin;
-    // variances m2 / n (normal_distributions.c:86-89), NaN -> 0
-#pragma unroll
-    for (int q = 0; q < kQ; q++) {
-        if (nn[q] == 0) continue;
-        const double cntn = (double)nn[q];
-        double var = acc / cntn;
-        if (var != var) var = 0.0;
-        const double out = (acc_lane && at < 3) ? var : acc;
-        const double v0 = __shfl_sync(0xffffffffu, out, q * 6 + 0), v1 = __shfl_sync(0xffffffffu, out, q * 6 + 1), v2 = __shfl_sync(0xffffffffu, out, q * 6 + 2);
-        const double c01 = __shfl_sync(0xffffffffu, out, q * 6 + 3), c02 = __shfl_sync(0xffffffffu, out, q * 6 + 4), c12 = __shfl_sync(0xffffffffu, out, q * 6 + 5);
-        const double m0 = __shfl_sync(0xffffffffu, mu, q * 3 + 0), m1 = __shfl_sync(0xffffffffu, mu, q * 3 + 1), m2 = __shfl_sync(0xffffffffu, mu, q * 3 + 2);
-        unsigned label = 0;
-        if (vote_bins > 0) label = vote_from_hist(sm.h[q], vote_bins, lane);
-        if (lane == 0) {
-            double *mo = mean + ((size_t)b * vcap + vv[q]) * 3;
-            mo[0] = m0; mo[1] = m1; mo[2] = m2;
-            double *co = cov + ((size_t)b * vcap + vv[q]) * 9;
-            co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
-            if (vote_bins > 0) cls[(size_t)b * vcap + vv[q]] = (uint16_t)label;
-        }
     }
 }
 
@@ -889,13 +910,6 @@ __global__ void __launch_bounds__(32 * kStatsWarps, NDT_STATS_MIN_BLOCKS) k_stat
 // of a warp is at the same count; see div_by_count for why the reciprocal form is the correctly rounded quotient).
 // vote_bins > 0: the label vote (normal_distributions.c:107-121) is taken here too, in per-thread 16-bit counters.
 // grid (ceil(vcap/128), B), block 128, dynamic smem vote_bins * 128 * 2 bytes.
-__device__ __forceinline__ bool in_recip_range(double u) {
-    // 2^-830 <= |u| < 2^963: inside the range (1e-250, 1e290) for which div_by_count's reciprocal form is proven
-    const unsigned h = (unsigned)__double2hiint(u) & 0x7fffffffu;
-    return h - 0x0C100000u < 0x70100000u;
-}
-__device__ __forceinline__ bool exp_all_ones(double u) { return ((unsigned)__double2hiint(u) & 0x7ff00000u) == 0x7ff00000u; }
-
 template <typename T>
 __global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restrict__ states, unsigned vcap, long N,
                                                      const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
@@ -1401,6 +1415,12 @@ __global__ void k_selftest_div(long n, unsigned seed, unsigned long long *mismat
     if (bad) atomicAdd(mismatches, bad);
 }
 
+cudaError_t fill_recip_table(double2 *tab, long n) {
+    if (n <= 0) return cudaSuccess;
+    k_fill_recip<<<(unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256>>>(tab, n);
+    return cudaDeviceSynchronize();
+}
+
 cudaError_t selftest_div(long n, unsigned seed, unsigned long long *mismatches_host) {
     unsigned long long *d = nullptr;
     cudaError_t e = cudaMalloc((void **)&d, 8);
@@ -1495,17 +1515,10 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         // label vote: taken inside the statistics kernels from the label lane of the records they read anyway when the
         // class count fits their shared-memory counters; wide label sets were counted by k_scatter's global atomics
         const int vote_bins = labels && !wide_labels ? nbins : 0;
-        constexpr size_t stats_smem = sizeof(StatsWarpSmem) * kStatsWarps;
-        {
-            static bool attr_set[64] = {};   // function attributes are per device
-            int dev = 0; cudaGetDevice(&dev);
-            if (!attr_set[dev & 63]) {
-                CK(cudaFuncSetAttribute(k_stats<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_smem));
-                attr_set[dev & 63] = true;
-            }
-        }
-        k_stats<T><<<dim3(B, (max_pairs + kStatsWarps - 1) / kStatsWarps), 32 * kStatsWarps, stats_smem, st>>>(
-            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
+        (void)max_pairs;
+        static const int stats_warps = [] { const char *e = getenv("NDNET_B200_STATS_WARPS"); const int v = e ? atoi(e) : 0; return v > 0 && v <= 64 ? v : kStatsWarpsPerCloud; }();
+        k_stats<T><<<dim3(B, stats_warps), 32, 0, st>>>(
+            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.recip, w.mean, w.cov, w.cls, vote_bins);
         DBG("k_stats");
         k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, (size_t)vote_bins * 128 * sizeof(unsigned short), w.side>>>(
             w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
