@@ -36,6 +36,9 @@ struct ndnet_b200_ctx {
     struct Lane {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
+        cudaEvent_t copied = nullptr;     // this lane's input chunk has arrived (recorded on the copy stream)
+        cudaEvent_t consumed = nullptr;   // the kernels that read this lane's input buffers have been enqueued up to here
+        bool used = false;
         Workspace ws;
         mlp::Scratch scratch;
         void *d_points = nullptr; size_t d_points_bytes = 0;
@@ -48,6 +51,10 @@ struct ndnet_b200_ctx {
     int chunk = 64;          // scans per chunk of ndnet_b200_infer_host (copies overlap kernels: more, smaller chunks)
     int chunk_device = 128;  // scans per chunk of ndnet_b200_infer_device (no copies to hide: fewer, larger chunks)
     cudaEvent_t start_ev = nullptr;
+    // host -> device copies of ndnet_b200_infer_host all go through ONE stream, in chunk order: copies issued on the lanes'
+    // own streams are served concurrently by the copy engine, so every chunk's data would arrive near the end of the
+    // step and the kernels could not overlap the transfer
+    cudaStream_t copy_stream = nullptr;
 };
 
 namespace {
@@ -192,9 +199,12 @@ extern "C" void ndnet_b200_destroy(ndnet_b200_ctx *c) {
         void *lp[] = {l.d_points, l.d_labels, l.d_feat, l.d_logits};
         for (void *p : lp) if (p) cudaFree(p);
         if (l.done) cudaEventDestroy(l.done);
+        if (l.copied) cudaEventDestroy(l.copied);
+        if (l.consumed) cudaEventDestroy(l.consumed);
         if (l.stream) cudaStreamDestroy(l.stream);
     }
     if (c->start_ev) cudaEventDestroy(c->start_ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -331,12 +341,16 @@ static int infer_pipelined(ndnet_b200_ctx *c, ndnet_b200_model *model, const voi
         for (auto &l : c->lanes) {
             if ((e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(c, e, "stream create");
             if ((e = cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming)) != cudaSuccess) return fail(c, e, "event create");
+            if ((e = cudaEventCreateWithFlags(&l.copied, cudaEventDisableTiming)) != cudaSuccess) return fail(c, e, "event create");
+            if ((e = cudaEventCreateWithFlags(&l.consumed, cudaEventDisableTiming)) != cudaSuccess) return fail(c, e, "event create");
         }
+        if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(c, e, "stream create");
         if ((e = cudaEventCreateWithFlags(&c->start_ev, cudaEventDisableTiming)) != cudaSuccess) return fail(c, e, "event create");
     }
     const size_t esz = dtype == 0 ? 4 : 8;
     // everything already enqueued on the caller's stream happens before the lanes start
     if ((e = cudaEventRecord(c->start_ev, user)) != cudaSuccess) return fail(c, e, "event record");
+    if (host_io && (e = cudaStreamWaitEvent(c->copy_stream, c->start_ev, 0)) != cudaSuccess) return fail(c, e, "stream wait");
     const int L = (int)c->lanes.size();
     // chunk size: host buffers - at most c->chunk, and a small batch is spread over all lanes so that every copy overlaps
     // kernels; device buffers - c->chunk_device (measured on B200, 512 scans: 4 x 128 beats 8 x 64 by 3-4 %, 1 x 512 loses 3 %)
@@ -356,14 +370,22 @@ static int infer_pipelined(ndnet_b200_ctx *c, ndnet_b200_model *model, const voi
             if ((e = grow(l.d_points, l.d_points_bytes, (size_t)nb * N * 3 * esz)) != cudaSuccess) return fail(c, e, "lane allocation");
             if (labels && (e = grow(l.d_labels, l.d_labels_bytes, (size_t)nb * N * lsz)) != cudaSuccess) return fail(c, e, "lane allocation");
             if ((e = grow(l.d_logits, l.d_logits_bytes, (size_t)nb * out_elems_per_cloud * 4)) != cudaSuccess) return fail(c, e, "lane allocation");
-            if ((e = cudaMemcpyAsync(l.d_points, psrc, (size_t)nb * N * 3 * esz, cudaMemcpyHostToDevice, l.stream)) != cudaSuccess) return fail(c, e, "H2D points");
-            if (labels && (e = cudaMemcpyAsync(l.d_labels, lsrc, (size_t)nb * N * lsz, cudaMemcpyHostToDevice, l.stream)) != cudaSuccess) return fail(c, e, "H2D labels");
+            // in chunk order on the copy stream; the lane's buffers are free once its previous kernels have read them
+            if (l.used && (e = cudaStreamWaitEvent(c->copy_stream, l.consumed, 0)) != cudaSuccess) return fail(c, e, "stream wait");
+            if ((e = cudaMemcpyAsync(l.d_points, psrc, (size_t)nb * N * 3 * esz, cudaMemcpyHostToDevice, c->copy_stream)) != cudaSuccess) return fail(c, e, "H2D points");
+            if (labels && (e = cudaMemcpyAsync(l.d_labels, lsrc, (size_t)nb * N * lsz, cudaMemcpyHostToDevice, c->copy_stream)) != cudaSuccess) return fail(c, e, "H2D labels");
+            if ((e = cudaEventRecord(l.copied, c->copy_stream)) != cudaSuccess) return fail(c, e, "event record");
+            if ((e = cudaStreamWaitEvent(l.stream, l.copied, 0)) != cudaSuccess) return fail(c, e, "stream wait");
             dp = l.d_points; dl = labels ? l.d_labels : nullptr; dout = l.d_logits;
         }
         if ((e = l.ws.reserve(nb, N, D, num_classes + 1)) != cudaSuccess) return fail(c, e, "lane workspace allocation");
         l.ws.last_B = nb; l.ws.last_N = N; l.ws.last_D = D;
         if ((e = ndt::run_batch(l.ws, dp, dtype, dl, nb, N, num_classes, D, NDNET_B200_NAN_TO_NUM | label_flags, l.d_feat, nullptr, nullptr, nullptr,
                                 nullptr, l.stream)) != cudaSuccess) return fail(c, e, "ndt::run_batch");
+        if (host_io) {       // the NDT kernels are the only readers of the lane's input buffers
+            if ((e = cudaEventRecord(l.consumed, l.stream)) != cudaSuccess) return fail(c, e, "event record");
+            l.used = true;
+        }
         std::string err;
         int r = model->m.forward(l.scratch, l.d_feat, nb, (int)D, dout, l.stream, err);
         if (r != 0) { c->err = err; fprintf(stderr, "ndnet_b200_infer: %s\n", err.c_str()); return r; }

@@ -460,7 +460,7 @@ void Model::release() {
 namespace {
 
 template <int BN, int STAGES>
-bool launch_gemm(const CUtensorMap &a, const CUtensorMap &b, const GemmArgs &g, dim3 grid, cudaStream_t st) {
+bool launch_gemm(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &c, const GemmArgs &g, dim3 grid, cudaStream_t st) {
     static bool attr[64] = {};          // function attributes are per device
     constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
     int dev = 0; cudaGetDevice(&dev);
@@ -468,7 +468,7 @@ bool launch_gemm(const CUtensorMap &a, const CUtensorMap &b, const GemmArgs &g, 
         if (cudaFuncSetAttribute(k_gemm<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
         attr[dev & 63] = true;
     }
-    k_gemm<BN, STAGES><<<grid, kGemmThreads, smem, st>>>(a, b, g);
+    k_gemm<BN, STAGES><<<grid, kGemmThreads, smem, st>>>(a, b, c, g);
     return cudaGetLastError() == cudaSuccess;
 }
 
@@ -482,21 +482,24 @@ struct Fwd {
               int ldcb, bool relu, __nv_bfloat16 *out) {
         if (!ok) return;
         const int BN = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
-        CUtensorMap ma, mb;
-        if (!make_map(&ma, act, K, P, B, 128) || !make_map(&mb, w, K, N, w_batched ? B : 1, BN)) { ok = false; *err = "cuTensorMapEncodeTiled failed"; return; }
+        CUtensorMap ma, mb, mc;
+        if (N % 64 != 0) { ok = false; *err = "rows(): the output width must be a multiple of 64 (TMA store boxes)"; return; }
+        if (!make_map(&ma, act, K, P, B, 128) || !make_map(&mb, w, K, N, w_batched ? B : 1, BN) || !make_map(&mc, out, N, P, B, 128)) {
+            ok = false; *err = "cuTensorMapEncodeTiled failed"; return;
+        }
         GemmArgs g{}; g.K = K; g.P = P; g.a_batched = 1; g.b_batched = w_batched ? 1 : 0; g.mode = MODE_ROWS; g.relu = relu ? 1 : 0; g.n_valid = N;
         g.bias = bias; g.cbias = cbias; g.ldcb = ldcb; g.out = out; g.ldo = N;
         dim3 grid((N + BN - 1) / BN, (P + 127) / 128, B);
         // one k-block (K = 64): a single stage keeps the CTA at 24-48 KB of shared memory so several CTAs share an SM
         // and one CTA's epilogue overlaps another's load/MMA; deeper K: two stages (still 2 CTAs per SM at BN = 256)
         if (K <= 64) {
-            if (BN == 256) ok = launch_gemm<256, 1>(ma, mb, g, grid, st);
-            else if (BN == 128) ok = launch_gemm<128, 1>(ma, mb, g, grid, st);
-            else ok = launch_gemm<64, 1>(ma, mb, g, grid, st);
+            if (BN == 256) ok = launch_gemm<256, 1>(ma, mb, mc, g, grid, st);
+            else if (BN == 128) ok = launch_gemm<128, 1>(ma, mb, mc, g, grid, st);
+            else ok = launch_gemm<64, 1>(ma, mb, mc, g, grid, st);
         } else {
-            if (BN == 256) ok = launch_gemm<256, 2>(ma, mb, g, grid, st);
-            else if (BN == 128) ok = launch_gemm<128, 2>(ma, mb, g, grid, st);
-            else ok = launch_gemm<64, 2>(ma, mb, g, grid, st);
+            if (BN == 256) ok = launch_gemm<256, 2>(ma, mb, mc, g, grid, st);
+            else if (BN == 128) ok = launch_gemm<128, 2>(ma, mb, mc, g, grid, st);
+            else ok = launch_gemm<64, 2>(ma, mb, mc, g, grid, st);
         }
         if (!ok) *err = "gemm launch failed";
         gemm_launches++;
@@ -526,7 +529,7 @@ struct Fwd {
         if (!make_map(&ma, act, K, P, B, 128) || !make_map(&mb, w, K, N, 1, 32)) { ok = false; *err = "cuTensorMapEncodeTiled failed"; return; }
         GemmArgs g{}; g.K = K; g.P = P; g.a_batched = 1; g.b_batched = 0; g.mode = MODE_LOGSM; g.n_valid = N; g.bias = bias; g.outf = out;
         dim3 grid(1, (P + 127) / 128, B);
-        ok = launch_gemm<32, 2>(ma, mb, g, grid, st);
+        ok = launch_gemm<32, 2>(ma, mb, ma, g, grid, st);
         if (!ok) *err = "gemm launch failed";
         gemm_launches++;
     }

@@ -54,17 +54,21 @@ __host__ __device__ __forceinline__ float dec_f32(unsigned u) {
 }
 
 
+// operand stages; MODE_ROWS re-uses them (all MMAs have retired) to stage the 128 x BN bf16 output tile for the TMA store
 template <int BN, int STAGES>
-constexpr size_t gemm_smem_bytes() { return (size_t)STAGES * (128 + BN) * 128 + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias tile*/; }
+__host__ __device__ constexpr size_t gemm_stage_bytes() { return (size_t)STAGES * (128 + BN) * 128 > (size_t)BN * 256 ? (size_t)STAGES * (128 + BN) * 128 : (size_t)BN * 256; }
+template <int BN, int STAGES>
+__host__ __device__ constexpr size_t gemm_smem_bytes() { return gemm_stage_bytes<BN, STAGES>() + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias tile*/; }
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads)
-k_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs args) {
+k_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapC,
+       const GemmArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;                               // STAGES x 16 KB
     uint8_t *sB = smem + (size_t)STAGES * 128 * 128;  // STAGES x BN*128 B
-    uint64_t *bars = (uint64_t *)(sB + (size_t)STAGES * BN * 128);
+    uint64_t *bars = (uint64_t *)(smem + gemm_stage_bytes<BN, STAGES>());
     uint64_t *full = bars, *empty = bars + STAGES, *tmem_full = bars + 2 * STAGES;
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 1);
     float *s_bias = (float *)(bars + 2 * STAGES + 2);   // BN floats: bias (+ per-cloud bias) of this tile's columns
@@ -83,7 +87,7 @@ k_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtenso
         ptx::mbar_init(tmem_full, 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&mapA); ptx::prefetch_tmap(&mapB); }
+    if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&mapA); ptx::prefetch_tmap(&mapB); if (args.mode == MODE_ROWS) ptx::prefetch_tmap(&mapC); }
     if (args.mode == MODE_ROWS && threadIdx.x < 128) {
         const float *cb = args.cbias ? args.cbias + (size_t)b * args.ldcb : nullptr;
         for (int i = threadIdx.x; i < BN; i += 128) {
@@ -152,9 +156,11 @@ k_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtenso
                 atomicMax(&args.gmax[(size_t)b * args.ldg + ch], enc_f32(r));
             }
         } else if (args.mode == MODE_ROWS) {
-            const int row = a_row0 + m;
-            const bool row_ok = row < args.P;
-            __nv_bfloat16 *orow = args.out + ((size_t)b * args.P + (row_ok ? row : 0)) * args.ldo + b_row0;
+            // The bf16 tile goes to shared memory in the 128B-swizzled box layout of the output tensor map (one 128 x 64
+            // sub-tile per 64 columns; 16-byte chunk c of row r sits at chunk c ^ (r & 7), so the eight rows of a quarter
+            // warp hit eight different bank groups), then ONE thread hands it to the TMA: full 128-byte lines leave the SM
+            // instead of 128 row-strided 16-byte stores per column chunk.  Rows past the cloud are clipped by the TMA.
+            uint8_t *stage = smem;                     // operand stages are dead: every MMA of this tile has retired
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
@@ -171,11 +177,20 @@ k_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtenso
                     __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
                     packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
                 }
-                if (row_ok) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
+                uint8_t *sub = stage + (size_t)(c0 >> 6) * 16384 + (size_t)m * 128;
+                const int chunk0 = (c0 & 63) >> 3;       // first of this step's four 16-byte chunks within the 128-byte row
 #pragma unroll
-                    for (int q = 0; q < 4; q++) dst[q] = make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
-                }
+                for (int q = 0; q < 4; q++)
+                    *reinterpret_cast<uint4 *>(sub + (((chunk0 + q) ^ (m & 7)) << 4)) =
+                        make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+            }
+            ptx::fence_proxy_async_smem();
+            ptx::named_barrier_sync(1, 128);             // the four epilogue warps only
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int st = 0; st < BN / 64; st++) ptx::tma_store_3d(&mapC, stage + (size_t)st * 16384, b_row0 + st * 64, a_row0, b);
+                ptx::tma_store_commit();
+                ptx::tma_store_wait_read();              // the CTA's shared memory must outlive the TMA's reads
             }
         } else {   // MODE_LOGSM: BN == 32, the whole row is in this thread
             const int row = a_row0 + m;
@@ -298,19 +313,42 @@ k_gemm_chmax(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             ptx::mbar_wait(&t_full[buf], (uint32_t)(t >> 1) & 1u);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 256);
+            if (valid == 64) {
+                // full tile of points: the 64 accumulator columns of channel tile ct+1 are in flight (tcgen05.ld is
+                // asynchronous) while the 64 of tile ct go through the running max, so the TMEM read latency is paid once
+                // per point tile instead of eight times
+                uint32_t a0[32], a1[32], b0[32], b1[32];
+                ptx::tmem_ld32(taddr, a0);
+                ptx::tmem_ld32(taddr + 32u, a1);
+                ptx::tmem_ld_wait();
+                ptx::tmem_ld_fence(a0); ptx::tmem_ld_fence(a1);
 #pragma unroll
-            for (int ct = 0; ct < 4; ct++) {
-                if (ct < ntile) {
+                for (int ct = 0; ct < 4; ct++) {
+                    if (ct < ntile) {
+                        const bool more = ct + 1 < ntile;
+                        if ((ct & 1) == 0) {
+                            if (more) { ptx::tmem_ld32(taddr + (uint32_t)((ct + 1) * 64), b0); ptx::tmem_ld32(taddr + (uint32_t)((ct + 1) * 64 + 32), b1); }
 #pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 32) {
-                        if (c0 < valid) {
-                            uint32_t v[32];
-                            ptx::tmem_ld32(taddr + (uint32_t)(ct * 64 + c0), v);
-                            ptx::tmem_ld_wait();
-                            if (c0 + 32 <= valid) {
+                            for (int j = 0; j < 32; j++) best[ct] = fmaxf(best[ct], fmaxf(__uint_as_float(a0[j]), __uint_as_float(a1[j])));
+                            if (more) { ptx::tmem_ld_wait(); ptx::tmem_ld_fence(b0); ptx::tmem_ld_fence(b1); }
+                        } else {
+                            if (more) { ptx::tmem_ld32(taddr + (uint32_t)((ct + 1) * 64), a0); ptx::tmem_ld32(taddr + (uint32_t)((ct + 1) * 64 + 32), a1); }
 #pragma unroll
-                                for (int j = 0; j < 32; j++) best[ct] = fmaxf(best[ct], __uint_as_float(v[j]));
-                            } else {
+                            for (int j = 0; j < 32; j++) best[ct] = fmaxf(best[ct], fmaxf(__uint_as_float(b0[j]), __uint_as_float(b1[j])));
+                            if (more) { ptx::tmem_ld_wait(); ptx::tmem_ld_fence(a0); ptx::tmem_ld_fence(a1); }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int ct = 0; ct < 4; ct++) {
+                    if (ct < ntile) {
+#pragma unroll
+                        for (int c0 = 0; c0 < 64; c0 += 32) {
+                            if (c0 < valid) {
+                                uint32_t v[32];
+                                ptx::tmem_ld32(taddr + (uint32_t)(ct * 64 + c0), v);
+                                ptx::tmem_ld_wait();
 #pragma unroll
                                 for (int j = 0; j < 32; j++) if (c0 + j < valid) best[ct] = fmaxf(best[ct], __uint_as_float(v[j]));
                             }

@@ -661,6 +661,12 @@ __device__ __forceinline__ bool in_recip_range(double u) {
     return hi_abs(u) - 0x0C100000u < 0x70100000u;
 }
 __device__ __forceinline__ bool exp_all_ones(double u) { return (hi_abs(u) & 0x7ff00000u) == 0x7ff00000u; }
+// ... or exactly zero: fma(+-0, rh, +-0 * rl) is the correctly signed zero quotient, so zeros need no division either
+// (a coordinate that is constant over a voxel - flat ground - makes every difference and product of that axis zero)
+__device__ __forceinline__ bool recip_ok(double u) {
+    const unsigned h = hi_abs(u);
+    return h - 0x0C100000u < 0x70100000u || (h | (unsigned)__double2loint(u)) == 0u;
+}
 
 // {RN(1/c), RN((1 - c RN(1/c)) RN(1/c))} for c = 1 .. n (index c - 1): the reciprocal pairs of div_by_count, tabulated
 // once per workspace (every voxel of every cloud divides by the same running counts)
@@ -707,11 +713,12 @@ __global__ void __launch_bounds__(32) k_stats(CloudState *__restrict__ states, u
     const T *pp[kQ];
     int prev_m[kQ];
     bool live[kQ];
+    bool wary[kQ];                         // the slot's voxel has shown |x - mu| << |x|: its rounds use the 4-operation chain
     T nx[kQ][3];                           // the next round's point of this lane (per slot), fetched one round ahead
     unsigned nl[kQ];                       // ... its label
     double2 nr[kQ];                        // ... and the reciprocal pair of its count
 #pragma unroll
-    for (int q = 0; q < kQ; q++) { vv[q] = 0; nn[q] = 0; base[q] = 0; pp[q] = sorted; prev_m[q] = 0; live[q] = false;
+    for (int q = 0; q < kQ; q++) { vv[q] = 0; nn[q] = 0; base[q] = 0; pp[q] = sorted; prev_m[q] = 0; live[q] = false; wary[q] = false;
                                    nx[q][0] = nx[q][1] = nx[q][2] = 0; nl[q] = 0; nr[q] = make_double2(0.0, 0.0); }
     bool queue_empty = false;
     bool prev_chk = false;                 // previous round produced a non-finite term: add with the NaN rule
@@ -731,7 +738,7 @@ __global__ void __launch_bounds__(32) k_stats(CloudState *__restrict__ states, u
                     const unsigned st = vox_start[(size_t)b * (vcap + 1) + vv[q]], en = vox_start[(size_t)b * (vcap + 1) + vv[q] + 1];
                     nn[q] = en - st; base[q] = 0;
                     pp[q] = sorted + ((size_t)b * N + st) * kSortedStride;
-                    live[q] = true;
+                    live[q] = true; wary[q] = false;
                     // the slot's first round adds 32 zero terms, so that it can take the straight path like any full round
                     prev_m[q] = 32;
 #pragma unroll
@@ -771,14 +778,18 @@ __global__ void __launch_bounds__(32) k_stats(CloudState *__restrict__ states, u
         }
         __syncwarp();
         // ---- A (this round's means) fused with C (previous round's running sums).  Per point the warp issues only
-        //      the dependency chain {d, t} -> q -> mu, one store and one add: q = RN(d / count) is fma(d, rh, t) with
-        //      t = (x - mu) * rl formed as fma(-mu, rl, x * rl) so that it does not wait for d (see div_by_count for
-        //      why the quotient is exact; the cancellation in t is harmless while |d| >= 2^-22 |x|).  Whether every
-        //      operand of the round was inside the proven range is checked afterwards, in parallel, by phase B; if
-        //      not, the round is redone with the IEEE division.
+        //      the dependency chain d -> q -> mu, one store and one add: q = RN(d / count) is fma(d, rh, t), t = d * rl
+        //      (div_by_count: exact for |d| inside the proven range, and trivially for d = 0).  The fast form takes t =
+        //      fma(-mu, rl, x * rl), which does not wait for d (three dependent operations per point instead of four) but
+        //      loses t to cancellation when |d| < 2^-22 |x|; a slot whose voxel shows that (a coordinate that is nearly
+        //      constant over the voxel: flat ground) is marked wary, and rounds with a wary slot take t = d * rl.  Phase B
+        //      checks every operand of the round afterwards, in parallel; a round that broke a condition is redone.
         const double mu_start = mu;
         const int my_m = m[cq], my_pm = prev_m[aq];
         bool straight = !prev_chk;             // every slot is in a full round after a full round, or idle
+        bool safe = false;                     // some live slot is wary
+#pragma unroll
+        for (int q = 0; q < kQ; q++) safe = safe || (live[q] && wary[q]);
 #pragma unroll
         for (int q = 0; q < kQ; q++) straight = straight && ((m[q] == 32 && prev_m[q] == 32) || (m[q] == 0 && prev_m[q] == 0));
         if (straight) {
@@ -788,32 +799,51 @@ __global__ void __launch_bounds__(32) k_stats(CloudState *__restrict__ states, u
             double2 rv[2], rn[2];
 #pragma unroll
             for (int j = 0; j < 2; j++) { xv[j] = xs[j]; rv[j] = rs[j]; tv[j] = tp[j]; }
+            if (!safe) {
 #pragma unroll
-            for (int k0 = 0; k0 < 32; k0 += 2) {
-                if (k0 + 2 < 32) {
+                for (int k0 = 0; k0 < 32; k0 += 2) {
+                    if (k0 + 2 < 32) {
 #pragma unroll
-                    for (int j = 0; j < 2; j++) { xn[j] = xs[k0 + 2 + j]; rn[j] = rs[k0 + 2 + j]; tn[j] = tp[k0 + 2 + j]; }
+                        for (int j = 0; j < 2; j++) { xn[j] = xs[k0 + 2 + j]; rn[j] = rs[k0 + 2 + j]; tn[j] = tp[k0 + 2 + j]; }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const double d = xv[j] - mu;
+                        const double t = fma(-mu, rv[j].y, xv[j] * rv[j].y);
+                        mu = mu + fma(d, rv[j].x, t);
+                        if (chain_lane) mus[k0 + j + 1] = mu;
+                        acc += tv[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; j++) { xv[j] = xn[j]; rv[j] = rn[j]; tv[j] = tn[j]; }
                 }
+            } else {
 #pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const double d = xv[j] - mu;
-                    const double t = fma(-mu, rv[j].y, xv[j] * rv[j].y);
-                    mu = mu + fma(d, rv[j].x, t);
-                    if (chain_lane) mus[k0 + j + 1] = mu;
-                    acc += tv[j];
+                for (int k0 = 0; k0 < 32; k0 += 2) {
+                    if (k0 + 2 < 32) {
+#pragma unroll
+                        for (int j = 0; j < 2; j++) { xn[j] = xs[k0 + 2 + j]; rn[j] = rs[k0 + 2 + j]; tn[j] = tp[k0 + 2 + j]; }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const double d = xv[j] - mu;
+                        mu = mu + fma(d, rv[j].x, d * rv[j].y);
+                        if (chain_lane) mus[k0 + j + 1] = mu;
+                        acc += tv[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; j++) { xv[j] = xn[j]; rv[j] = rn[j]; tv[j] = tn[j]; }
                 }
-#pragma unroll
-                for (int j = 0; j < 2; j++) { xv[j] = xn[j]; rv[j] = rn[j]; tv[j] = tn[j]; }
             }
         } else {
             // last (partial) round of a voxel, the round after it (only the sums move), or a round after non-finite
-            // terms: per-lane predicates
+            // terms: per-lane predicates, 4-operation chain
+            safe = true;
             for (int k = 0; k < 32; k++) {
                 if (k < my_m) {
-                    const double xk = xs[k];
                     const double2 r = rs[k];
-                    const double d = xk - mu;
-                    mu = mu + fma(d, r.x, fma(-mu, r.y, xk * r.y));
+                    const double d = xs[k] - mu;
+                    mu = mu + fma(d, r.x, d * r.y);
                     if (chain_lane) mus[k + 1] = mu;
                 }
                 if (k < my_pm) {
@@ -831,25 +861,26 @@ __global__ void __launch_bounds__(32) k_stats(CloudState *__restrict__ states, u
             bool redone = false;
             const double rh = rq[q].x, rl = rq[q].y;
             while (true) {
-                bool bad = false;
+                bool bad = false, cancel = false;
                 if (lane < m[q]) {
                     const double(*mq)[33] = sm.mu[q];
                     const double o0 = mq[0][lane], o1 = mq[1][lane], o2 = mq[2][lane];
                     const double n0 = mq[0][lane + 1], n1 = mq[1][lane + 1], n2 = mq[2][lane + 1];
                     const double x0 = sm.x[q][0][lane], x1 = sm.x[q][1][lane], x2 = sm.x[q][2][lane];
                     const double d0 = x0 - o0, d1 = x1 - o1, d2 = x2 - o2;          // the chain's d, bit for bit
-                    // the chain's reciprocal form needs |d| inside its proven range and |d| 2^22 >= |x| (on the high words:
-                    // a strict inequality there implies the real one; the few equal cases just take the redo)
-                    bad = !(in_recip_range(d0) && hi_abs(d0) + 0x01600000u > hi_abs(x0)) ||
-                          !(in_recip_range(d1) && hi_abs(d1) + 0x01600000u > hi_abs(x1)) ||
-                          !(in_recip_range(d2) && hi_abs(d2) + 0x01600000u > hi_abs(x2));
+                    // the chain's reciprocal form needs d = 0 or |d| inside the proven range (else: IEEE division), the fast
+                    // form also |d| 2^22 >= |x| (compared on the high words: a strict inequality there implies the real
+                    // one; the few equal cases just count as failing)
+                    bad = !(recip_ok(d0) && recip_ok(d1) && recip_ok(d2));
+                    cancel = !safe && !((hi_abs(d0) + 0x01600000u > hi_abs(x0) || d0 == 0.0) && (hi_abs(d1) + 0x01600000u > hi_abs(x1) || d1 == 0.0) &&
+                                        (hi_abs(d2) + 0x01600000u > hi_abs(x2) || d2 == 0.0));
                     double(*t)[33] = sm.t[q];
                     const double e0 = x0 - n0, e1 = x1 - n1;
                     const double t0 = d0 * e0, t1 = d1 * e1, t2 = d2 * (x2 - n2);
                     // (x_j - new_j)(x_k - old_k) / count: mu_k (k > j) is not yet updated when dimension j runs
                     const double p01 = e0 * d1, p02 = e0 * d2, p12 = e1 * d2;
                     double q01 = fma(p01, rh, p01 * rl), q02 = fma(p02, rh, p02 * rl), q12 = fma(p12, rh, p12 * rl);
-                    if (!(in_recip_range(p01) && in_recip_range(p02) && in_recip_range(p12))) {
+                    if (!(recip_ok(p01) && recip_ok(p02) && recip_ok(p12))) {
                         const double c = (double)(base[q] + lane + 1);
                         q01 = p01 / c; q02 = p02 / c; q12 = p12 / c;                   // zeros, tiny or huge products: IEEE division
                     }
@@ -858,14 +889,27 @@ __global__ void __launch_bounds__(32) k_stats(CloudState *__restrict__ states, u
                     hm = max(hm, hi_abs(t1)); hm = max(hm, hi_abs(t2)); hm = max(hm, hi_abs(q01)); hm = max(hm, hi_abs(q02)); hm = max(hm, hi_abs(q12));
                     nonfinite |= hm >= 0x7ff00000u;
                 }
-                if (redone || !__any_sync(0xffffffffu, bad)) break;
-                // rare: redo this slot's round with the IEEE division on its three chain lanes, then its terms
+                if (redone) break;
+                const bool any_bad = __any_sync(0xffffffffu, bad), any_cancel = __any_sync(0xffffffffu, cancel);
+                if (!any_bad && !any_cancel) break;
+                // redo this slot's round on its three chain lanes, then its terms: with the IEEE division when an operand
+                // left the proven range (rare), else with the 4-operation chain; the slot stays wary for the rest of its voxel
+                if (any_cancel) wary[q] = true;
                 if (chain_lane && cq == q) {
                     mu = mu_start;
-                    for (int k = 0; k < m[q]; k++) {
-                        const double cnt = (double)(base[q] + k + 1);
-                        mu = mu + (xs[k] - mu) / cnt;
-                        mus[k + 1] = mu;
+                    if (any_bad) {
+                        for (int k = 0; k < m[q]; k++) {
+                            const double cnt = (double)(base[q] + k + 1);
+                            mu = mu + (xs[k] - mu) / cnt;
+                            mus[k + 1] = mu;
+                        }
+                    } else {
+                        for (int k = 0; k < m[q]; k++) {
+                            const double2 r = rs[k];
+                            const double d = xs[k] - mu;
+                            mu = mu + fma(d, r.x, d * r.y);
+                            mus[k + 1] = mu;
+                        }
                     }
                 }
                 redone = true;
@@ -956,7 +1000,7 @@ __global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restric
         const double2 r = s_rc[k];
         const double rh = r.x, rl = r.y;
         // RN(u / c): reciprocal form inside its proven range, IEEE division otherwise
-#define QDIV(u) (in_recip_range(u) ? fma((u), rh, (u) * rl) : (u) / (double)(k + 1))
+#define QDIV(u) (recip_ok(u) ? fma((u), rh, (u) * rl) : (u) / (double)(k + 1))
         // j = 0
         const double d0 = x0 - mu0;
         const double o0 = mu0;
