@@ -259,6 +259,18 @@ int ndnet_b200_trainer_backward(ndnet_b200_trainer *t, const float *dlogp, float
 int ndnet_b200_trainer_backward_flat(ndnet_b200_trainer *t, const float *dlogp, float *const *tensors, float *flat_grads,
                                      void *stream);
 long ndnet_b200_trainer_grad_layout(const ndnet_b200_trainer *t, long *offsets, int n_tensors);
+/* Gradient buckets for an all-reduce that overlaps the backward pass (/root/reference/tools/train.py:72-81 has one process;
+ * data-parallel training adds the collective).  The flat layout follows the order in which backward finishes the parameters:
+ * bucket 0 = segmentation head, 1 = trunk conv2/conv3 + feature T-Net, 2 = conv1 + input T-Net; bucket i covers floats
+ * [begin, end) of the flat buffer.  After ndnet_b200_trainer_backward_flat returns (everything is only enqueued),
+ * ndnet_b200_trainer_bucket_ready(t, i, flat, side) makes the stream `side` wait for the event recorded when bucket i became
+ * final - so a collective launched on `side` runs while the rest of the backward still executes.  With CUDA graphs the
+ * gradients are produced in a library-owned buffer; set_deferred_copy(1) drops the whole-buffer copy at the end of
+ * backward_flat and bucket_ready copies each bucket into `flat` on `side` instead. */
+int ndnet_b200_trainer_num_buckets(const ndnet_b200_trainer *t);
+int ndnet_b200_trainer_bucket_range(const ndnet_b200_trainer *t, int i, long *begin, long *end);
+int ndnet_b200_trainer_set_deferred_copy(ndnet_b200_trainer *t, int enable);
+int ndnet_b200_trainer_bucket_ready(ndnet_b200_trainer *t, int i, float *flat_grads, void *side_stream);
 /* enable = 1: the ~100 / ~250 kernel launches of a forward / backward pass are captured into CUDA graphs (one per shape
  * and pointer set; the first pass of a configuration runs eagerly) and replayed; inputs and outputs are staged through
  * library-owned buffers so the replayed pointers never change.  Default 0. */

@@ -357,6 +357,13 @@ struct Trainer {
     std::vector<long> grad_off;           // per tensor: offset (floats) of its gradient in the flat buffer, -1 for buffers
     long flat_elems = 0;
     std::vector<float *> static_grads;
+    // gradient buckets: the flat layout follows the order in which backward finishes the parameters (head, trunk + feature
+    // T-Net, first layer + input T-Net); an event is recorded as each bucket completes, so that its all-reduce can start
+    // while the rest of the backward still runs
+    static constexpr int kBuckets = 3;
+    long bucket_end[kBuckets] = {0, 0, 0};
+    cudaEvent_t bucket_ev[kBuckets] = {nullptr, nullptr, nullptr};
+    int defer_copy = 0;                   // graph mode: the caller fetches flat_grad bucket by bucket (bucket_ready) instead of one copy at the end
     int tf32 = 0;                         // 1: eligible GEMMs run on the tensor cores (kind::tf32), 0: fp32 FMA everywhere
     float *sT1 = nullptr, *sT2 = nullptr, *sW = nullptr;      // transposed dY / X / W for the tensor-core wgrad and dgrad
     long ldT = 0;
@@ -728,6 +735,14 @@ static int forward(Trainer &t, const float *feat, int B, int N, float *const *te
     return 0;
 }
 
+// the gradients of bucket i are final: record its event (an external-event node when the pass is being captured)
+static void record_bucket(Trainer &t, int i, cudaStream_t st) {
+    if (!t.bucket_ev[i] && cudaEventCreateWithFlags(&t.bucket_ev[i], cudaEventDisableTiming) != cudaSuccess) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    cudaEventRecordWithFlags(t.bucket_ev[i], st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+
 static int backward(Trainer &t, const float *dlogp, float *const *tensors, float *const *grads, cudaStream_t st) {
     if (!t.arena || !t.feat) { t.err = "backward without forward"; return -204; }
     const int B = t.B, N = t.N;
@@ -741,6 +756,7 @@ static int backward(Trainer &t, const float *dlogp, float *const *tensors, float
     block_bwd(ps, t.h3, t.h2.A, 256, t.h2.dA, 256, false);
     block_bwd(ps, t.h2, t.h1.A, 512, t.h1.dA, 512, false);
     block_bwd(ps, t.h1, t.H0, W, t.dH0, W, false);
+    record_bucket(t, 0, st);
     // dH0 = [dX2 | per-row gradient of the broadcast global feature]
     {
         RedP r{};
@@ -755,9 +771,11 @@ static int backward(Trainer &t, const float *dlogp, float *const *tensors, float
     gemm(st, t.dH0, W, 1, t.t2.T, 64, 1, t.c1.dA, 64, N, 64, 64, nullptr, false, B, (long)N * W, 4096, (long)N * 64);
     gemm(st, t.c1.A, 1, 64, t.dH0, 1, W, t.t2.dT, 64, 64, 64, N, nullptr, false, B, (long)N * 64, (long)N * W, 4096);
     tnet_bwd(ps, t.t2, t.c1.A, 64, t.c1.dA, 64, true);
+    record_bucket(t, 1, st);
     block_bwd(ps, t.c1, t.X12, 12, t.dX12, 12, false);
     train_count(), k_apply_t_bwd<<<B, 256, 0, st>>>(t.feat, t.dX12, N, t.t1.dT);
     tnet_bwd(ps, t.t1, t.feat, 12, nullptr, 0, false);
+    record_bucket(t, 2, st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { t.err = std::string("backward: ") + cudaGetErrorString(e); return -100 - (int)e; }
     return 0;
@@ -832,7 +850,21 @@ static int backward_flat(Trainer &t, const float *dlogp, float *const *tensors, 
         return backward(t, t.dlogp_static, tensors, t.static_grads.data(), s);
     });
     if (rc != 0) return rc;
-    cudaMemcpyAsync(flat_out, t.flat_grad, sizeof(float) * t.flat_elems, cudaMemcpyDeviceToDevice, st);
+    if (!t.defer_copy) cudaMemcpyAsync(flat_out, t.flat_grad, sizeof(float) * t.flat_elems, cudaMemcpyDeviceToDevice, st);
+    return 0;
+}
+
+// makes `side` wait until bucket i of the last backward is final and (graph mode with deferred copy) copies it from the
+// library's static buffer into the caller's flat buffer on `side`
+static int bucket_ready(Trainer &t, int i, float *flat_out, cudaStream_t side) {
+    if (i < 0 || i >= Trainer::kBuckets || !t.bucket_ev[i]) { t.err = "bucket_ready: no backward pass recorded"; return -204; }
+    cudaError_t e = cudaStreamWaitEvent(side, t.bucket_ev[i], 0);
+    if (e != cudaSuccess) { t.err = std::string("bucket wait: ") + cudaGetErrorString(e); return -100 - (int)e; }
+    if (t.use_graph && t.defer_copy) {
+        const long b0 = i == 0 ? 0 : t.bucket_end[i - 1], b1 = t.bucket_end[i];
+        e = cudaMemcpyAsync(flat_out + b0, t.flat_grad + b0, sizeof(float) * (size_t)(b1 - b0), cudaMemcpyDeviceToDevice, side);
+        if (e != cudaSuccess) { t.err = std::string("bucket copy: ") + cudaGetErrorString(e); return -100 - (int)e; }
+    }
     return 0;
 }
 
@@ -877,22 +909,27 @@ extern "C" int ndnet_b200_trainer_create(int device, int n_tensors, const char *
               bind_block(t, t.h2, "conv2", "bn2", 512, 256, true) && bind_block(t, t.h3, "conv3", "bn3", 256, 128, true) &&
               bind_block(t, t.h4, "conv4", "", 128, t.C, false);
     if (!ok) return fail("tensor binding failed");
-    {   // flat gradient layout: parameters (weights, biases, BatchNorm scale/shift) in tensor order, 16-byte aligned
+    {   // flat gradient layout: parameters (weights, biases, BatchNorm scale/shift) in the order backward finishes them,
+        // 16-byte aligned; three buckets (head | trunk conv2-3 + feature T-Net | conv1 + input T-Net)
         t.grad_off.assign(n_tensors, -1);
-        std::vector<char> is_param(n_tensors, 0);
-        Block *all[] = {&t.t1.c1, &t.t1.c2, &t.t1.c3, &t.t1.f1, &t.t1.f2, &t.t1.f3, &t.t2.c1, &t.t2.c2, &t.t2.c3, &t.t2.f1, &t.t2.f2, &t.t2.f3,
-                        &t.c1, &t.c2, &t.c3, &t.h1, &t.h2, &t.h3, &t.h4};
-        for (Block *k : all) {
-            is_param[k->lin.w] = is_param[k->lin.b] = 1;
-            if (k->has_bn) is_param[k->bn.g] = is_param[k->bn.be] = 1;
-        }
+        Block *order[] = {&t.h4, &t.h3, &t.h2, &t.h1,
+                          &t.c3, &t.c2, &t.t2.f3, &t.t2.f2, &t.t2.f1, &t.t2.c3, &t.t2.c2, &t.t2.c1,
+                          &t.c1, &t.t1.f3, &t.t1.f2, &t.t1.f1, &t.t1.c3, &t.t1.c2, &t.t1.c1};
+        const int bucket_last[Trainer::kBuckets] = {3, 11, 18};
         long off = 0;
-        for (int i = 0; i < n_tensors; i++) {
-            if (!is_param[i]) continue;
+        int bucket = 0;
+        auto place = [&](int i) {
+            if (i < 0 || t.grad_off[i] >= 0) return;
             long numel = 1;
             for (auto v : t.shapes[i]) numel *= v;
             t.grad_off[i] = off;
             off += (numel + 3) / 4 * 4;
+        };
+        for (int k = 0; k < 19; k++) {
+            Block *b = order[k];
+            place(b->lin.w); place(b->lin.b);
+            if (b->has_bn) { place(b->bn.g); place(b->bn.be); }
+            if (k == bucket_last[bucket]) t.bucket_end[bucket++] = off;
         }
         t.flat_elems = off;
     }
@@ -906,6 +943,28 @@ extern "C" int ndnet_b200_trainer_backward_flat(ndnet_b200_trainer *h, const flo
     cudaError_t e = cudaSetDevice(h->t.device);
     if (e != cudaSuccess) return -100 - (int)e;
     return train::backward_flat(h->t, dlogp, tensors, flat_grads, (cudaStream_t)stream);
+}
+
+extern "C" int ndnet_b200_trainer_num_buckets(const ndnet_b200_trainer *h) { return h ? train::Trainer::kBuckets : -200; }
+
+extern "C" int ndnet_b200_trainer_bucket_range(const ndnet_b200_trainer *h, int i, long *begin, long *end) {
+    if (!h || i < 0 || i >= train::Trainer::kBuckets || !begin || !end) return -200;
+    *begin = i == 0 ? 0 : h->t.bucket_end[i - 1];
+    *end = h->t.bucket_end[i];
+    return 0;
+}
+
+extern "C" int ndnet_b200_trainer_set_deferred_copy(ndnet_b200_trainer *h, int enable) {
+    if (!h || (enable != 0 && enable != 1)) return -200;
+    h->t.defer_copy = enable;
+    return 0;
+}
+
+extern "C" int ndnet_b200_trainer_bucket_ready(ndnet_b200_trainer *h, int i, float *flat_grads, void *side_stream) {
+    if (!h || !flat_grads) return -200;
+    cudaError_t e = cudaSetDevice(h->t.device);
+    if (e != cudaSuccess) return -100 - (int)e;
+    return train::bucket_ready(h->t, i, flat_grads, (cudaStream_t)side_stream);
 }
 
 extern "C" long ndnet_b200_trainer_grad_layout(const ndnet_b200_trainer *h, long *offsets, int n) {
@@ -1010,6 +1069,7 @@ extern "C" void ndnet_b200_trainer_destroy(ndnet_b200_trainer *h) {
     if (h->t.gf.exec) cudaGraphExecDestroy(h->t.gf.exec);
     if (h->t.gb.exec) cudaGraphExecDestroy(h->t.gb.exec);
     if (h->t.cap) cudaStreamDestroy(h->t.cap);
+    for (cudaEvent_t e : h->t.bucket_ev) if (e) cudaEventDestroy(e);
     if (h->t.arena) cudaFree(h->t.arena);
     delete h;
 }

@@ -122,6 +122,7 @@ class _B200Mixin:
             if tr is None or tr.device != points.device:
                 tr = SegTrainer(self, points.device, tf32=bool(getattr(self, "b200_tf32", False)))
                 object.__setattr__(self, "_b200_trainer", tr)
+            tr.overlap_allreduce = bool(getattr(self, "b200_overlap_allreduce", False))
             return tr(points, covariances)
         m = getattr(self, "_b200_model", None)
         stamp = _state_stamp(self)

@@ -108,6 +108,14 @@ def lib() -> C.CDLL:
     L.ndnet_b200_trainer_backward_flat.argtypes = [vp, vp, C.POINTER(vp), vp, vp]
     L.ndnet_b200_trainer_grad_layout.restype = l
     L.ndnet_b200_trainer_grad_layout.argtypes = [vp, vp, i]
+    L.ndnet_b200_trainer_num_buckets.restype = i
+    L.ndnet_b200_trainer_num_buckets.argtypes = [vp]
+    L.ndnet_b200_trainer_bucket_range.restype = i
+    L.ndnet_b200_trainer_bucket_range.argtypes = [vp, i, C.POINTER(l), C.POINTER(l)]
+    L.ndnet_b200_trainer_set_deferred_copy.restype = i
+    L.ndnet_b200_trainer_set_deferred_copy.argtypes = [vp, i]
+    L.ndnet_b200_trainer_bucket_ready.restype = i
+    L.ndnet_b200_trainer_bucket_ready.argtypes = [vp, i, vp, vp]
     L.ndnet_b200_trainer_set_graph.restype = i
     L.ndnet_b200_trainer_set_graph.argtypes = [vp, i]
     L.ndnet_b200_trainer_set_precision.restype = i
@@ -136,5 +144,6 @@ EXPORTED = [
     "ndnet_b200_ply_load", "ndnet_b200_ply_num_points", "ndnet_b200_ply_sample", "ndnet_b200_ply_free",
     "ndnet_b200_trainer_create", "ndnet_b200_trainer_forward", "ndnet_b200_trainer_backward", "ndnet_b200_trainer_last_error",
     "ndnet_b200_trainer_backward_flat", "ndnet_b200_trainer_grad_layout", "ndnet_b200_trainer_set_graph",
+    "ndnet_b200_trainer_num_buckets", "ndnet_b200_trainer_bucket_range", "ndnet_b200_trainer_set_deferred_copy", "ndnet_b200_trainer_bucket_ready",
     "ndnet_b200_trainer_set_precision", "ndnet_b200_debug_train_gemm", "ndnet_b200_trainer_debug_buffer", "ndnet_b200_trainer_destroy",
 ]

@@ -5,8 +5,17 @@ keys, /root/reference/ndnet/models/ndtnet.py:198-243) to `ndnet_b200_trainer_*`;
 `module(points, covs)` inside the reference's training loop (/root/reference/tools/train.py:66-76) gives the same
 train-mode forward (batch-statistics BatchNorm, running statistics updated in place) and, through one
 `torch.autograd.Function`, the gradients of every parameter from our kernels instead of torch autograd.  The loss and
-the optimizer stay ordinary torch code.  Multi-GPU: one process per GPU, `allreduce_gradients` averages the gradients
-with one flat NCCL all-reduce (the only collective of the training path).
+the optimizer stay ordinary torch code.
+
+Multi-GPU (one process per GPU, scans sharded over the ranks): the gradient average is the training path's only collective
+(SURVEY.md §8e).  `SegTrainer(..., overlap_allreduce=True)` (or `module.b200_overlap_allreduce = True`) launches it from
+INSIDE the backward pass: the library lays the gradients out in the order backward finishes them and records an event per
+bucket (head | trunk + feature T-Net | first layer + input T-Net); each bucket's NCCL all-reduce starts on a side stream
+as soon as its event fires, while the kernels of the earlier layers still run.  `allreduce_gradients(module)` is the
+plain version (one flat all-reduce after backward) and a no-op for gradients that were already averaged in backward.
+BatchNorm: batch statistics are per replica, and every rank updates its own running statistics (stock DDP instead
+broadcasts rank 0's buffers at every forward); call `sync_batchnorm_buffers(module)` before evaluating or saving a
+checkpoint so that all ranks hold the same (averaged) running statistics.
 """
 from __future__ import annotations
 
@@ -19,10 +28,13 @@ from . import _lib
 
 
 class SegTrainer:
-    def __init__(self, module: torch.nn.Module, device: torch.device | int | None = None, tf32: bool = False, graph: bool = True):
+    def __init__(self, module: torch.nn.Module, device: torch.device | int | None = None, tf32: bool = False, graph: bool = True,
+                 overlap_allreduce: bool = False):
         """tf32=False: fp32 FMA everywhere (parity configuration).  tf32=True: the large GEMMs run on the tensor cores
         (tcgen05 kind::tf32, fp32 accumulation) — the counterpart of torch.backends.cuda.matmul.allow_tf32.
-        graph=True: each pass is captured into a CUDA graph per (shape, parameter storage) and replayed."""
+        graph=True: each pass is captured into a CUDA graph per (shape, parameter storage) and replayed.
+        overlap_allreduce=True: with an initialised process group of more than one rank, backward averages the gradients
+        over the ranks itself, bucket by bucket, overlapped with the rest of the backward pass."""
         self.module = module
         p0 = next(module.parameters())
         dev = p0.device if device is None else (torch.device("cuda", device) if isinstance(device, int) else torch.device(device))
@@ -55,6 +67,14 @@ class SegTrainer:
         self._grad_off = [int(o) for o in offs]
         assert all((o >= 0) == (k in set(self.param_names)) for o, k in zip(self._grad_off, self.names)), "gradient layout mismatch"
         self.num_out = int(module.num_classes) + 1
+        self.overlap_allreduce = bool(overlap_allreduce)
+        self._buckets = []
+        for i in range(int(self._L.ndnet_b200_trainer_num_buckets(h))):
+            b, e = C.c_long(0), C.c_long(0)
+            self._L.ndnet_b200_trainer_bucket_range(h, i, C.byref(b), C.byref(e))
+            self._buckets.append((int(b.value), int(e.value)))
+        self._side = None                      # stream the bucket all-reduces are launched from
+        self.last_allreduce = None             # (bytes, number of collectives) of the last overlapped backward
 
     def _tensors(self):
         params = dict(self.module.named_parameters())
@@ -70,6 +90,9 @@ class SegTrainer:
 
     def __call__(self, points: torch.Tensor, covariances: torch.Tensor) -> torch.Tensor:
         """(B,N,3), (B,N,9) -> log-probabilities (B,N,num_classes+1), differentiable w.r.t. the module's parameters."""
+        if not self.module.training:
+            raise RuntimeError("SegTrainer normalises with batch statistics and updates the running ones: the module is in eval() "
+                               "mode - call module(points, covs) / forward_b200 (the folded inference kernels) instead")
         feat = torch.cat((points, covariances), dim=2).float().contiguous()
         return _SegTrainFn.apply(self, feat, *[p for _, p in self.module.named_parameters()])
 
@@ -123,8 +146,30 @@ class _SegTrainFn(torch.autograd.Function):
         flat = torch.empty((trainer._flat_elems,), dtype=torch.float32, device=dout.device)    # fresh storage every pass
         dout = dout.float().contiguous()
         stream = torch.cuda.current_stream(dout.device).cuda_stream
+        import torch.distributed as dist
+        overlap = trainer.overlap_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        trainer._L.ndnet_b200_trainer_set_deferred_copy(trainer._h, int(overlap))
         rc = trainer._L.ndnet_b200_trainer_backward_flat(trainer._h, dout.data_ptr(), trainer._ptr_array(tensors), flat.data_ptr(), stream)
         trainer._check(rc, "ndnet_b200_trainer_backward_flat")
+        if overlap:
+            # everything above is only enqueued.  Per bucket: the side stream waits for the bucket's event (and, with
+            # CUDA graphs, copies the bucket out of the library's buffer), then NCCL averages it - while the main
+            # stream is still running the backward kernels of the earlier layers
+            if trainer._side is None:
+                trainer._side = torch.cuda.Stream(dout.device)
+            side = trainer._side
+            flat.record_stream(side)
+            works = []
+            for i, (b, e) in enumerate(trainer._buckets):
+                rc = trainer._L.ndnet_b200_trainer_bucket_ready(trainer._h, i, flat.data_ptr(), side.cuda_stream)
+                trainer._check(rc, "ndnet_b200_trainer_bucket_ready")
+                with torch.cuda.stream(side):
+                    works.append(dist.all_reduce(flat[b:e], op=dist.ReduceOp.AVG, async_op=True))
+            for w in works:
+                w.wait()                          # the CURRENT stream waits for the collective; the host does not block
+            trainer.last_allreduce = (4 * trainer._flat_elems, len(works))
+            for t in tensors[:n_params]:
+                t._b200_grad_averaged = True      # allreduce_gradients() skips these
         grads = [flat[o:o + t.numel()].view_as(t) for o, t in zip(trainer._grad_off[:n_params], tensors[:n_params])]
         return (None, None, *grads)
 
@@ -150,18 +195,56 @@ def allreduce_gradients(module: torch.nn.Module, world_size: int | None = None) 
     if not (dist.is_available() and dist.is_initialized()):
         return 0
     world = dist.get_world_size() if world_size is None else world_size
-    grads = [p.grad for p in module.parameters() if p.grad is not None]
-    if not grads or world == 1:
+    # every parameter that takes gradients takes part on every rank (a missing gradient counts as zeros), so that the ranks
+    # always issue the same collective; parameters whose gradients backward already averaged are left alone
+    params = [p for p in module.parameters() if p.requires_grad]
+    if all(getattr(p, "_b200_grad_averaged", False) for p in params):
+        for p in params:
+            p._b200_grad_averaged = False
         return 0
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    if not params or world == 1:
+        return 0
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     flat /= world
     off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+    for p in params:
+        n = p.numel()
+        if p.grad is None:
+            p.grad = flat[off:off + n].view_as(p).clone()
+        else:
+            p.grad.copy_(flat[off:off + n].view_as(p))
         off += n
     return off
+
+
+def sync_batchnorm_buffers(module: torch.nn.Module) -> int:
+    """Averages the BatchNorm running statistics over the ranks (num_batches_tracked: maximum).  Training uses per-replica
+    batch statistics and every rank updates its own running statistics, so the ranks drift apart; call this before
+    evaluating or saving a checkpoint (stock DDP broadcasts rank 0's buffers at every forward instead).  Returns the number
+    of values reduced; a no-op without an initialised process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    floats = [b for b in module.buffers() if b.is_floating_point()]
+    ints = [b for b in module.buffers() if not b.is_floating_point()]
+    n = 0
+    if floats:
+        flat = torch.cat([b.reshape(-1).float() for b in floats])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat /= dist.get_world_size()
+        off = 0
+        for b in floats:
+            b.copy_(flat[off:off + b.numel()].view_as(b))
+            off += b.numel()
+        n += off
+    if ints:
+        flat = torch.stack([b.reshape(()).long() for b in ints])
+        dist.all_reduce(flat, op=dist.ReduceOp.MAX)
+        for b, v in zip(ints, flat):
+            b.copy_(v)
+        n += len(ints)
+    return n
 
 
 def reference_loss(pred: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
