@@ -171,6 +171,9 @@ int ndnet_b200_model_create(ndnet_b200_ctx *ctx, ndnet_b200_model **model, int k
                             const char *const *names, const float *const *data, const int64_t *const *shapes,
                             const int *ndims);
 void ndnet_b200_model_destroy(ndnet_b200_model *model);
+/* Segmentation head layers 1 + 2 (ndtnet.py:231-232) run as ONE kernel by default: the 512-wide activation stays in tensor
+ * memory / shared memory.  enable = 0 runs them as two GEMMs (the activation goes through HBM and can be tapped as "head.l1"). */
+int ndnet_b200_model_set_fused_head(ndnet_b200_model *model, int enable);
 /* floats per input row the model expects: 12 for NDT-Net (mean + covariance), point_dim for PointNet */
 int ndnet_b200_model_input_dim(const ndnet_b200_model *model);
 

@@ -676,6 +676,12 @@ extern "C" int ndnet_b200_model_create(ndnet_b200_ctx *c, ndnet_b200_model **mod
 
 extern "C" int ndnet_b200_model_input_dim(const ndnet_b200_model *m) { return m ? m->m.input_dim() : -200; }
 
+extern "C" int ndnet_b200_model_set_fused_head(ndnet_b200_model *m, int enable) {
+    if (!m || (enable != 0 && enable != 1)) return -200;
+    m->m.set_fused_head(enable != 0);
+    return 0;
+}
+
 extern "C" void ndnet_b200_model_destroy(ndnet_b200_model *m) {
     if (!m) return;
     m->m.release();

@@ -314,6 +314,7 @@ struct ModelImpl {
     // classification head
     float *k1_w = nullptr, *k1_b = nullptr, *k2_w = nullptr, *k2_b = nullptr, *k3_w = nullptr, *k3_b = nullptr;
     std::vector<void *> allocs;
+    bool fuse_head = true;           // segmentation head layers 1 + 2 in one kernel (k_head12); off: two GEMMs, "head.l1" can be tapped
     // where the activations of the last forward live (Model::tap)
     struct Tap { const void *ptr; int kind; long count; };
     std::map<std::string, Tap> taps;
@@ -435,6 +436,7 @@ int Model::build(int kind, int n_tensors, const char *const *names, const float 
 }
 
 int Model::input_dim() const { return impl ? impl->in_dim : 0; }
+void Model::set_fused_head(bool on) { if (impl) impl->fuse_head = on; }
 
 long Model::tap(const char *name, float *out, long cap, cudaStream_t st) {
     if (!impl || !name) return -300;
@@ -523,6 +525,24 @@ struct Fwd {
         if (!ok) *err = "gemm launch failed";
         gemm_launches++;
     }
+    // fused head layers 1 + 2 (k_head12): x_t2 [B][P][64] -> relu(relu(x W1a^T + cb[cloud]) W2^T + b2) [B][P][256]
+    void head12(const __nv_bfloat16 *xt2, const __nv_bfloat16 *w1a, const float *cbias, const __nv_bfloat16 *w2, const float *b2, __nv_bfloat16 *out) {
+        if (!ok) return;
+        CUtensorMap mx, mw1, mw2, mo;
+        if (!make_map(&mx, xt2, 64, P, B, 128) || !make_map(&mw1, w1a, 64, 512, 1, 256) || !make_map(&mw2, w2, 512, 256, 1, 256) ||
+            !make_map(&mo, out, 256, P, B, 128)) { ok = false; *err = "cuTensorMapEncodeTiled failed"; return; }
+        static bool attr[64] = {};      // function attributes are per device
+        int dev = 0; cudaGetDevice(&dev);
+        if (!attr[dev & 63]) {
+            if (cudaFuncSetAttribute(k_head12, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHead12SmemBytes) != cudaSuccess) { ok = false; *err = "smem attribute"; return; }
+            attr[dev & 63] = true;
+        }
+        Head12Args a{P, cbias, b2};
+        k_head12<<<dim3((P + 127) / 128, B), kGemmThreads, kHead12SmemBytes, st>>>(mx, mw1, mw2, mo, a);
+        ok = cudaGetLastError() == cudaSuccess;
+        if (!ok) *err = "k_head12 launch failed";
+        gemm_launches++;
+    }
     void logsm(const __nv_bfloat16 *act, int K, const __nv_bfloat16 *w, int N, const float *bias, float *out) {
         if (!ok) return;
         CUtensorMap ma, mb;
@@ -595,8 +615,12 @@ int Model::forward(Scratch &scratch, const float *feat, int B, int D, float *out
     if (m.kind == 1) {
         // ---- segmentation head (ndtnet.py:224-241)
         f.fc(m.h1g_w, m.h1_b, g3, m.F, true, cb, 512, m.F, 512, false);
-        f.rows(xt2, 64, m.h1a_w, 512, false, nullptr, cb, 512, true, s1);
-        f.rows(s1, 512, m.h2_w, 256, false, m.h2_b, nullptr, 0, true, s2);
+        if (m.fuse_head) {
+            f.head12(xt2, m.h1a_w, cb, m.h2_w, m.h2_b, s2);           // the 512-wide activation stays in TMEM / shared memory
+        } else {
+            f.rows(xt2, 64, m.h1a_w, 512, false, nullptr, cb, 512, true, s1);
+            f.rows(s1, 512, m.h2_w, 256, false, m.h2_b, nullptr, 0, true, s2);
+        }
         f.rows(s2, 256, m.h3_w, 128, false, m.h3_b, nullptr, 0, true, h128);
         f.logsm(h128, 128, m.h4_w, m.ncls, m.h4_b, out);
     } else {
@@ -618,7 +642,7 @@ int Model::forward(Scratch &scratch, const float *feat, int B, int D, float *out
         m.taps["trunk.xt2"] = {xt2, 1, Ml * 64};               // x . T2  (ndtnet.py:153-155)              [B, N, 64]
         m.taps["trunk.pool"] = {g3, 2, Bl * m.F};              // max over points of bn3(conv3(.))         [B, F]
         if (m.kind == 1) {
-            m.taps["head.l1"] = {s1, 1, Ml * 512};             // segmentation head layers (ndtnet.py:231-233)
+            if (!m.fuse_head) m.taps["head.l1"] = {s1, 1, Ml * 512};   // segmentation head layers (ndtnet.py:231-233); fused: never stored
             m.taps["head.l2"] = {s2, 1, Ml * 256};
             m.taps["head.l3"] = {h128, 1, Ml * 128};
         } else {

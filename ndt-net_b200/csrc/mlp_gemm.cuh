@@ -377,4 +377,182 @@ k_gemm_chmax(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     if (warp == 5) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_head12: the first two layers of the segmentation head fused (ndtnet.py:231-232):
+//   H1 = relu(X . W1a^T + cb[cloud])      X: [P, 64] x_t2 rows of one cloud, W1a: [512, 64], cb = W1g . g + b1 per cloud
+//   out = relu(H1 . W2^T + b2)            W2: [256, 512]
+// The 512-wide activation never leaves the SM: it is produced 64 columns at a time in TMEM (MMA1, N = 64), read back by the
+// four epilogue warps (tcgen05.ld), biased / rectified / rounded to bf16 and written into shared memory in the K-major
+// 128B-swizzled operand layout, from where MMA2 (N = 256) accumulates out += H1[:, chunk] . W2[:, chunk]^T in TMEM.
+// The W2 chunks (32 KB each) stream through a TMA ring; W1a (64 KB) and the X tile are loaded once.  TMEM: columns
+// [0, 256) = out accumulator, [256, 320) and [320, 384) = the two H1 chunk buffers.  MMA1 of chunk c is issued before
+// MMA2 of chunk c - 1, so the tensor pipe works on chunk c while the epilogue warps convert chunk c - 1.
+// One CTA per (128-row tile, cloud); grid (ceil(P/128), B), block 192.  The unfused pair moved 1 GB per 512 scans through
+// HBM for this activation (write 524 MB + read 524 MB).
+// ------------------------------------------------------------------------------------------------
+constexpr int kHead12W2Stages = 2;
+constexpr size_t kHead12SmemBytes = 16384 /*X*/ + 65536 /*W1a, later the output staging*/ + kHead12W2Stages * 32768 /*W2 ring*/ +
+                                    2 * 16384 /*H1 bf16 chunk buffers*/ + 1024 /*align*/ + 256 /*barriers*/ + 512 * 4 + 256 * 4;
+
+struct Head12Args {
+    int P;
+    const float *cbias;     // [B][512]
+    const float *bias2;     // [256]
+};
+
+__global__ void __launch_bounds__(kGemmThreads)
+k_head12(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
+         const __grid_constant__ CUtensorMap mapOut, const Head12Args args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sX = smem;                                        // [128 rows x 128 B]
+    uint8_t *sW1 = sX + 16384;                                 // 8 chunks of [64 rows x 128 B]
+    uint8_t *sW2 = sW1 + 65536;                                // ring of [256 rows x 128 B]
+    uint8_t *sH = sW2 + (size_t)kHead12W2Stages * 32768;       // 2 x [128 rows x 128 B]
+    uint64_t *bars = (uint64_t *)(sH + 2 * 16384);
+    uint64_t *x_full = bars, *acc_full = bars + 1;
+    uint64_t *w2_full = bars + 2, *w2_empty = w2_full + kHead12W2Stages;
+    uint64_t *ht_full = w2_empty + kHead12W2Stages, *ht_empty = ht_full + 2;     // H1 chunk in TMEM
+    uint64_t *hs_full = ht_empty + 2, *hs_empty = hs_full + 2;                   // H1 chunk in shared memory (bf16)
+    uint32_t *tmem_slot = (uint32_t *)(hs_empty + 2);
+    float *s_cb = (float *)(bars + 32);                        // 512 per-cloud biases of layer 1, then 256 biases of layer 2
+    float *s_b2 = s_cb + 512;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, row0 = blockIdx.x * 128;
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(x_full, 1); ptx::mbar_init(acc_full, 1);
+        for (int s = 0; s < kHead12W2Stages; s++) { ptx::mbar_init(&w2_full[s], 1); ptx::mbar_init(&w2_empty[s], 1); }
+        for (int i = 0; i < 2; i++) { ptx::mbar_init(&ht_full[i], 1); ptx::mbar_init(&ht_empty[i], 4); ptx::mbar_init(&hs_full[i], 4); ptx::mbar_init(&hs_empty[i], 1); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&mapX); ptx::prefetch_tmap(&mapW1); ptx::prefetch_tmap(&mapW2); ptx::prefetch_tmap(&mapOut); }
+    if (threadIdx.x < 128) {
+        for (int i = threadIdx.x; i < 512; i += 128) s_cb[i] = args.cbias[(size_t)b * 512 + i];
+        for (int i = threadIdx.x; i < 256; i += 128) s_b2[i] = args.bias2[i];
+    }
+    if (warp == 5) ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            ptx::mbar_expect_tx(x_full, 16384u + 65536u);
+            ptx::tma_load_3d(&mapX, x_full, sX, 0, row0, b);
+            ptx::tma_load_3d(&mapW1, x_full, sW1, 0, 0, 0);                     // rows 0..255 of W1a
+            ptx::tma_load_3d(&mapW1, x_full, sW1 + 32768, 0, 256, 0);           // rows 256..511
+            for (int c = 0; c < 8; c++) {
+                const int s = c % kHead12W2Stages;
+                ptx::mbar_wait(&w2_empty[s], ((uint32_t)(c / kHead12W2Stages) & 1u) ^ 1u);
+                ptx::mbar_expect_tx(&w2_full[s], 32768u);
+                ptx::tma_load_3d(&mapW2, &w2_full[s], sW2 + (size_t)s * 32768, c * 64, 0, 0);     // K columns [64c, 64c + 64) of all 256 rows
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = make_idesc_bf16(128, 64), idesc2 = make_idesc_bf16(128, 256);
+            ptx::mbar_wait(x_full, 0);
+            ptx::tc_fence_after();
+            const uint64_t dx = make_kmajor_sw128_desc(ptx::smem_u32(sX));
+            for (int c = 0; c <= 8; c++) {
+                if (c < 8) {
+                    // MMA1: H1[:, 64c .. 64c+64) into TMEM buffer c & 1 (free once the epilogue has read chunk c - 2 out of it)
+                    ptx::mbar_wait(&ht_empty[c & 1], ((uint32_t)(c >> 1) & 1u) ^ 1u);
+                    ptx::tc_fence_after();
+                    const uint64_t dw = make_kmajor_sw128_desc(ptx::smem_u32(sW1 + (size_t)c * 8192));
+                    const uint32_t d1 = tmem_base + 256u + (uint32_t)((c & 1) * 64);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++) ptx::umma_bf16(d1, dx + (uint64_t)(k4 * 2), dw + (uint64_t)(k4 * 2), idesc1, k4 ? 1u : 0u);
+                    ptx::umma_commit(&ht_full[c & 1]);
+                }
+                if (c >= 1) {
+                    // MMA2: out += H1 chunk (c - 1) (bf16 in shared memory) . W2[:, chunk]^T
+                    const int cc = c - 1, s = cc % kHead12W2Stages;
+                    ptx::mbar_wait(&hs_full[cc & 1], (uint32_t)(cc >> 1) & 1u);
+                    ptx::mbar_wait(&w2_full[s], (uint32_t)(cc / kHead12W2Stages) & 1u);
+                    ptx::tc_fence_after();
+                    const uint64_t da = make_kmajor_sw128_desc(ptx::smem_u32(sH + (size_t)(cc & 1) * 16384));
+                    const uint64_t db = make_kmajor_sw128_desc(ptx::smem_u32(sW2 + (size_t)s * 32768));
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++) ptx::umma_bf16(tmem_base, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc2, (cc | k4) ? 1u : 0u);
+                    ptx::umma_commit(&w2_empty[s]);
+                    ptx::umma_commit(&hs_empty[cc & 1]);
+                }
+            }
+            ptx::umma_commit(acc_full);
+        }
+    } else {
+        // ---- epilogue warps: thread = row m of the tile (TMEM lane)
+        const int m = warp * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < 8; c++) {
+            const int buf = c & 1;
+            ptx::mbar_wait(&ht_full[buf], (uint32_t)(c >> 1) & 1u);
+            ptx::tc_fence_after();
+            uint32_t v0[32], v1[32];
+            ptx::tmem_ld32(tlane + 256u + (uint32_t)(buf * 64), v0);
+            ptx::tmem_ld32(tlane + 256u + (uint32_t)(buf * 64 + 32), v1);
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_fence(v0); ptx::tmem_ld_fence(v1);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(&ht_empty[buf])) : "memory");
+            uint32_t packed[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const float a0 = fmaxf(__uint_as_float(v0[j]) + s_cb[c * 64 + j], 0.f), a1 = fmaxf(__uint_as_float(v0[j + 1]) + s_cb[c * 64 + j + 1], 0.f);
+                const float b0 = fmaxf(__uint_as_float(v1[j]) + s_cb[c * 64 + 32 + j], 0.f), b1 = fmaxf(__uint_as_float(v1[j + 1]) + s_cb[c * 64 + 32 + j + 1], 0.f);
+                __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
+                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&ha);
+                packed[16 + (j >> 1)] = *reinterpret_cast<uint32_t *>(&hb);
+            }
+            // the MMA2 that read this shared-memory buffer (chunk c - 2) has retired
+            ptx::mbar_wait(&hs_empty[buf], ((uint32_t)(c >> 1) & 1u) ^ 1u);
+            uint8_t *rowp = sH + (size_t)buf * 16384 + (size_t)m * 128;
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                *reinterpret_cast<uint4 *>(rowp + ((q ^ (m & 7)) << 4)) = make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(&hs_full[buf])) : "memory");
+        }
+        // ---- layer-2 epilogue: +b2, ReLU, bf16, swizzled staging (W1a's buffer: every MMA1 has retired), TMA store
+        ptx::mbar_wait(acc_full, 0);
+        ptx::tc_fence_after();
+        uint8_t *stage = sW1;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t v[32];
+            ptx::tmem_ld32(tlane + (uint32_t)c0, v);
+            ptx::tmem_ld_wait();
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const float x0 = fmaxf(__uint_as_float(v[j]) + s_b2[c0 + j], 0.f), x1 = fmaxf(__uint_as_float(v[j + 1]) + s_b2[c0 + j + 1], 0.f);
+                __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            uint8_t *sub = stage + (size_t)(c0 >> 6) * 16384 + (size_t)m * 128;
+            const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                *reinterpret_cast<uint4 *>(sub + (((chunk0 + q) ^ (m & 7)) << 4)) = make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::named_barrier_sync(1, 128);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int st = 0; st < 4; st++) ptx::tma_store_3d(&mapOut, stage + (size_t)st * 16384, st * 64, row0, b);
+            ptx::tma_store_commit();
+            ptx::tma_store_wait_read();
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace mlp

@@ -21,6 +21,7 @@ struct Model {
     int forward(Scratch &scratch, const float *feat, int B, int D, float *out, cudaStream_t st, std::string &err);
     void release();
     int input_dim() const;
+    void set_fused_head(bool on);    // segmentation head layers 1 + 2 as one kernel (default) or as two GEMMs
     // inspection: copy one internal activation of the LAST forward (still in its scratch buffer) to `out` as fp32;
     // returns the element count (out == nullptr: query only) or a negative error
     long tap(const char *name, float *out, long cap, cudaStream_t st);

@@ -75,6 +75,8 @@ def lib() -> C.CDLL:
     L.ndnet_b200_model_destroy.argtypes = [vp]
     L.ndnet_b200_model_forward.restype = i
     L.ndnet_b200_model_forward.argtypes = [vp, vp, vp, i, i, vp, vp]
+    L.ndnet_b200_model_set_fused_head.restype = i
+    L.ndnet_b200_model_set_fused_head.argtypes = [vp, i]
     L.ndnet_b200_model_tap.restype = l
     L.ndnet_b200_model_tap.argtypes = [vp, vp, C.c_char_p, vp, l, vp]
     L.ndnet_b200_test_fail_next_reserve.restype = i
@@ -139,7 +141,7 @@ EXPORTED = [
     "ndnet_b200_last_kl_list", "ndnet_b200_selftest_div", "ndnet_b200_launch_count", "ndnet_b200_stage_timing", "ndnet_b200_stage_times",
     "ndnet_b200_last_search_passes",
     "ndnet_b200_model_create", "ndnet_b200_model_input_dim", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
-    "ndnet_b200_model_tap", "ndnet_b200_test_fail_next_reserve",
+    "ndnet_b200_model_tap", "ndnet_b200_model_set_fused_head", "ndnet_b200_test_fail_next_reserve",
     "ndnet_b200_infer_host", "ndnet_b200_infer_host_u8", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline", "ndnet_b200_set_device_chunk",
     "ndnet_b200_ply_load", "ndnet_b200_ply_num_points", "ndnet_b200_ply_sample", "ndnet_b200_ply_free",
     "ndnet_b200_trainer_create", "ndnet_b200_trainer_forward", "ndnet_b200_trainer_backward", "ndnet_b200_trainer_last_error",

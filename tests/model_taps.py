@@ -54,5 +54,7 @@ def library_tap(model, name, like):
     out = torch.empty(like.numel(), dtype=torch.float32, device=like.device)
     n = L.ndnet_b200_model_tap(model.engine.handle, model._h, name.encode(), out.data_ptr(), out.numel(),
                                torch.cuda.current_stream(like.device).cuda_stream)
+    if n == -307:
+        return None            # not materialised by this configuration (the fused head keeps "head.l1" on chip)
     assert n == like.numel(), (name, n, like.numel())
     return out.reshape(like.shape)
