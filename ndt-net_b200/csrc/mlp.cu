@@ -159,55 +159,86 @@ __global__ void __launch_bounds__(128) k_trunk_l1(const float *__restrict__ feat
     }
 }
 
-// y[b][o] = act(W[o] . x[b] + bias[o]) for B rows (the per-cloud FC stacks, ndtnet.py:54-60,189-191): a small
-// fp32 GEMM tiled through shared memory.  Block = 8 outputs x 32 batch rows (one output per warp, lane = batch
-// row) so that even a 32-scan chunk spreads a 512-wide layer over 64 CTAs; the x tile is stored transposed so both
-// operands are read conflict-free (w is a broadcast).  grid (ceil(out/8), ceil(B/32)), block 256.
+// y[b][o] = act(W[o] . x[b] + bias[o]) for B rows (the per-cloud FC stacks, ndtnet.py:54-60,189-191): an fp32 SIMT GEMM.
+// CTA tile = 32 rows (clouds) x 64 outputs, k-steps of 32; both operand tiles sit k-major in shared memory so that a thread
+// reads its 2 rows with one 8-byte load (a broadcast within the warp) and its 4 outputs with one 16-byte load: 10
+// instructions per 8 FMAs (the previous one-output-per-lane version issued 2 loads per FMA and took 95 us for the
+// 1024 -> 512 layer of 512 clouds).  grid (ceil(out/64), ceil(B/32)), block 256 = 16 (rows / 2) x 16 (outputs / 4).
+constexpr int kFcTM = 32, kFcTN = 64, kFcBK = 32;
+
 __global__ void __launch_bounds__(256) k_fc(const float *__restrict__ W, const float *__restrict__ bias, const void *__restrict__ xin,
                                             int ldx, int decode, float *__restrict__ y, int ldy, int B, int in, int out, int relu,
                                             int identity_dim, __nv_bfloat16 *__restrict__ y_t /*[B][dim][dim] transposed bf16*/) {
-    __shared__ float sx[128][33];
-    __shared__ float sw[8][129];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o0 = blockIdx.x * 8, r0 = blockIdx.y * 32;
-    float acc = 0.f;
-    for (int k0 = 0; k0 < in; k0 += 128) {
-#pragma unroll 4
-        for (int i = threadIdx.x; i < 32 * 128; i += 256) {
-            const int r = i >> 7, k = i & 127;
-            float xv = 0.f;
-            if (k0 + k < in && r0 + r < B) {
-                if (decode) xv = dec_f32(((const unsigned *)xin)[(size_t)(r0 + r) * ldx + k0 + k]);
-                else xv = ((const float *)xin)[(size_t)(r0 + r) * ldx + k0 + k];
+    __shared__ __align__(16) float sx[kFcBK][kFcTM];
+    __shared__ __align__(16) float sw[kFcBK][kFcTN];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int o0 = blockIdx.x * kFcTN, r0 = blockIdx.y * kFcTM;
+    float acc[2][4] = {};
+    // loaders: lanes run over rows / outputs (conflict-free transposing stores), 4 consecutive k per thread
+    const int xr = tid & 31, xk = (tid >> 5) * 4;            // x tile: 32 rows x 8 k-quads
+    const int wo = tid & 63, wk = (tid >> 6) * 4;            // w tile: 64 outputs x 4 k-quads, two passes (+16)
+    const bool vec = (in & 3) == 0 && (ldx & 3) == 0;
+    for (int k0 = 0; k0 < in; k0 += kFcBK) {
+        {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            const int r = r0 + xr, k = k0 + xk;
+            if (r < B) {
+                if (vec && k + 3 < in) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>((const unsigned *)xin + (size_t)r * ldx + k);
+                    v[0] = decode ? dec_f32(q.x) : __uint_as_float(q.x); v[1] = decode ? dec_f32(q.y) : __uint_as_float(q.y);
+                    v[2] = decode ? dec_f32(q.z) : __uint_as_float(q.z); v[3] = decode ? dec_f32(q.w) : __uint_as_float(q.w);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (k + j < in) v[j] = decode ? dec_f32(((const unsigned *)xin)[(size_t)r * ldx + k + j]) : ((const float *)xin)[(size_t)r * ldx + k + j];
+                }
             }
-            sx[k][r] = xv;
+#pragma unroll
+            for (int j = 0; j < 4; j++) sx[xk + j][xr] = v[j];
         }
 #pragma unroll
-        for (int i = threadIdx.x; i < 8 * 128; i += 256) {
-            const int r = i >> 7, k = i & 127;
-            sw[r][k] = (k0 + k < in && o0 + r < out) ? W[(size_t)(o0 + r) * in + k0 + k] : 0.f;
+        for (int pass = 0; pass < 2; pass++) {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            const int o = o0 + wo, k = k0 + wk + pass * 16;
+            if (o < out) {
+                if ((in & 3) == 0 && k + 3 < in) {
+                    const float4 q = *reinterpret_cast<const float4 *>(W + (size_t)o * in + k);
+                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (k + j < in) v[j] = W[(size_t)o * in + k + j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) sw[wk + pass * 16 + j][wo] = v[j];
         }
         __syncthreads();
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < 128; k += 4) {
-            a0 += sw[warp][k] * sx[k][lane];
-            a1 += sw[warp][k + 1] * sx[k + 1][lane];
-            a2 += sw[warp][k + 2] * sx[k + 2][lane];
-            a3 += sw[warp][k + 3] * sx[k + 3][lane];
+#pragma unroll
+        for (int k = 0; k < kFcBK; k++) {
+            const float2 a = *reinterpret_cast<const float2 *>(&sx[k][2 * ty]);
+            const float4 w = *reinterpret_cast<const float4 *>(&sw[k][4 * tx]);
+            acc[0][0] += a.x * w.x; acc[0][1] += a.x * w.y; acc[0][2] += a.x * w.z; acc[0][3] += a.x * w.w;
+            acc[1][0] += a.y * w.x; acc[1][1] += a.y * w.y; acc[1][2] += a.y * w.z; acc[1][3] += a.y * w.w;
         }
-        acc += (a0 + a1) + (a2 + a3);
         __syncthreads();
     }
-    const int row = r0 + lane, o = o0 + warp;
-    if (row >= B || o >= out) return;
-    float v = acc + (bias ? bias[o] : 0.f);
-    if (identity_dim > 0 && (o / identity_dim) == (o % identity_dim)) v += 1.f;   // + eye (ndtnet.py:59)
-    if (relu) v = fmaxf(v, 0.f);
-    y[(size_t)row * ldy + o] = v;
-    if (y_t) {
-        const int i = o / identity_dim, jj = o % identity_dim;
-        y_t[(size_t)row * identity_dim * identity_dim + (size_t)jj * identity_dim + i] = __float2bfloat16(v);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int row = r0 + 2 * ty + i;
+        if (row >= B) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int o = o0 + 4 * tx + j;
+            if (o >= out) continue;
+            float v = acc[i][j] + (bias ? bias[o] : 0.f);
+            if (identity_dim > 0 && (o / identity_dim) == (o % identity_dim)) v += 1.f;   // + eye (ndtnet.py:59)
+            if (relu) v = fmaxf(v, 0.f);
+            y[(size_t)row * ldy + o] = v;
+            if (y_t) {
+                const int ii = o / identity_dim, jj = o % identity_dim;
+                y_t[(size_t)row * identity_dim * identity_dim + (size_t)jj * identity_dim + ii] = __float2bfloat16(v);
+            }
+        }
     }
 }
 
@@ -538,7 +569,7 @@ struct Fwd {
             attr[dev & 63] = true;
         }
         Head12Args a{P, cbias, b2};
-        k_head12<<<dim3((P + 127) / 128, B), kGemmThreads, kHead12SmemBytes, st>>>(mx, mw1, mw2, mo, a);
+        k_head12<<<dim3((P + 127) / 128, B), kHead12Threads, kHead12SmemBytes, st>>>(mx, mw1, mw2, mo, a);
         ok = cudaGetLastError() == cudaSuccess;
         if (!ok) *err = "k_head12 launch failed";
         gemm_launches++;
@@ -556,7 +587,7 @@ struct Fwd {
     void fc(const float *W, const float *bias, const void *x, int ldx, bool decode, float *y, int ldy, int in, int out, bool relu,
             int identity_dim = 0, __nv_bfloat16 *y_t = nullptr) {
         if (!ok) return;
-        dim3 grid((out + 7) / 8, (B + 31) / 32);
+        dim3 grid((out + kFcTN - 1) / kFcTN, (B + kFcTM - 1) / kFcTM);
         k_fc<<<grid, 256, 0, st>>>(W, bias, x, ldx, decode ? 1 : 0, y, ldy, B, in, out, relu ? 1 : 0, identity_dim, y_t);
     }
 };

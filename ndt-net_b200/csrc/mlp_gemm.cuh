@@ -197,22 +197,32 @@ k_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtenso
             uint32_t v[32];
             ptx::tmem_ld32(taddr, v);
             ptx::tmem_ld_wait();
-            if (row < args.P) {
+            // The tile's rows are one contiguous block of the [B, P, n_valid] fp32 output (row stride = n_valid floats), so
+            // it goes through shared memory (row m at word m * n_valid: an odd stride for 29 classes, conflict-free) and
+            // leaves as consecutive words: a row-per-thread store would fill 4 bytes of every 32-byte sector it touches.
+            float *s_out = reinterpret_cast<float *>(smem);          // operand stages are dead (every MMA has retired)
+            const int nv = args.n_valid;
+            {
                 float x[32];
                 float mx = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
-                    x[j] = (j < args.n_valid) ? __uint_as_float(v[j]) + args.bias[j] : -INFINITY;
+                    x[j] = (j < nv) ? __uint_as_float(v[j]) + args.bias[j] : -INFINITY;
                     mx = fmaxf(mx, x[j]);
                 }
                 float sum = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; j++) if (j < args.n_valid) sum += __expf(x[j] - mx);
+                for (int j = 0; j < 32; j++) if (j < nv) sum += __expf(x[j] - mx);
                 const float lse = mx + __logf(sum);
-                float *o = args.outf + ((size_t)b * args.P + row) * args.n_valid;
 #pragma unroll
-                for (int j = 0; j < 32; j++) if (j < args.n_valid) o[j] = x[j] - lse;
+                for (int j = 0; j < 32; j++) if (j < nv) s_out[m * nv + j] = x[j] - lse;
             }
+            ptx::named_barrier_sync(1, 128);
+            int rows_here = args.P - a_row0; if (rows_here > 128) rows_here = 128;
+            float *o = args.outf + ((size_t)b * args.P + a_row0) * nv;
+            const int total = rows_here * nv;
+            for (int i = threadIdx.x; i < total; i += 128) o[i] = s_out[i];
+            (void)row;
         }
     }
     ptx::tc_fence_before();
@@ -387,10 +397,13 @@ k_gemm_chmax(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
 // The W2 chunks (32 KB each) stream through a TMA ring; W1a (64 KB) and the X tile are loaded once.  TMEM: columns
 // [0, 256) = out accumulator, [256, 320) and [320, 384) = the two H1 chunk buffers.  MMA1 of chunk c is issued before
 // MMA2 of chunk c - 1, so the tensor pipe works on chunk c while the epilogue warps convert chunk c - 1.
-// One CTA per (128-row tile, cloud); grid (ceil(P/128), B), block 192.  The unfused pair moved 1 GB per 512 scans through
-// HBM for this activation (write 524 MB + read 524 MB).
+// The conversion of a chunk (TMEM -> registers -> bias / ReLU / bf16 -> swizzled shared memory) paces the chain, so eight
+// epilogue warps share it: warp w owns TMEM lanes 32 (w % 4) .. +32 (the hardware's rule) and the column half w / 4.
+// One CTA per (128-row tile, cloud); grid (ceil(P/128), B), block 320 (warps 0-7 epilogue, 8 TMA, 9 MMA).  The unfused pair
+// moved 1 GB per 512 scans through HBM for this activation (write 524 MB + read 524 MB).
 // ------------------------------------------------------------------------------------------------
 constexpr int kHead12W2Stages = 2;
+constexpr int kHead12Threads = 320;
 constexpr size_t kHead12SmemBytes = 16384 /*X*/ + 65536 /*W1a, later the output staging*/ + kHead12W2Stages * 32768 /*W2 ring*/ +
                                     2 * 16384 /*H1 bf16 chunk buffers*/ + 1024 /*align*/ + 256 /*barriers*/ + 512 * 4 + 256 * 4;
 
@@ -400,7 +413,7 @@ struct Head12Args {
     const float *bias2;     // [256]
 };
 
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kHead12Threads)
 k_head12(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
          const __grid_constant__ CUtensorMap mapOut, const Head12Args args) {
     extern __shared__ uint8_t smem_raw[];
@@ -424,21 +437,21 @@ k_head12(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     if (threadIdx.x == 0) {
         ptx::mbar_init(x_full, 1); ptx::mbar_init(acc_full, 1);
         for (int s = 0; s < kHead12W2Stages; s++) { ptx::mbar_init(&w2_full[s], 1); ptx::mbar_init(&w2_empty[s], 1); }
-        for (int i = 0; i < 2; i++) { ptx::mbar_init(&ht_full[i], 1); ptx::mbar_init(&ht_empty[i], 4); ptx::mbar_init(&hs_full[i], 4); ptx::mbar_init(&hs_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { ptx::mbar_init(&ht_full[i], 1); ptx::mbar_init(&ht_empty[i], 8); ptx::mbar_init(&hs_full[i], 8); ptx::mbar_init(&hs_empty[i], 1); }
         ptx::fence_barrier_init();
     }
-    if (warp == 4 && lane == 0) { ptx::prefetch_tmap(&mapX); ptx::prefetch_tmap(&mapW1); ptx::prefetch_tmap(&mapW2); ptx::prefetch_tmap(&mapOut); }
-    if (threadIdx.x < 128) {
-        for (int i = threadIdx.x; i < 512; i += 128) s_cb[i] = args.cbias[(size_t)b * 512 + i];
-        for (int i = threadIdx.x; i < 256; i += 128) s_b2[i] = args.bias2[i];
+    if (warp == 8 && lane == 0) { ptx::prefetch_tmap(&mapX); ptx::prefetch_tmap(&mapW1); ptx::prefetch_tmap(&mapW2); ptx::prefetch_tmap(&mapOut); }
+    if (threadIdx.x < 256) {
+        for (int i = threadIdx.x; i < 512; i += 256) s_cb[i] = args.cbias[(size_t)b * 512 + i];
+        s_b2[threadIdx.x] = args.bias2[threadIdx.x];
     }
-    if (warp == 5) ptx::tmem_alloc(tmem_slot, 512);
+    if (warp == 9) ptx::tmem_alloc(tmem_slot, 512);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             ptx::mbar_expect_tx(x_full, 16384u + 65536u);
             ptx::tma_load_3d(&mapX, x_full, sX, 0, row0, b);
@@ -451,7 +464,7 @@ k_head12(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 ptx::tma_load_3d(&mapW2, &w2_full[s], sW2 + (size_t)s * 32768, c * 64, 0, 0);     // K columns [64c, 64c + 64) of all 256 rows
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         if (lane == 0) {
             constexpr uint32_t idesc1 = make_idesc_bf16(128, 64), idesc2 = make_idesc_bf16(128, 256);
             ptx::mbar_wait(x_full, 0);
@@ -485,36 +498,34 @@ k_head12(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
             ptx::umma_commit(acc_full);
         }
     } else {
-        // ---- epilogue warps: thread = row m of the tile (TMEM lane)
-        const int m = warp * 32 + lane;
-        const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        // ---- epilogue warps: thread = row m of the tile (TMEM lane quadrant warp % 4), column half warp / 4
+        const int m = (warp & 3) * 32 + lane, half = warp >> 2;
+        const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         for (int c = 0; c < 8; c++) {
             const int buf = c & 1;
             ptx::mbar_wait(&ht_full[buf], (uint32_t)(c >> 1) & 1u);
             ptx::tc_fence_after();
-            uint32_t v0[32], v1[32];
-            ptx::tmem_ld32(tlane + 256u + (uint32_t)(buf * 64), v0);
-            ptx::tmem_ld32(tlane + 256u + (uint32_t)(buf * 64 + 32), v1);
+            uint32_t v[32];
+            ptx::tmem_ld32(tlane + 256u + (uint32_t)(buf * 64 + half * 32), v);
             ptx::tmem_ld_wait();
-            ptx::tmem_ld_fence(v0); ptx::tmem_ld_fence(v1);
+            ptx::tmem_ld_fence(v);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(&ht_empty[buf])) : "memory");
-            uint32_t packed[32];
+            uint32_t packed[16];
+            const float *cb = s_cb + c * 64 + half * 32;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-                const float a0 = fmaxf(__uint_as_float(v0[j]) + s_cb[c * 64 + j], 0.f), a1 = fmaxf(__uint_as_float(v0[j + 1]) + s_cb[c * 64 + j + 1], 0.f);
-                const float b0 = fmaxf(__uint_as_float(v1[j]) + s_cb[c * 64 + 32 + j], 0.f), b1 = fmaxf(__uint_as_float(v1[j + 1]) + s_cb[c * 64 + 32 + j + 1], 0.f);
-                __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
-                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&ha);
-                packed[16 + (j >> 1)] = *reinterpret_cast<uint32_t *>(&hb);
+                const float a0 = fmaxf(__uint_as_float(v[j]) + cb[j], 0.f), a1 = fmaxf(__uint_as_float(v[j + 1]) + cb[j + 1], 0.f);
+                __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
             }
             // the MMA2 that read this shared-memory buffer (chunk c - 2) has retired
             ptx::mbar_wait(&hs_empty[buf], ((uint32_t)(c >> 1) & 1u) ^ 1u);
             uint8_t *rowp = sH + (size_t)buf * 16384 + (size_t)m * 128;
 #pragma unroll
-            for (int q = 0; q < 8; q++)
-                *reinterpret_cast<uint4 *>(rowp + ((q ^ (m & 7)) << 4)) = make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+            for (int q = 0; q < 4; q++)
+                *reinterpret_cast<uint4 *>(rowp + (((half * 4 + q) ^ (m & 7)) << 4)) = make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(&hs_full[buf])) : "memory");
@@ -524,7 +535,7 @@ k_head12(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
         ptx::tc_fence_after();
         uint8_t *stage = sW1;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
             uint32_t v[32];
             ptx::tmem_ld32(tlane + (uint32_t)c0, v);
             ptx::tmem_ld_wait();
@@ -542,7 +553,7 @@ k_head12(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
                 *reinterpret_cast<uint4 *>(sub + (((chunk0 + q) ^ (m & 7)) << 4)) = make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
         }
         ptx::fence_proxy_async_smem();
-        ptx::named_barrier_sync(1, 128);
+        ptx::named_barrier_sync(1, 256);
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int st = 0; st < 4; st++) ptx::tma_store_3d(&mapOut, stage + (size_t)st * 16384, st * 64, row0, b);
@@ -552,7 +563,7 @@ k_head12(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 5) ptx::tmem_dealloc(tmem_base, 512);
+    if (warp == 9) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace mlp
