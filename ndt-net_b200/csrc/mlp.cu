@@ -160,65 +160,67 @@ __global__ void __launch_bounds__(128) k_trunk_l1(const float *__restrict__ feat
 }
 
 // y[b][o] = act(W[o] . x[b] + bias[o]) for B rows (the per-cloud FC stacks, ndtnet.py:54-60,189-191): an fp32 SIMT GEMM.
-// CTA tile = 32 rows (clouds) x 64 outputs, k-steps of 32; both operand tiles sit k-major in shared memory so that a thread
-// reads its 2 rows with one 8-byte load (a broadcast within the warp) and its 4 outputs with one 16-byte load: 10
-// instructions per 8 FMAs (the previous one-output-per-lane version issued 2 loads per FMA and took 95 us for the
-// 1024 -> 512 layer of 512 clouds).  grid (ceil(out/64), ceil(B/32)), block 256 = 16 (rows / 2) x 16 (outputs / 4).
+// CTA tile = 32 rows (clouds) x 64 outputs, k-steps of 32, operands of the next step prefetched into registers.  The weights
+// are stored transposed ([in][out_pad]), so a warp's 16-byte loads cover whole 128-byte lines of four input channels and go
+// to shared memory as they are; the x tile is transposed on the way in (padded rows: conflict-free).  A thread multiplies its
+// 2 rows by its 4 outputs: 11 instructions per 8 FMAs.  grid (ceil(out/64), ceil(B/32)), block 256 = 16 x 16.
 constexpr int kFcTM = 32, kFcTN = 64, kFcBK = 32;
 
-__global__ void __launch_bounds__(256) k_fc(const float *__restrict__ W, const float *__restrict__ bias, const void *__restrict__ xin,
-                                            int ldx, int decode, float *__restrict__ y, int ldy, int B, int in, int out, int relu,
-                                            int identity_dim, __nv_bfloat16 *__restrict__ y_t /*[B][dim][dim] transposed bf16*/) {
-    __shared__ __align__(16) float sx[kFcBK][kFcTM];
+__global__ void __launch_bounds__(256) k_fc(const float *__restrict__ Wt /*[in][ldw]*/, int ldw, const float *__restrict__ bias,
+                                            const void *__restrict__ xin, int ldx, int decode, float *__restrict__ y, int ldy, int B, int in,
+                                            int out, int relu, int identity_dim, __nv_bfloat16 *__restrict__ y_t /*[B][dim][dim] transposed bf16*/) {
+    __shared__ float sx[kFcBK][kFcTM + 1];
     __shared__ __align__(16) float sw[kFcBK][kFcTN];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int o0 = blockIdx.x * kFcTN, r0 = blockIdx.y * kFcTM;
     float acc[2][4] = {};
-    // loaders: lanes run over rows / outputs (conflict-free transposing stores), 4 consecutive k per thread
-    const int xr = tid & 31, xk = (tid >> 5) * 4;            // x tile: 32 rows x 8 k-quads
-    const int wo = tid & 63, wk = (tid >> 6) * 4;            // w tile: 64 outputs x 4 k-quads, two passes (+16)
+    const int xr = tid >> 3, xk = (tid & 7) * 4;             // x tile: row tid / 8, four consecutive k (lanes run along k: coalesced)
+    const int wk = tid >> 4, wo = (tid & 15) * 4;            // w tile: input channel tid / 16 (+16), four consecutive outputs
     const bool vec = (in & 3) == 0 && (ldx & 3) == 0;
-    for (int k0 = 0; k0 < in; k0 += kFcBK) {
+    float xv[4], wv[2][4];
+    auto fetch = [&](int k0) {
         {
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
             const int r = r0 + xr, k = k0 + xk;
+#pragma unroll
+            for (int j = 0; j < 4; j++) xv[j] = 0.f;
             if (r < B) {
                 if (vec && k + 3 < in) {
                     const uint4 q = *reinterpret_cast<const uint4 *>((const unsigned *)xin + (size_t)r * ldx + k);
-                    v[0] = decode ? dec_f32(q.x) : __uint_as_float(q.x); v[1] = decode ? dec_f32(q.y) : __uint_as_float(q.y);
-                    v[2] = decode ? dec_f32(q.z) : __uint_as_float(q.z); v[3] = decode ? dec_f32(q.w) : __uint_as_float(q.w);
+                    xv[0] = decode ? dec_f32(q.x) : __uint_as_float(q.x); xv[1] = decode ? dec_f32(q.y) : __uint_as_float(q.y);
+                    xv[2] = decode ? dec_f32(q.z) : __uint_as_float(q.z); xv[3] = decode ? dec_f32(q.w) : __uint_as_float(q.w);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (k + j < in) v[j] = decode ? dec_f32(((const unsigned *)xin)[(size_t)r * ldx + k + j]) : ((const float *)xin)[(size_t)r * ldx + k + j];
+                        if (k + j < in) xv[j] = decode ? dec_f32(((const unsigned *)xin)[(size_t)r * ldx + k + j]) : ((const float *)xin)[(size_t)r * ldx + k + j];
                 }
             }
-#pragma unroll
-            for (int j = 0; j < 4; j++) sx[xk + j][xr] = v[j];
         }
 #pragma unroll
         for (int pass = 0; pass < 2; pass++) {
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            const int o = o0 + wo, k = k0 + wk + pass * 16;
-            if (o < out) {
-                if ((in & 3) == 0 && k + 3 < in) {
-                    const float4 q = *reinterpret_cast<const float4 *>(W + (size_t)o * in + k);
-                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-                } else {
+            const int k = k0 + wk + pass * 16, o = o0 + wo;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) if (k + j < in) v[j] = W[(size_t)o * in + k + j];
-                }
+            for (int j = 0; j < 4; j++) wv[pass][j] = 0.f;
+            if (k < in && o < ldw) {                          // ldw is a multiple of 4 and the padding columns hold zeros
+                const float4 q = *reinterpret_cast<const float4 *>(Wt + (size_t)k * ldw + o);
+                wv[pass][0] = q.x; wv[pass][1] = q.y; wv[pass][2] = q.z; wv[pass][3] = q.w;
             }
-#pragma unroll
-            for (int j = 0; j < 4; j++) sw[wk + pass * 16 + j][wo] = v[j];
         }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < in; k0 += kFcBK) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) sx[xk + j][xr] = xv[j];
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++)
+            *reinterpret_cast<float4 *>(&sw[wk + pass * 16][wo]) = make_float4(wv[pass][0], wv[pass][1], wv[pass][2], wv[pass][3]);
         __syncthreads();
+        if (k0 + kFcBK < in) fetch(k0 + kFcBK);          // the next step's operands travel while this one is multiplied
 #pragma unroll
         for (int k = 0; k < kFcBK; k++) {
-            const float2 a = *reinterpret_cast<const float2 *>(&sx[k][2 * ty]);
+            const float a0 = sx[k][2 * ty], a1 = sx[k][2 * ty + 1];
             const float4 w = *reinterpret_cast<const float4 *>(&sw[k][4 * tx]);
-            acc[0][0] += a.x * w.x; acc[0][1] += a.x * w.y; acc[0][2] += a.x * w.z; acc[0][3] += a.x * w.w;
-            acc[1][0] += a.y * w.x; acc[1][1] += a.y * w.y; acc[1][2] += a.y * w.z; acc[1][3] += a.y * w.w;
+            acc[0][0] += a0 * w.x; acc[0][1] += a0 * w.y; acc[0][2] += a0 * w.z; acc[0][3] += a0 * w.w;
+            acc[1][0] += a1 * w.x; acc[1][1] += a1 * w.y; acc[1][2] += a1 * w.z; acc[1][3] += a1 * w.w;
         }
         __syncthreads();
     }
@@ -390,6 +392,15 @@ bool up_f32(ModelImpl &m, const std::vector<float> &h, float *&d) {
     m.allocs.push_back(d);
     return cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
 }
+// fp32 weight [out][in] uploaded TRANSPOSED ([in][out_pad], out_pad = out rounded up to 4): k_fc reads four consecutive
+// outputs of one input channel with a single 16-byte load, coalesced over the outputs
+bool up_f32_t(ModelImpl &m, const Folded &f, float *&d) {
+    const int op = (f.out + 3) / 4 * 4;
+    std::vector<float> t((size_t)f.in * op, 0.f);
+    for (int o = 0; o < f.out; o++)
+        for (int k = 0; k < f.in; k++) t[(size_t)k * op + o] = f.w[(size_t)o * f.in + k];
+    return up_f32(m, t, d);
+}
 bool up_bf16(ModelImpl &m, const float *h, size_t n, __nv_bfloat16 *&d) {
     std::vector<uint16_t> tmp(n);
     for (size_t i = 0; i < n; i++) tmp[i] = f2bf(h[i]);
@@ -408,8 +419,8 @@ bool build_tnet(ModelImpl &m, const TensorMapHost &t, const std::string &p, int 
     bool ok = true;
     if (in != 64) ok = ok && up_f32(m, a.w, w.l1_w); else ok = ok && up_bf16(m, a.w.data(), a.w.size(), w.l1_wb);
     ok = ok && up_f32(m, a.b, w.l1_b) && up_bf16(m, b.w.data(), b.w.size(), w.l2_w) && up_f32(m, b.b, w.l2_b) &&
-         up_bf16(m, c.w.data(), c.w.size(), w.l3_w) && up_f32(m, c.b, w.l3_b) && up_f32(m, f1.w, w.fc1_w) && up_f32(m, f1.b, w.fc1_b) &&
-         up_f32(m, f2.w, w.fc2_w) && up_f32(m, f2.b, w.fc2_b) && up_f32(m, f3.w, w.fc3_w) && up_f32(m, f3.b, w.fc3_b);
+         up_bf16(m, c.w.data(), c.w.size(), w.l3_w) && up_f32(m, c.b, w.l3_b) && up_f32_t(m, f1, w.fc1_w) && up_f32(m, f1.b, w.fc1_b) &&
+         up_f32_t(m, f2, w.fc2_w) && up_f32(m, f2.b, w.fc2_b) && up_f32_t(m, f3, w.fc3_w) && up_f32(m, f3.b, w.fc3_b);
     if (!ok) err = "device upload failed";
     return ok;
 }
@@ -451,7 +462,8 @@ int Model::build(int kind, int n_tensors, const char *const *names, const float 
             for (int k = 0; k < 64; k++) wa[(size_t)o * 64 + k] = h1.w[(size_t)o * h1.in + k];              // x_t2 part (cat order ndtnet.py:230)
             for (int k = 0; k < m.F; k++) wg[(size_t)o * m.F + k] = h1.w[(size_t)o * h1.in + 64 + k];       // global-feature part
         }
-        ok = ok && up_bf16(m, wa.data(), wa.size(), m.h1a_w) && up_f32(m, wg, m.h1g_w) && up_f32(m, h1.b, m.h1_b) &&
+        Folded fg; fg.out = 512; fg.in = m.F; fg.w = wg;
+        ok = ok && up_bf16(m, wa.data(), wa.size(), m.h1a_w) && up_f32_t(m, fg, m.h1g_w) && up_f32(m, h1.b, m.h1_b) &&
              up_bf16(m, h2.w.data(), h2.w.size(), m.h2_w) && up_f32(m, h2.b, m.h2_b) && up_bf16(m, h3.w.data(), h3.w.size(), m.h3_w) &&
              up_f32(m, h3.b, m.h3_b) && up_bf16(m, h4.w.data(), h4.w.size(), m.h4_w) && up_f32(m, h4.b, m.h4_b);
     } else {
@@ -459,8 +471,8 @@ int Model::build(int kind, int n_tensors, const char *const *names, const float 
         if (!fold(t, "conv1", "", k1, err) || !fold(t, "conv2", "", k2, err) || !fold(t, "conv3", "", k3, err)) return -301;
         if (k1.in != m.F || k1.out != 512 || k2.in != 512 || k2.out != 256 || k3.in != 256) { err = "unexpected classification head shapes"; return -302; }
         m.ncls = k3.out;
-        ok = ok && up_f32(m, k1.w, m.k1_w) && up_f32(m, k1.b, m.k1_b) && up_f32(m, k2.w, m.k2_w) && up_f32(m, k2.b, m.k2_b) &&
-             up_f32(m, k3.w, m.k3_w) && up_f32(m, k3.b, m.k3_b);
+        ok = ok && up_f32_t(m, k1, m.k1_w) && up_f32(m, k1.b, m.k1_b) && up_f32_t(m, k2, m.k2_w) && up_f32(m, k2.b, m.k2_b) &&
+             up_f32_t(m, k3, m.k3_w) && up_f32(m, k3.b, m.k3_b);
     }
     if (!ok) { err = "device upload failed"; return -303; }
     return 0;
@@ -588,7 +600,7 @@ struct Fwd {
             int identity_dim = 0, __nv_bfloat16 *y_t = nullptr) {
         if (!ok) return;
         dim3 grid((out + kFcTN - 1) / kFcTN, (B + kFcTM - 1) / kFcTM);
-        k_fc<<<grid, 256, 0, st>>>(W, bias, x, ldx, decode ? 1 : 0, y, ldy, B, in, out, relu ? 1 : 0, identity_dim, y_t);
+        k_fc<<<grid, 256, 0, st>>>(W, (out + 3) / 4 * 4, bias, x, ldx, decode ? 1 : 0, y, ldy, B, in, out, relu ? 1 : 0, identity_dim, y_t);
     }
 };
 
