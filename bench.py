@@ -235,6 +235,7 @@ def run_ours(args):
     net = build_network(dev)
     model = B200Model(net, KIND_SEG, dev)
     out_host = torch.empty((B, N_NDS, N_CLASSES + 1), dtype=torch.float32).pin_memory()
+    out_host2 = [out_host, torch.empty((B, N_NDS, N_CLASSES + 1), dtype=torch.float32).pin_memory()]
     stream = torch.cuda.current_stream(dev)
 
     model.set_pipeline(args.lanes, args.chunk, args.device_chunk)
@@ -244,6 +245,19 @@ def run_ours(args):
 
     def step_host(i):
         return model.infer_host(host_pts[i % n_sets], N_NDS, host_lab[i % n_sets], N_CLASSES, out_host)
+
+    batch_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def step_host_async(i):
+        # a serving loop with two batches in flight: batch i's results land in its own pinned buffer; the call returns once
+        # the copies and kernels are enqueued, so batch i + 1's host->device copies overlap batch i's kernels.  Both the
+        # H2D of the scans and the D2H of the log-probabilities of EVERY step are inside the timed region (the events
+        # bracket the stream all of them are ordered on).
+        if i >= 2:
+            batch_done[i % 2].synchronize()     # batch i - 2 has its results in host memory: out_host2[i % 2] is free again
+        out = model.infer_host(host_pts[i % n_sets], N_NDS, host_lab[i % n_sets], N_CLASSES, out_host2[i % 2], wait=False)
+        batch_done[i % 2].record(stream)
+        return out
 
     from ndnet_b200 import dist as ndist
 
@@ -318,7 +332,9 @@ def run_ours(args):
     launches0 = L.ndnet_b200_launch_count()
     ms = timed(step_device, args.steps)
     launches = L.ndnet_b200_launch_count() - launches0
-    ms_e2e = timed(step_host, args.steps)
+    ms_e2e_sync = timed(step_host, args.steps)
+    ms_e2e = timed(step_host_async, args.steps)
+    model.infer_wait()
     clocks = sampler.stop()
     ms_h2d = h2d_ceiling(args.steps)
     ms_copies = h2d_ceiling(args.steps, with_d2h=True)
@@ -377,7 +393,11 @@ def run_ours(args):
                    "l2": f"inputs rotate over {n_sets} resident batches ({n_sets * B * ALGO_BYTES_PER_CLOUD / 1e6:.0f} MB vs 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": "clouds/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": B * N_POINTS * 13, "d2h_bytes_per_step": B * N_NDS * (N_CLASSES + 1) * 4,
-                "labels": "uint8 (29 classes; ndnet_b200_infer_host_u8)",
+                "labels": "uint8 (29 classes)",
+                "api": "ndnet_b200_infer_host_async, two batches in flight (the next batch's copies overlap this batch's kernels); "
+                       "every step's H2D and D2H are inside the timed region",
+                "one_batch_at_a_time": {"value": clouds / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync / args.steps,
+                                        "api": "ndnet_b200_infer_host_u8 (returns with the results in host memory)"},
                 # the same bytes, same chunks and lanes, copies only: what PCIe gives this rank count on this box
                 "h2d_ceiling_ms": ms_h2d / args.steps,
                 "h2d_gbs_aggregate": world * B * N_POINTS * 13 / (ms_h2d / args.steps * 1e-3) / 1e9,

@@ -200,6 +200,14 @@ int ndnet_b200_infer_host(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const vo
 int ndnet_b200_infer_host_u8(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const void *points, int dtype,
                              const uint8_t *labels, int B, long N, int num_classes, long num_desired, float *out_host,
                              long out_elems_per_cloud, void *stream);
+/* Asynchronous form for a caller that keeps several batches in flight (a serving loop): returns once the copies and kernels
+ * are enqueued; `out_host` is valid after ndnet_b200_infer_wait (or a synchronise of `stream`).  Consecutive calls overlap -
+ * the copies of one batch travel while the kernels of the previous one drain - so every call needs its own `out_host`, and the
+ * input buffers must stay untouched until the wait.  labels_u8 != 0: `labels` holds one byte per point. */
+int ndnet_b200_infer_host_async(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const void *points, int dtype, const void *labels,
+                                int labels_u8, int B, long N, int num_classes, long num_desired, float *out_host,
+                                long out_elems_per_cloud, void *stream);
+int ndnet_b200_infer_wait(ndnet_b200_ctx *ctx, void *stream);
 /* Same with DEVICE buffers in and out, asynchronous (the caller's stream waits for the result). */
 int ndnet_b200_infer_device(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const void *points, int dtype,
                             const uint16_t *labels, int B, long N, int num_classes, long num_desired, float *out_dev,

@@ -332,7 +332,7 @@ extern "C" int ndnet_b200_set_device_chunk(ndnet_b200_ctx *c, int chunk) {
 
 static int infer_pipelined(ndnet_b200_ctx *c, ndnet_b200_model *model, const void *points, int dtype, const uint16_t *labels,
                            int B, long N, int num_classes, long D, float *out, long out_elems_per_cloud, cudaStream_t user,
-                           bool host_io, unsigned label_flags = 0) {
+                           bool host_io, unsigned label_flags = 0, bool synchronise = true) {
     const size_t lsz = (label_flags & NDNET_B200_LABELS_U8) ? 1 : 2;      // bytes per point label
     cudaError_t e = cudaSetDevice(c->device);
     if (e != cudaSuccess) return fail(c, e, "cudaSetDevice");
@@ -349,8 +349,11 @@ static int infer_pipelined(ndnet_b200_ctx *c, ndnet_b200_model *model, const voi
     }
     const size_t esz = dtype == 0 ? 4 : 8;
     // everything already enqueued on the caller's stream happens before the lanes start
-    if ((e = cudaEventRecord(c->start_ev, user)) != cudaSuccess) return fail(c, e, "event record");
-    if (host_io && (e = cudaStreamWaitEvent(c->copy_stream, c->start_ev, 0)) != cudaSuccess) return fail(c, e, "stream wait");
+    // Device buffers: what the caller enqueued on its stream (the producer of the scans) comes first.  Host buffers are
+    // ready when the call is made, and the library's own buffers are protected by the order of the lanes' streams and the
+    // `consumed` events, so a host call does not wait for the caller's stream: consecutive asynchronous calls overlap
+    // (the copies of one batch travel while the kernels of the previous one drain).
+    if (!host_io && (e = cudaEventRecord(c->start_ev, user)) != cudaSuccess) return fail(c, e, "event record");
     const int L = (int)c->lanes.size();
     // chunk size: host buffers - at most c->chunk, and a small batch is spread over all lanes so that every copy overlaps
     // kernels; device buffers - c->chunk_device (measured on B200, 512 scans: 4 x 128 beats 8 x 64 by 3-4 %, 1 x 512 loses 3 %)
@@ -360,7 +363,7 @@ static int infer_pipelined(ndnet_b200_ctx *c, ndnet_b200_model *model, const voi
     for (int b0 = 0; b0 < B; b0 += chunk, lane_i = (lane_i + 1) % L) {
         const int nb = B - b0 < chunk ? B - b0 : chunk;
         ndnet_b200_ctx::Lane &l = c->lanes[lane_i];
-        if ((e = cudaStreamWaitEvent(l.stream, c->start_ev, 0)) != cudaSuccess) return fail(c, e, "stream wait");
+        if (!host_io && (e = cudaStreamWaitEvent(l.stream, c->start_ev, 0)) != cudaSuccess) return fail(c, e, "stream wait");
         const char *psrc = (const char *)points + (size_t)b0 * N * 3 * esz;
         const uint16_t *lsrc = labels ? (const uint16_t *)((const char *)labels + (size_t)b0 * N * lsz) : nullptr;
         float *odst = out + (size_t)b0 * out_elems_per_cloud;
@@ -396,7 +399,7 @@ static int infer_pipelined(ndnet_b200_ctx *c, ndnet_b200_model *model, const voi
         if ((e = cudaEventRecord(l.done, l.stream)) != cudaSuccess) return fail(c, e, "event record");
         if ((e = cudaStreamWaitEvent(user, l.done, 0)) != cudaSuccess) return fail(c, e, "stream wait");
     }
-    if (host_io && (e = cudaStreamSynchronize(user)) != cudaSuccess) return fail(c, e, "stream synchronise");
+    if (host_io && synchronise && (e = cudaStreamSynchronize(user)) != cudaSuccess) return fail(c, e, "stream synchronise");
     return 0;
 }
 
@@ -416,6 +419,24 @@ extern "C" int ndnet_b200_infer_host_u8(ndnet_b200_ctx *c, ndnet_b200_model *mod
     if (!c || !model || !points || !out_host || B <= 0 || N < 0 || D <= 0 || (dtype != 0 && dtype != 1) || num_classes > 255) return -200;
     return infer_pipelined(c, model, points, dtype, (const uint16_t *)labels, B, N, num_classes, D, out_host, out_elems_per_cloud,
                            (cudaStream_t)stream, true, NDNET_B200_LABELS_U8);
+}
+
+// Asynchronous form of the host-buffer call: returns once everything is enqueued; the results are in `out_host` after the
+// caller's stream has been synchronised (cudaStreamSynchronize / ndnet_b200_infer_wait).  labels_u8 != 0: one byte per label.
+extern "C" int ndnet_b200_infer_host_async(ndnet_b200_ctx *c, ndnet_b200_model *model, const void *points, int dtype,
+                                           const void *labels, int labels_u8, int B, long N, int num_classes, long D,
+                                           float *out_host, long out_elems_per_cloud, void *stream) {
+    if (!c || !model || !points || !out_host || B <= 0 || N < 0 || D <= 0 || (dtype != 0 && dtype != 1)) return -200;
+    if (labels_u8 && num_classes > 255) return -200;
+    return infer_pipelined(c, model, points, dtype, (const uint16_t *)labels, B, N, num_classes, D, out_host, out_elems_per_cloud,
+                           (cudaStream_t)stream, true, labels_u8 ? NDNET_B200_LABELS_U8 : 0u, false);
+}
+
+extern "C" int ndnet_b200_infer_wait(ndnet_b200_ctx *c, void *stream) {
+    if (!c) return -200;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail(c, e, "stream synchronise");
 }
 
 // Same from/to DEVICE buffers; asynchronous: on return the caller's stream waits for the result.

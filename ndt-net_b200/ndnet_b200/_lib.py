@@ -85,6 +85,10 @@ def lib() -> C.CDLL:
     L.ndnet_b200_infer_host.argtypes = [vp, vp, vp, i, vp, i, l, i, l, vp, l, vp]
     L.ndnet_b200_infer_host_u8.restype = i
     L.ndnet_b200_infer_host_u8.argtypes = [vp, vp, vp, i, vp, i, l, i, l, vp, l, vp]
+    L.ndnet_b200_infer_host_async.restype = i
+    L.ndnet_b200_infer_host_async.argtypes = [vp, vp, vp, i, vp, i, i, l, i, l, vp, l, vp]
+    L.ndnet_b200_infer_wait.restype = i
+    L.ndnet_b200_infer_wait.argtypes = [vp, vp]
     L.ndnet_b200_infer_device.restype = i
     L.ndnet_b200_infer_device.argtypes = [vp, vp, vp, i, vp, i, l, i, l, vp, l, vp]
     L.ndnet_b200_set_pipeline.restype = i
@@ -142,7 +146,7 @@ EXPORTED = [
     "ndnet_b200_last_search_passes",
     "ndnet_b200_model_create", "ndnet_b200_model_input_dim", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
     "ndnet_b200_model_tap", "ndnet_b200_model_set_fused_head", "ndnet_b200_test_fail_next_reserve",
-    "ndnet_b200_infer_host", "ndnet_b200_infer_host_u8", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline", "ndnet_b200_set_device_chunk",
+    "ndnet_b200_infer_host", "ndnet_b200_infer_host_u8", "ndnet_b200_infer_host_async", "ndnet_b200_infer_wait", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline", "ndnet_b200_set_device_chunk",
     "ndnet_b200_ply_load", "ndnet_b200_ply_num_points", "ndnet_b200_ply_sample", "ndnet_b200_ply_free",
     "ndnet_b200_trainer_create", "ndnet_b200_trainer_forward", "ndnet_b200_trainer_backward", "ndnet_b200_trainer_last_error",
     "ndnet_b200_trainer_backward_flat", "ndnet_b200_trainer_grad_layout", "ndnet_b200_trainer_set_graph",

@@ -96,9 +96,11 @@ class B200Model:
 
 
     def infer_host(self, points: torch.Tensor, num_desired: int, labels: torch.Tensor | None, num_classes: int,
-                   out: torch.Tensor) -> torch.Tensor:
+                   out: torch.Tensor, wait: bool = True) -> torch.Tensor:
         """HOST tensors in (pinned for speed), HOST tensor out: H2D + NDT + forward + D2H + sync in one C call.
-        labels: int16/uint16 [B, N] (the reference's dtype) or uint8 [B, N] (one byte per point, num_classes <= 255)."""
+        labels: int16/uint16 [B, N] (the reference's dtype) or uint8 [B, N] (one byte per point, num_classes <= 255).
+        wait=False: returns once everything is enqueued (several batches in flight: the next batch's copies overlap this
+        one's kernels); `out` is valid after `infer_wait()`, and every batch in flight needs its own `out`."""
         assert not points.is_cuda and points.is_contiguous() and not out.is_cuda
         B, N, _ = points.shape
         per_cloud = out.numel() // B
@@ -108,6 +110,16 @@ class B200Model:
             assert labels.is_contiguous() and labels.dtype in (torch.int16, torch.uint16, torch.uint8)
             if labels.dtype == torch.uint8:
                 fn = self._L.ndnet_b200_infer_host_u8
+        if not wait:
+            with torch.cuda.device(self.device):
+                rc = self._L.ndnet_b200_infer_host_async(
+                    self.engine.handle, self._h, points.data_ptr(), _lib.F32 if points.dtype == torch.float32 else _lib.F64,
+                    labels.data_ptr() if labels is not None else None, int(labels is not None and labels.dtype == torch.uint8),
+                    B, N, int(num_classes), int(num_desired), out.data_ptr(), per_cloud, stream)
+            if rc != 0:
+                raise RuntimeError(f"ndnet_b200_infer_host_async failed ({rc}): "
+                                   f"{self._L.ndnet_b200_last_error(self.engine.handle).decode()}")
+            return out
         with torch.cuda.device(self.device):
             rc = fn(
                 self.engine.handle, self._h, points.data_ptr(), _lib.F32 if points.dtype == torch.float32 else _lib.F64,
@@ -118,6 +130,12 @@ class B200Model:
                                f"{self._L.ndnet_b200_last_error(self.engine.handle).decode()}")
         return out
 
+
+    def infer_wait(self) -> None:
+        """Blocks until every batch enqueued with infer_host(..., wait=False) on the current stream has its result in host memory."""
+        rc = self._L.ndnet_b200_infer_wait(self.engine.handle, torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"ndnet_b200_infer_wait failed ({rc})")
 
     def infer_device(self, points: torch.Tensor, num_desired: int, labels: torch.Tensor | None = None,
                      num_classes: int = 0) -> torch.Tensor:

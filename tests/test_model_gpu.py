@@ -218,6 +218,18 @@ def test_pipelined_inference_equals_single_stream_calls():
     got_host = m.infer_host(torch.from_numpy(pts).pin_memory(), 300, torch.from_numpy(lab.astype(np.int16)).pin_memory(), 28, out_host)
     torch.cuda.synchronize()
     assert torch.equal(ref, got_dev) and torch.equal(ref.cpu(), got_host)
+    # asynchronous host calls, several batches in flight (uint8 labels too): same results after infer_wait()
+    pts2, lab2 = lidar_batch(7, 20000, seed0=950, with_labels=True)
+    ref2 = m(eng.downsample(torch.from_numpy(pts2).cuda(), 300, torch.from_numpy(lab2.astype(np.int16)).cuda(), 28, nan_to_num=True,
+                            want_info=False).feat)
+    outs = [torch.empty((7, 300, 29), dtype=torch.float32).pin_memory() for _ in range(3)]
+    hp, hp2 = torch.from_numpy(pts).pin_memory(), torch.from_numpy(pts2).pin_memory()
+    hl, hl2 = torch.from_numpy(lab.astype(np.uint8)).pin_memory(), torch.from_numpy(lab2.astype(np.uint8)).pin_memory()
+    m.infer_host(hp, 300, hl, 28, outs[0], wait=False)
+    m.infer_host(hp2, 300, hl2, 28, outs[1], wait=False)
+    m.infer_host(hp, 300, hl, 28, outs[2], wait=False)
+    m.infer_wait()
+    assert torch.equal(outs[0], ref.cpu()) and torch.equal(outs[1], ref2.cpu()) and torch.equal(outs[2], ref.cpu())
 
 
 def test_pointnet_forward_matches_torch_fp32():
