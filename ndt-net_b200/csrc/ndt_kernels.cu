@@ -12,6 +12,9 @@
 #include <cstdlib>
 #include <cstring>
 
+#ifndef NDT_STATS_MIN_CTAS
+#define NDT_STATS_MIN_CTAS 16                  // one-warp CTAs of k_stats per SM the register allocation must allow (<= 128 registers)
+#endif
 #ifndef NDT_STATS_WARPS_PER_CLOUD
 #define NDT_STATS_WARPS_PER_CLOUD 3
 #endif
@@ -424,18 +427,21 @@ __global__ void __launch_bounds__(128) k_rank(const T *__restrict__ pts, long N,
     const long n_used = chunk * kWorkers;
     const GridCtx gc = make_grid_ctx(s);
     const bool risky = s.risky != 0;
+    const int slot_bits = 32 - __clz(V | 1u);            // slots are < V
     // ranks the 32 points [base, base + 32) in order: rank among earlier points of the tile in the same slot
     auto rank32 = [&](long base, unsigned slot, unsigned id) {
         const long i = base + lane;
-        // lanes of the group that hold the same slot.  32 broadcast-and-compare steps: independent, fully pipelined
-        // instructions (3 per point), where MATCH.ANY iterates over the distinct values of the warp - about 31 of them
-        // for a scan in random point order.
+        // lanes of the group that hold the same slot: one ballot per bit of the slot number (11 for ~1200 voxels), each
+        // lane keeping the lanes that agree with it on that bit.  (MATCH.ANY iterates over the distinct values of the warp,
+        // ~31 for a scan in random point order: 0.70 ms per 512 scans; 32 shuffle-and-compare steps: 0.52 ms.)
 #if NDT_RANK_MATCH_ANY
         const unsigned peers = __match_any_sync(0xffffffffu, slot);
 #else
-        unsigned peers = 0;
-#pragma unroll
-        for (int j = 0; j < 32; j++) peers |= (__shfl_sync(0xffffffffu, slot, j) == slot ? 1u : 0u) << j;
+        unsigned peers = __ballot_sync(0xffffffffu, slot != kDropped);
+        for (int bit = 0; bit < slot_bits; bit++) {
+            const unsigned m = __ballot_sync(0xffffffffu, (slot >> bit) & 1u);
+            peers &= ((slot >> bit) & 1u) ? m : ~m;
+        }
 #endif
         unsigned packed = kDropped;
         unsigned basec = 0;
@@ -583,19 +589,22 @@ __global__ void __launch_bounds__(256) k_scatter(const T *__restrict__ pts, cons
                                                  unsigned *__restrict__ hist, int nbins) {
     const int b = blockIdx.y;
     if (states[b].status != 0) return;
+    // one point per thread: four points per thread (16-byte loads) measured SLOWER here (0.61 vs 0.49 ms per 512 scans) -
+    // the kernel lives on the number of independent gather -> store chains in flight, which is the thread count
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const unsigned packed = slot_rank[(size_t)b * N + i];
     if (packed == kDropped) return;
     const unsigned slot = packed / (unsigned)kRankTile, rank = packed % (unsigned)kRankTile;
     const int tile = (int)(i / kRankTile);
+    // position in the voxel-major order: the voxel's segment start + its points in earlier tiles + the rank within the tile
     const unsigned pos = vox_start[(size_t)b * (vcap + 1) + slot] + tile_cnt[((size_t)b * ntiles + tile) * vcap + slot] + rank;
     const T *p = pts + ((size_t)b * N + i) * 3;
     // labels: uint16 per point (the reference's dtype) or, with NDNET_B200_LABELS_U8, one byte per point
     const unsigned l = !labels ? 0u : (label_bytes == 1 ? (unsigned)reinterpret_cast<const uint8_t *>(labels)[(size_t)b * N + i]
                                                         : (unsigned)labels[(size_t)b * N + i]);
     store_sorted<T>(sorted + ((size_t)b * N + pos) * kSortedStride, p[0], p[1], p[2], l);
-    // wide label sets (> kSmemLabelBins classes) vote through global atomics; small ones are counted by k_votes
+    // wide label sets (> kSmemLabelBins classes) vote through global atomics; small ones are counted by the statistics kernels
     if (labels && hist && l < (unsigned)nbins) atomicAdd(&hist[((size_t)b * vcap + slot) * nbins + l], 1u);
 }
 
@@ -686,7 +695,7 @@ __global__ void k_fill_recip(double2 *__restrict__ tab, long n) {
 // lane of the same records (shared-memory histogram per slot, <= kSmemLabelBins classes).
 // grid (B, warps per cloud), block 32.
 template <typename T>
-__global__ void __launch_bounds__(32) k_stats(CloudState *__restrict__ states, unsigned vcap, long N,
+__global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(CloudState *__restrict__ states, unsigned vcap, long N,
                                               const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                               const unsigned *__restrict__ vox_order, const double2 *__restrict__ recip,
                                               double *__restrict__ mean, double *__restrict__ cov,
@@ -1561,11 +1570,16 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         const int vote_bins = labels && !wide_labels ? nbins : 0;
         (void)max_pairs;
         static const int stats_warps = [] { const char *e = getenv("NDNET_B200_STATS_WARPS"); const int v = e ? atoi(e) : 0; return v > 0 && v <= 64 ? v : kStatsWarpsPerCloud; }();
+        static const bool light_first = [] { const char *e = getenv("NDNET_B200_STATS_LIGHT_FIRST"); return e && *e == '1'; }();
+        auto launch_light = [&]() {
+            k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, (size_t)vote_bins * 128 * sizeof(unsigned short), w.side>>>(
+                w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
+        };
+        if (light_first) launch_light();
         k_stats<T><<<dim3(B, stats_warps), 32, 0, st>>>(
             w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.recip, w.mean, w.cov, w.cls, vote_bins);
         DBG("k_stats");
-        k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, (size_t)vote_bins * 128 * sizeof(unsigned short), w.side>>>(
-            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
+        if (!light_first) launch_light();
         if (wide_labels) {
             k_votes<T><<<dim3(B, (vcap + 3) / 4), 128, 0, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.hist, nbins, w.cls);
         }
