@@ -565,7 +565,8 @@ static bool launch_tf32(cudaStream_t st, const CUtensorMap &ma, const CUtensorMa
 
 // C[M, N] (+)= A[M, K] . B[N, K]^T (+ bias) on the tensor cores; false when the shape / alignment is not eligible
 static bool gemm_tf32(cudaStream_t st, const float *A, long lda, const float *Bm, long ldb, float *C, long ldc, int M, int N, int K,
-                      const float *bias, bool accumulate) {
+                      const float *bias, bool accumulate, double *stat_sum = nullptr, double *stat_sq = nullptr, bool *stats_fused = nullptr) {
+    if (stats_fused) *stats_fused = false;
     if (!tf32_eligible(A, lda, Bm, ldb, M, N, K)) return false;
     const int BN = N > 64 ? 128 : 64;
     CUtensorMap ma, mb;
@@ -583,6 +584,9 @@ static bool gemm_tf32(cudaStream_t st, const float *A, long lda, const float *Bm
     }
     a.kb_per_split = (nkb + splitk - 1) / splitk;
     a.splitk = (nkb + a.kb_per_split - 1) / a.kb_per_split;          // every z gets at least one K-block
+    const bool fuse = stat_sum && stat_sq && a.splitk == 1 && !accumulate;      // BatchNorm statistics in the epilogue
+    a.stat_sum = fuse ? stat_sum : nullptr; a.stat_sq = fuse ? stat_sq : nullptr;
+    if (stats_fused) *stats_fused = fuse;
     if (a.splitk > 1 && !accumulate) {
         if (ldc == N) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st);
         else cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st);
@@ -630,12 +634,18 @@ struct Pass {
 
 static void block_fwd(const Pass &ps, Block &k, const float *X, long ldx) {
     const int out = k.lin.out, in = k.lin.in;
-    if (!(ps.t.tf32 && gemm_tf32(ps.st, X, ldx, ps.P(k.lin.w), in, k.Y, out, (int)k.rows, out, in, ps.P(k.lin.b), false)))
+    // train-mode BatchNorm statistics (sum y, sum y^2 per channel): accumulated in the tensor-core GEMM's epilogue when it
+    // runs unsplit, else by a column-reduction pass over Y (fp32 parity mode, split-K shapes, the small FC layers)
+    bool stats_fused = false;
+    if (!(ps.t.tf32 && gemm_tf32(ps.st, X, ldx, ps.P(k.lin.w), in, k.Y, out, (int)k.rows, out, in, ps.P(k.lin.b), false,
+                                 k.has_bn ? k.red : nullptr, k.has_bn ? k.red + out : nullptr, &stats_fused)))
         gemm(ps.st, X, ldx, 1, ps.P(k.lin.w), in, 1, k.Y, out, (int)k.rows, out, in, ps.P(k.lin.b), false);
     if (!k.has_bn) return;
-    RedP r{};
-    r.P = k.Y; r.ldp = out; r.rows = (int)k.rows; r.cols = out; r.s0 = k.red; r.s1 = k.red + out;
-    colred<RED_STATS>(ps.st, r, 1);
+    if (!stats_fused) {
+        RedP r{};
+        r.P = k.Y; r.ldp = out; r.rows = (int)k.rows; r.cols = out; r.s0 = k.red; r.s1 = k.red + out;
+        colred<RED_STATS>(ps.st, r, 1);
+    }
     train_count(), k_bn_finalize<<<cdiv(out, 128), 128, 0, ps.st>>>(k.red, k.red + out, (int)k.rows, out, k.mean, k.rstd, ps.P(k.bn.rm), ps.P(k.bn.rv),
                                                      (long long *)ps.P(k.bn.nbt), ps.update_running);
     train_count(), k_bn_apply<<<cdiv(k.rows * out, 256), 256, 0, ps.st>>>(k.Y, k.rows, out, k.mean, k.rstd, ps.P(k.bn.g), ps.P(k.bn.be), k.relu ? 1 : 0, k.A);

@@ -16,6 +16,10 @@ struct Tf32Args {
     const float *bias;
     int accumulate;       // C += result (ignored when splitk > 1: the atomics always add)
     int splitk, kb_per_split;
+    // train-mode BatchNorm: per-column sum and sum of squares of the OUTPUT (bias included) over the rows, accumulated here
+    // in the epilogue (fp32 over the 32 rows of a warp, then one fp64 atomic per column per warp) instead of a separate
+    // column-reduction pass over the activation.  Only with splitk == 1 and accumulate == 0; null = off.
+    double *stat_sum, *stat_sq;
 };
 
 // kind::tf32 instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, K-major both, N>>3 [17,23), M>>4 [24,29)
@@ -109,18 +113,19 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             uint32_t v[32];
             ptx::tmem_ld32(taddr + (uint32_t)c0, v);
             ptx::tmem_ld_wait();
+            float y[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                y[j] = __uint_as_float(v[j]);
+                if (add_bias && b_row0 + c0 + j < args.N) y[j] += args.bias[b_row0 + c0 + j];
+            }
             if (row < args.M) {
                 float *dst = args.C + (size_t)row * args.ldc + b_row0 + c0;
                 if (vec && b_row0 + c0 + 32 <= args.N) {          // full 32-column chunk: eight 16-byte stores per row
                     float4 *d4 = reinterpret_cast<float4 *>(dst);
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
-                        float4 r = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                               __uint_as_float(v[4 * q + 3]));
-                        if (add_bias) {
-                            const float *bq = args.bias + b_row0 + c0 + 4 * q;
-                            r.x += bq[0]; r.y += bq[1]; r.z += bq[2]; r.w += bq[3];
-                        }
+                        float4 r = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
                         if (args.accumulate) { const float4 o = d4[q]; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
                         d4[q] = r;
                     }
@@ -129,13 +134,34 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                     for (int j = 0; j < 32; j++) {
                         const int col = b_row0 + c0 + j;
                         if (col < args.N) {
-                            float r = __uint_as_float(v[j]);
-                            if (add_bias) r += args.bias[col];
-                            if (args.splitk > 1) atomicAdd(dst + j, r);
-                            else if (args.accumulate) dst[j] += r;
-                            else dst[j] = r;
+                            if (args.splitk > 1) atomicAdd(dst + j, y[j]);
+                            else if (args.accumulate) dst[j] += y[j];
+                            else dst[j] = y[j];
                         }
                     }
+                }
+            }
+            if (args.stat_sum) {
+                // column sums over the warp's 32 rows by recursive halving: after the step with distance d a lane holds
+                // the partial sums of d columns; lane l ends with column l.  62 shuffles per chunk for both statistics.
+                float q[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) { if (row >= args.M) y[j] = 0.f; q[j] = y[j] * y[j]; }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    const bool upper = (lane & d) != 0;
+#pragma unroll
+                    for (int j = 0; j < d; j++) {
+                        const float ys = upper ? y[j] : y[j + d], yk = upper ? y[j + d] : y[j];
+                        const float qs = upper ? q[j] : q[j + d], qk = upper ? q[j + d] : q[j];
+                        y[j] = yk + __shfl_xor_sync(0xffffffffu, ys, d);
+                        q[j] = qk + __shfl_xor_sync(0xffffffffu, qs, d);
+                    }
+                }
+                const int col = b_row0 + c0 + lane;
+                if (col < args.N) {
+                    atomicAdd(args.stat_sum + col, (double)y[0]);
+                    atomicAdd(args.stat_sq + col, (double)q[0]);
                 }
             }
         }
