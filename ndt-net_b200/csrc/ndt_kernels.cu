@@ -15,18 +15,11 @@
 #ifndef NDT_STATS_MIN_CTAS
 #define NDT_STATS_MIN_CTAS 16                  // one-warp CTAs of k_stats per SM the register allocation must allow (<= 128 registers)
 #endif
-#ifndef NDT_STATS_WARPS_PER_CLOUD
-#define NDT_STATS_WARPS_PER_CLOUD 3
-#endif
-constexpr int kStatsWarpsPerCloud = NDT_STATS_WARPS_PER_CLOUD;   // one-warp CTAs of k_stats that share a cloud's queue of heavy voxels
+constexpr unsigned kMaxSortedHeavy = 1024;       // k_offsets sorts up to this many heavy voxels exactly (one thread each)
 constexpr int kSelectThreads = 512;             // k_select: three 512-thread CTAs per SM overlap one another's barriers
 #ifndef NDT_RANK_MATCH_ANY
 #define NDT_RANK_MATCH_ANY 0
 #endif
-#ifndef NDT_STATS_Q
-#define NDT_STATS_Q 4
-#endif
-constexpr int kQ = NDT_STATS_Q;                // heavy voxels each warp of k_stats runs in lockstep (3 kQ chain lanes, 6 kQ sum lanes <= 32)
 
 namespace ndt {
 
@@ -568,12 +561,25 @@ __global__ void __launch_bounds__(1024) k_offsets(CloudState *__restrict__ state
         unsigned run = 0;
         for (int k = 0; k < 32; k++) { const unsigned c = s_hist[k]; s_hist[k] = run; run += c; }
         s.n_heavy = s_hist[__clz(kHeavyVoxel) + 1];      // keys 0..clz(kHeavyVoxel) hold the voxels with n >= kHeavyVoxel
-        s.next_heavy = 0;                                // k_stats' queue of heavy voxels
     }
     __syncthreads();
     for (unsigned v = tid; v < V; v += blockDim.x) {
         const int key = __clz(vox_n[(size_t)b * vcap + v] | 1u);
         vox_order[(size_t)b * vcap + s_hist[key] + atomicAdd(&s_cursor[key], 1u)] = v;
+    }
+    // the heavy voxels in exact descending size (ties by voxel slot): k_stats runs eight consecutive entries per warp for as
+    // many steps as the largest of them has points
+    __shared__ unsigned s_hv[kMaxSortedHeavy], s_hn[kMaxSortedHeavy];
+    __syncthreads();
+    const unsigned nh = s.n_heavy;
+    if (nh > kMaxSortedHeavy) return;                    // (more than 1024 voxels of >= kHeavyVoxel points: leave them bucketed)
+    if ((unsigned)tid < nh) { const unsigned v = vox_order[(size_t)b * vcap + tid]; s_hv[tid] = v; s_hn[tid] = vox_n[(size_t)b * vcap + v]; }
+    __syncthreads();
+    if ((unsigned)tid < nh) {
+        const unsigned v = s_hv[tid], n = s_hn[tid];
+        unsigned rank = 0;
+        for (unsigned t = 0; t < nh; t++) rank += (s_hn[t] > n || (s_hn[t] == n && s_hv[t] < v)) ? 1u : 0u;
+        vox_order[(size_t)b * vcap + rank] = v;
     }
 }
 
@@ -611,15 +617,16 @@ __global__ void __launch_bounds__(256) k_scatter(const T *__restrict__ pts, cons
 // ------------------------------------------------------------------------------------------------
 // K7  per-voxel statistics: the sequential recurrence of normal_distributions.c:76-104 over the voxel's
 // points in ascending index order (bit-exact; the off-diagonal is order dependent, A6), plus the label
-// vote (:107-121).  One WARP per voxel, 32 points per round staged in shared memory:
-//   A. lanes 0-2 run the three mean chains  mu += (x - mu) / i  (the only loop-carried fp64 dependency);
-//      the division by the integer count uses a reciprocal computed off the chain and one FMA residual
-//      correction, which is correctly rounded for integer divisors < 2^26 (see div_by_count);
-//   B. all lanes compute, in parallel, the per-point terms that only need mu^{i-1} and mu^{i}:
-//      (x_j - old_j)(x_j - new_j) and (x_j - new_j)(x_k - old_k) / i;
-//   C. lanes 0-5 add the terms of the previous round to the six running sums in order (one DADD per step,
-//      issued in the shadow of the mean chain's latency).
-// grid (B, ceil(vcap/4)), block 128; voxels are visited heaviest-first (vox_order from k_offsets).
+// vote (:107-121).
+//
+// Heavy voxels (k_stats): FOUR LANES PER VOXEL, eight voxels per warp.  Lane j < 3 of a voxel owns dimension j: its mean
+// chain  mu_j += (x_j - mu_j) / i  (the only loop-carried fp64 dependency), its m2_j, and one off-diagonal sum
+// (lane 0: c01, lane 1: c12, lane 2: c02), whose second factor comes from a sibling lane by one shuffle per point; lane 3
+// reads the label lane of the same 16-byte records and counts the votes.  Every lane of the warp is at the same point count,
+// so the reciprocal pair of the count is one uniform load per step.  Nothing is staged in shared memory and no lane waits
+// for another voxel: a warp issues ~40 instructions per step for its eight voxels and runs as many steps as its largest
+// voxel has points (the voxels are sorted by size, k_offsets, so the eight of a warp are alike).
+// Light voxels (k_stats_light): one thread per voxel.
 // ------------------------------------------------------------------------------------------------
 
 // RN(d / cnt) for an integer-valued cnt in [1, 2^26) without a division on the dependent chain:
@@ -638,43 +645,24 @@ __device__ __forceinline__ double div_by_count(double d, double cnt) {
     return d / cnt;
 }
 
-// Shared memory of one warp of k_stats.  Dimension-major rows of 33 doubles: lane k (phase B, staging) touches word 2k of
-// a row, chain / accumulator lane l (phase A) touches row l at a common k; rows are 66 words apart (132 for the reciprocal
-// pairs), so both patterns are bank-conflict free.
-struct StatsWarpSmem {
-    double x[kQ][3][33];        // this round's points
-    double mu[kQ][3][33];       // means: [.][0] before the round's first point, [.][k+1] after point k
-    double t[kQ][6][33];        // terms of the round: m2 x3, c01, c02, c12 (phase A of the next round adds them)
-    double2 r[kQ][33];          // 1 / count of this round's points as an unevaluated sum {rh, rl} (~106 bits), per slot
-    unsigned h[kQ][kSmemLabelBins];   // label histograms
-};
-
-// Label vote of a voxel from a warp's shared-memory histogram (normal_distributions.c:107-121): most frequent class,
-// lowest index on ties, 0 when nothing was counted.  Every lane returns the class.
-__device__ __forceinline__ unsigned vote_from_hist(const unsigned *h, int nbins, int lane) {
-    unsigned best = 0; int bc = 0x7fffffff;
-    for (int j = lane; j < nbins; j += 32) { const unsigned x = h[j]; if (x > best) { best = x; bc = j; } }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-        if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
-    }
-    return best > 0 ? (unsigned)bc : 0u;
-}
-
 // magnitude tests on the high word (exponent and top mantissa bits) of a double: integer pipe, no fp64 compare
 __device__ __forceinline__ unsigned hi_abs(double u) { return (unsigned)__double2hiint(u) & 0x7fffffffu; }
-__device__ __forceinline__ bool in_recip_range(double u) {
-    // 2^-830 <= |u| < 2^963: inside the range (1e-250, 1e290) for which div_by_count's reciprocal form is proven
-    return hi_abs(u) - 0x0C100000u < 0x70100000u;
-}
 __device__ __forceinline__ bool exp_all_ones(double u) { return (hi_abs(u) & 0x7ff00000u) == 0x7ff00000u; }
-// ... or exactly zero: fma(+-0, rh, +-0 * rl) is the correctly signed zero quotient, so zeros need no division either
-// (a coordinate that is constant over a voxel - flat ground - makes every difference and product of that axis zero)
+// 2^-830 <= |u| < 2^963 (inside the range (1e-250, 1e290) for which div_by_count's reciprocal form is proven) or exactly
+// zero: fma(+-0, rh, +-0 * rl) is the correctly signed zero quotient, so zeros need no division either (a coordinate that is
+// constant over a voxel - flat ground - makes every difference and product of that axis zero)
 __device__ __forceinline__ bool recip_ok(double u) {
     const unsigned h = hi_abs(u);
     return h - 0x0C100000u < 0x70100000u || (h | (unsigned)__double2loint(u)) == 0u;
+}
+// the negation of the same test, OR-ed into an accumulator without a branch (four integer instructions; doubling the high
+// word drops the sign bit): acc becomes non-zero when u is neither zero nor inside the proven range
+__device__ __forceinline__ void note_recip_unsafe(double u, unsigned &acc) {
+    const unsigned hi = (unsigned)__double2hiint(u), lo = (unsigned)__double2loint(u);
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 t, z;\n\t"
+        "add.u32 t, %1, %1;\n\tsub.u32 t, t, 0x18200000;\n\tsetp.ge.u32 p, t, 0xE0200000;\n\t"
+        "and.b32 z, %1, 0x7fffffff;\n\tor.b32 z, z, %2;\n\t@p or.b32 %0, %0, z;\n\t}"
+        : "+r"(acc) : "r"(hi), "r"(lo));
 }
 
 // {RN(1/c), RN((1 - c RN(1/c)) RN(1/c))} for c = 1 .. n (index c - 1): the reciprocal pairs of div_by_count, tabulated
@@ -687,272 +675,173 @@ __global__ void k_fill_recip(double2 *__restrict__ tab, long n) {
     }
 }
 
-// K7 (heavy voxels).  One warp per CTA; the warps of a cloud share a queue of its heavy voxels (vox_order, heaviest first)
-// and each runs kQ of them at a time in lockstep: the three mean chains of slot q sit on lanes 3q..3q+2, its six running
-// sums on lanes 6q..6q+5, so the paced instruction stream (phase A) is shared.  The slots advance independently (each at
-// its own count, reciprocals from the table) and a slot that finishes its voxel pulls the next one from the queue, so the
-// lanes stay busy whatever the spread of voxel sizes.  vote_bins > 0: the label vote is taken here too, from the label
-// lane of the same records (shared-memory histogram per slot, <= kSmemLabelBins classes).
-// grid (B, warps per cloud), block 32.
+template <typename T> __device__ __forceinline__ unsigned record_label(T v);
+template <> __device__ __forceinline__ unsigned record_label<float>(float v) { return __float_as_uint(v); }
+template <> __device__ __forceinline__ unsigned record_label<double>(double v) { return (unsigned)__double_as_longlong(v); }
+// the coordinate a lane computes on.  Label lanes compute too (their results are never written): the label bits of a float
+// record widen to a harmless normal double, those of a double record are a denormal and would take the rare paths
+template <typename T> __device__ __forceinline__ double record_coord(T v, bool label_lane);
+template <> __device__ __forceinline__ double record_coord<float>(float v, bool) { return (double)v; }
+template <> __device__ __forceinline__ double record_coord<double>(double v, bool label_lane) { return label_lane ? 0.0 : v; }
+
+constexpr int kStatsVoxelsPerWarp = 8;          // four lanes per voxel
+constexpr int kStatsUnroll = 8;                 // steps per block: one 128-byte line of float records, operands fetched a block ahead
+
+// m ? a : b on the bit patterns (m = all ones or zero, loop invariant per lane): two LOP3, no predicate to rebuild per step
+__device__ __forceinline__ double blend_bits(double a, double b, unsigned m) {
+    const unsigned lo = ((unsigned)__double2loint(a) & m) | ((unsigned)__double2loint(b) & ~m);
+    const unsigned hi = ((unsigned)__double2hiint(a) & m) | ((unsigned)__double2hiint(b) & ~m);
+    return __hiloint2double((int)hi, (int)lo);
+}
+
+// One step of the recurrence for the warp's eight voxels:
+//   d = x - mu ; mu' = mu + RN(d / i) ; e = x - mu' ; m2 += d e                              (normal_distributions.c:76-89)
+//   c_jk += RN((x_j - mu_j')(x_k - mu_k) / i), j < k: mu_k is not yet updated when dimension j runs      (:91-104)
+// Lane roles: lane 0 sends e0 and receives d1 (c01 = e0 d1), lane 1 sends d1 and receives d2 (c12 = e1 d2), lane 2 sends d2
+// and receives e0 (c02 = d2 e0).
+// Fast form: straight-line, the quotients in reciprocal form whatever the operands; it only RECORDS whether an operand left
+// the range the reciprocal form is proven for.  The caller then redoes the block with the careful form.
+__device__ __forceinline__ void stats_step_fast(double x, double rh, double rl, int src, unsigned m_j0, unsigned m_j2,
+                                                double &mu, double &m2, double &c, unsigned &bad) {
+    const double d = x - mu;
+    mu = mu + fma(d, rh, d * rl);
+    const double e = x - mu;
+    m2 = m2 + d * e;
+    const double rcv = __shfl_sync(0xffffffffu, blend_bits(e, d, m_j0), src);
+    const double pr = blend_bits(d, e, m_j2) * rcv;
+    c = c + fma(pr, rh, pr * rl);
+    note_recip_unsafe(d, bad);
+    note_recip_unsafe(pr, bad);
+}
+
+// out-of-line IEEE divisions for operands outside the reciprocal form's proven range (tiny, huge, non-finite): rare
+static __device__ __noinline__ double quotient_rare(double u, double cnt) { return u / cnt; }
+
+// Careful form: IEEE division wherever the reciprocal form is not proven, NaN -> 0 on the off-diagonal sum
+// (normal_distributions.c:98-100; a sum that is not NaN stays not NaN under a finite addend, so the fast form needs no test).
+__device__ __forceinline__ void stats_step_careful(double x, double rh, double rl, double cnt, int src, unsigned m_j0, unsigned m_j2,
+                                                   double &mu, double &m2, double &c) {
+    const double d = x - mu;
+    mu = mu + (recip_ok(d) ? fma(d, rh, d * rl) : quotient_rare(d, cnt));
+    const double e = x - mu;
+    m2 = m2 + d * e;
+    const double rcv = __shfl_sync(0xffffffffu, blend_bits(e, d, m_j0), src);
+    const double pr = blend_bits(d, e, m_j2) * rcv;
+    c = c + (recip_ok(pr) ? fma(pr, rh, pr * rl) : quotient_rare(pr, cnt));
+    if (exp_all_ones(c) && c != c) c = 0.0;
+}
+
+// a voxel's last point was just added: lane j < 3 writes its mean, its variance m2 / n (normal_distributions.c:86-89, NaN -> 0)
+// and its off-diagonal sum (mirrored); the label lane writes the vote (most frequent class, lowest index on ties, 0 when
+// nothing was counted, :107-121)
+__device__ __forceinline__ void stats_finish(double *__restrict__ mean, double *__restrict__ cov, uint16_t *__restrict__ cls, size_t slot,
+                                             int j, int q, unsigned n, double mu, double m2, double c, const unsigned *s_hist, int vote_bins) {
+    if (j < 3) {
+        double var = m2 / (double)n;
+        if (var != var) var = 0.0;
+        mean[slot * 3 + j] = mu;
+        double *co = cov + slot * 9;
+        co[j * 4] = var;
+        const int a = j == 0 ? 1 : (j == 1 ? 5 : 2);        // c01 -> [0][1], c12 -> [1][2], c02 -> [0][2]
+        const int m = j == 0 ? 3 : (j == 1 ? 7 : 6);
+        co[a] = c; co[m] = c;
+    } else if (vote_bins > 0) {
+        unsigned best = 0, bc = 0;
+        for (int t = 0; t < vote_bins; t++) { const unsigned x = s_hist[t * 32 + q]; if (x > best) { best = x; bc = (unsigned)t; } }
+        cls[slot] = (uint16_t)(best > 0 ? bc : 0u);
+    }
+}
+
+// K7 (heavy voxels).  grid (B, ceil(max heavy voxels / 8)), block 32: warp g of a cloud takes entries 8g .. 8g+7 of vox_order
+// (descending size), so the first wave of CTAs holds every cloud's largest voxels.  vote_bins > 0: the label vote is taken
+// here too (shared-memory counters, <= kSmemLabelBins classes): row t of s_hist holds class t, word q the count of the warp's
+// voxel q, words 8..31 take the (discarded) increments of the other lanes so that the vote is branch-free.
 template <typename T>
-__global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(CloudState *__restrict__ states, unsigned vcap, long N,
+__global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
                                               const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                               const unsigned *__restrict__ vox_order, const double2 *__restrict__ recip,
                                               double *__restrict__ mean, double *__restrict__ cov,
                                               uint16_t *__restrict__ cls, int vote_bins) {
     const int b = blockIdx.x;
-    CloudState &s = states[b];
+    const CloudState &s = states[b];
     if (s.status != 0) return;
     const unsigned n_heavy = s.n_heavy;
-    if (blockIdx.y * kQ >= n_heavy) return;              // fewer heavy voxels than this warp's first slot: nothing to pull
-    const int lane = threadIdx.x;
-    __shared__ __align__(16) StatsWarpSmem sm;
-
-    const int cq = lane < 3 * kQ ? lane / 3 : kQ - 1, cj = lane < 3 * kQ ? lane % 3 : 2;     // chain lane -> (slot, dimension)
-    const int aq = lane < 6 * kQ ? lane / 6 : kQ - 1, at = lane < 6 * kQ ? lane % 6 : 5;     // accumulator lane -> (slot, term)
-    const bool chain_lane = lane < 3 * kQ, acc_lane = lane < 6 * kQ, cov_lane = acc_lane && at >= 3;
-    const double *xs = sm.x[cq][cj];
-    double *mus = sm.mu[cq][cj];
-    const double *tp = sm.t[aq][at];
-    const double2 *rs = sm.r[cq];
-    double mu = 0.0, acc = 0.0;
-
-    // per-slot state, identical in every lane
-    unsigned vv[kQ], nn[kQ], base[kQ];
-    const T *pp[kQ];
-    int prev_m[kQ];
-    bool live[kQ];
-    bool wary[kQ];                         // the slot's voxel has shown |x - mu| << |x|: its rounds use the 4-operation chain
-    T nx[kQ][3];                           // the next round's point of this lane (per slot), fetched one round ahead
-    unsigned nl[kQ];                       // ... its label
-    double2 nr[kQ];                        // ... and the reciprocal pair of its count
+    const unsigned first = blockIdx.y * kStatsVoxelsPerWarp;
+    if (first >= n_heavy) return;
+    const int lane = threadIdx.x, q = lane >> 2, j = lane & 3;
+    __shared__ unsigned s_hist[(kSmemLabelBins + 1) * 32];
+    for (int i = lane; i < (vote_bins + 1) * 32; i += 32) s_hist[i] = 0u;
+    __syncwarp();
+    unsigned v = 0, n = 0, st = 0;
+    if (first + q < n_heavy) {
+        v = vox_order[(size_t)b * vcap + first + q];
+        st = vox_start[(size_t)b * (vcap + 1) + v];
+        n = vox_start[(size_t)b * (vcap + 1) + v + 1] - st;
+    }
+    const unsigned nmax = __reduce_max_sync(0xffffffffu, n);           // steps of the warp (uniform)
+    const T *p = sorted + ((size_t)b * N + st) * kSortedStride + j;
+    const int src = (lane & ~3) | (j == 0 ? 1 : (j == 1 ? 2 : 0));
+    const unsigned m_j0 = j == 0 ? 0xffffffffu : 0u, m_j2 = j == 2 ? 0xffffffffu : 0u;
+    // vote target of this lane: label lanes count class min(label, vote_bins) of their voxel (row vote_bins = out of range,
+    // discarded), the other lanes increment a word of their own in the discarded part of row 0
+    unsigned *const my_hist = s_hist + (j == 3 ? q : 8 + q * 3 + j);
+    const unsigned my_bins = j == 3 ? (unsigned)vote_bins : 0u;
+    double mu = 0.0, m2 = 0.0, c = 0.0;
+    T bx[kStatsUnroll];
+    double2 br[kStatsUnroll];
 #pragma unroll
-    for (int q = 0; q < kQ; q++) { vv[q] = 0; nn[q] = 0; base[q] = 0; pp[q] = sorted; prev_m[q] = 0; live[q] = false; wary[q] = false;
-                                   nx[q][0] = nx[q][1] = nx[q][2] = 0; nl[q] = 0; nr[q] = make_double2(0.0, 0.0); }
-    bool queue_empty = false;
-    bool prev_chk = false;                 // previous round produced a non-finite term: add with the NaN rule
-
-    while (true) {
-        // ---- refill: an idle slot takes the next heavy voxel of the cloud
-        bool any_live = false;
+    for (int i = 0; i < kStatsUnroll; i++) {
+        bx[i] = (unsigned)i < n ? p[(size_t)i * kSortedStride] : T(0);
+        br[i] = recip[i];                                  // (the table is padded by two blocks)
+    }
+    for (unsigned k0 = 0; k0 < nmax; k0 += kStatsUnroll) {
+        const int ahead = (int)(n - k0) - kStatsUnroll;    // points of this lane's voxel after this block
+        if (ahead > 4 * kStatsUnroll) prefetch_l2(p + (size_t)(k0 + 5 * kStatsUnroll) * kSortedStride);
+        const double2 *rnext = recip + k0 + kStatsUnroll;
+        const T *pnext = p + (size_t)(k0 + kStatsUnroll) * kSortedStride;
+        if (!__any_sync(0xffffffffu, n - k0 - 1u < (unsigned)kStatsUnroll)) {
+            const double mu0 = mu, m20 = m2, c0 = c;
+            unsigned bad = 0u;
 #pragma unroll
-        for (int q = 0; q < kQ; q++) {
-            if (!live[q] && !queue_empty) {
-                unsigned idx = 0;
-                if (lane == 0) idx = atomicAdd(&s.next_heavy, 1u);
-                idx = __shfl_sync(0xffffffffu, idx, 0);
-                if (idx >= n_heavy) queue_empty = true;
-                else {
-                    vv[q] = vox_order[(size_t)b * vcap + idx];
-                    const unsigned st = vox_start[(size_t)b * (vcap + 1) + vv[q]], en = vox_start[(size_t)b * (vcap + 1) + vv[q] + 1];
-                    nn[q] = en - st; base[q] = 0;
-                    pp[q] = sorted + ((size_t)b * N + st) * kSortedStride;
-                    live[q] = true; wary[q] = false;
-                    // the slot's first round adds 32 zero terms, so that it can take the straight path like any full round
-                    prev_m[q] = 32;
-#pragma unroll
-                    for (int t = 0; t < 6; t++) sm.t[q][t][lane] = 0.0;
-                    if (chain_lane && cq == q) { mu = 0.0; mus[0] = 0.0; }
-                    if (acc_lane && aq == q) acc = 0.0;
-                    if (vote_bins > 0) for (int j = lane; j < kSmemLabelBins; j += 32) sm.h[q][j] = 0u;
-                    nx[q][0] = nx[q][1] = nx[q][2] = 0; nl[q] = 0;
-                    if ((unsigned)lane < nn[q]) { load_sorted_rec<T>(pp[q] + lane * kSortedStride, nx[q][0], nx[q][1], nx[q][2], nl[q]); nr[q] = recip[lane]; }
-                    if ((unsigned)lane + 32u < nn[q]) prefetch_l2(pp[q] + (size_t)(lane + 32) * kSortedStride);
-                    if ((unsigned)lane + 64u < nn[q]) prefetch_l2(pp[q] + (size_t)(lane + 64) * kSortedStride);
-                }
+            for (int i = 0; i < kStatsUnroll; i++) {
+                const T raw = bx[i];
+                const double2 r = br[i];
+                // the operands of the same step of the next block travel while this block is on the chain; a finished
+                // voxel's lanes compute on zeros
+                bx[i] = i < ahead ? pnext[(size_t)i * kSortedStride] : T(0);
+                br[i] = rnext[i];
+                atomicAdd(my_hist + min(record_label<T>(raw), my_bins) * 32u, 1u);
+                stats_step_fast(record_coord<T>(raw, j == 3), r.x, r.y, src, m_j0, m_j2, mu, m2, c, bad);
             }
-            any_live = any_live || live[q];
-        }
-        if (!any_live) break;
-
-        // ---- staging: this round's points, reciprocal pairs and labels; the next round's loads are issued now
-        int m[kQ];
-        double2 rq[kQ];                    // reciprocal pair of this lane's point (phase B)
-#pragma unroll
-        for (int q = 0; q < kQ; q++) {
-            m[q] = live[q] ? (int)(nn[q] - base[q] < 32u ? nn[q] - base[q] : 32u) : 0;
-            rq[q] = nr[q];
-            if (lane < m[q]) {
-#pragma unroll
-                for (int j = 0; j < 3; j++) sm.x[q][j][lane] = (double)nx[q][j];
-                sm.r[q][lane] = rq[q];
-                if (vote_bins > 0 && nl[q] < (unsigned)vote_bins) atomicAdd(&sm.h[q][nl[q]], 1u);
-            }
-            // a round lasts about one DRAM round trip: pull the records of the round after the next two into L2 now
-            if (live[q] && base[q] + 96 + lane < nn[q]) prefetch_l2(pp[q] + (size_t)(base[q] + 96 + lane) * kSortedStride);
-            if (live[q] && base[q] + 32 + lane < nn[q]) {
-                load_sorted_rec<T>(pp[q] + (size_t)(base[q] + 32 + lane) * kSortedStride, nx[q][0], nx[q][1], nx[q][2], nl[q]);
-                nr[q] = recip[base[q] + 32 + lane];
-            }
-        }
-        __syncwarp();
-        // ---- A (this round's means) fused with C (previous round's running sums).  Per point the warp issues only
-        //      the dependency chain d -> q -> mu, one store and one add: q = RN(d / count) is fma(d, rh, t), t = d * rl
-        //      (div_by_count: exact for |d| inside the proven range, and trivially for d = 0).  The fast form takes t =
-        //      fma(-mu, rl, x * rl), which does not wait for d (three dependent operations per point instead of four) but
-        //      loses t to cancellation when |d| < 2^-22 |x|; a slot whose voxel shows that (a coordinate that is nearly
-        //      constant over the voxel: flat ground) is marked wary, and rounds with a wary slot take t = d * rl.  Phase B
-        //      checks every operand of the round afterwards, in parallel; a round that broke a condition is redone.
-        const double mu_start = mu;
-        const int my_m = m[cq], my_pm = prev_m[aq];
-        bool straight = !prev_chk;             // every slot is in a full round after a full round, or idle
-        bool safe = false;                     // some live slot is wary
-#pragma unroll
-        for (int q = 0; q < kQ; q++) safe = safe || (live[q] && wary[q]);
-#pragma unroll
-        for (int q = 0; q < kQ; q++) straight = straight && ((m[q] == 32 && prev_m[q] == 32) || (m[q] == 0 && prev_m[q] == 0));
-        if (straight) {
-            // full rounds: straight-line, no per-step predicates; the operands of the next two points are fetched while
-            // the current two are on the chain (an idle slot's lanes compute on stale rows; they are reset at refill)
-            double xv[2], tv[2], xn[2], tn[2];
-            double2 rv[2], rn[2];
-#pragma unroll
-            for (int j = 0; j < 2; j++) { xv[j] = xs[j]; rv[j] = rs[j]; tv[j] = tp[j]; }
-            if (!safe) {
-#pragma unroll
-                for (int k0 = 0; k0 < 32; k0 += 2) {
-                    if (k0 + 2 < 32) {
-#pragma unroll
-                        for (int j = 0; j < 2; j++) { xn[j] = xs[k0 + 2 + j]; rn[j] = rs[k0 + 2 + j]; tn[j] = tp[k0 + 2 + j]; }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        const double d = xv[j] - mu;
-                        const double t = fma(-mu, rv[j].y, xv[j] * rv[j].y);
-                        mu = mu + fma(d, rv[j].x, t);
-                        if (chain_lane) mus[k0 + j + 1] = mu;
-                        acc += tv[j];
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2; j++) { xv[j] = xn[j]; rv[j] = rn[j]; tv[j] = tn[j]; }
-                }
-            } else {
-#pragma unroll
-                for (int k0 = 0; k0 < 32; k0 += 2) {
-                    if (k0 + 2 < 32) {
-#pragma unroll
-                        for (int j = 0; j < 2; j++) { xn[j] = xs[k0 + 2 + j]; rn[j] = rs[k0 + 2 + j]; tn[j] = tp[k0 + 2 + j]; }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        const double d = xv[j] - mu;
-                        mu = mu + fma(d, rv[j].x, d * rv[j].y);
-                        if (chain_lane) mus[k0 + j + 1] = mu;
-                        acc += tv[j];
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2; j++) { xv[j] = xn[j]; rv[j] = rn[j]; tv[j] = tn[j]; }
+            if (__any_sync(0xffffffffu, bad != 0u)) {      // rare: redo the block from its operands in memory
+                mu = mu0; m2 = m20; c = c0;
+                for (int i = 0; i < kStatsUnroll; i++) {
+                    const unsigned k = k0 + i;
+                    const T raw = k < n ? p[(size_t)k * kSortedStride] : T(0);
+                    const double2 r = recip[k];
+                    stats_step_careful(record_coord<T>(raw, j == 3), r.x, r.y, (double)(k + 1), src, m_j0, m_j2, mu, m2, c);
                 }
             }
         } else {
-            // last (partial) round of a voxel, the round after it (only the sums move), or a round after non-finite
-            // terms: per-lane predicates, 4-operation chain
-            safe = true;
-            for (int k = 0; k < 32; k++) {
-                if (k < my_m) {
-                    const double2 r = rs[k];
-                    const double d = xs[k] - mu;
-                    mu = mu + fma(d, r.x, d * r.y);
-                    if (chain_lane) mus[k + 1] = mu;
-                }
-                if (k < my_pm) {
-                    const double a2 = acc + tp[k];
-                    acc = (prev_chk && cov_lane && a2 != a2) ? 0.0 : a2;          // NaN -> 0 (normal_distributions.c:98-100)
+            // some voxel of the warp ends inside this block
+#pragma unroll 1
+            for (int i = 0; i < kStatsUnroll; i++) {
+                const unsigned k = k0 + i;
+                const T raw = k < n ? p[(size_t)k * kSortedStride] : T(0);
+                const double2 r = recip[k];
+                if (k < n) atomicAdd(my_hist + min(record_label<T>(raw), my_bins) * 32u, 1u);
+                stats_step_careful(record_coord<T>(raw, j == 3), r.x, r.y, (double)(k + 1), src, m_j0, m_j2, mu, m2, c);
+                if (k + 1 == n) {
+                    stats_finish(mean, cov, cls, (size_t)b * vcap + v, j, q, n, mu, m2, c, s_hist, vote_bins);
+                    mu = 0.0;
                 }
             }
-        }
-        __syncwarp();
-        // ---- B: per-point terms, all lanes in parallel, one slot after the other; also validates the operands
-        bool nonfinite = false;
 #pragma unroll
-        for (int q = 0; q < kQ; q++) {
-            if (m[q] == 0) continue;
-            bool redone = false;
-            const double rh = rq[q].x, rl = rq[q].y;
-            while (true) {
-                bool bad = false, cancel = false;
-                if (lane < m[q]) {
-                    const double(*mq)[33] = sm.mu[q];
-                    const double o0 = mq[0][lane], o1 = mq[1][lane], o2 = mq[2][lane];
-                    const double n0 = mq[0][lane + 1], n1 = mq[1][lane + 1], n2 = mq[2][lane + 1];
-                    const double x0 = sm.x[q][0][lane], x1 = sm.x[q][1][lane], x2 = sm.x[q][2][lane];
-                    const double d0 = x0 - o0, d1 = x1 - o1, d2 = x2 - o2;          // the chain's d, bit for bit
-                    // the chain's reciprocal form needs d = 0 or |d| inside the proven range (else: IEEE division), the fast
-                    // form also |d| 2^22 >= |x| (compared on the high words: a strict inequality there implies the real
-                    // one; the few equal cases just count as failing)
-                    bad = !(recip_ok(d0) && recip_ok(d1) && recip_ok(d2));
-                    cancel = !safe && !((hi_abs(d0) + 0x01600000u > hi_abs(x0) || d0 == 0.0) && (hi_abs(d1) + 0x01600000u > hi_abs(x1) || d1 == 0.0) &&
-                                        (hi_abs(d2) + 0x01600000u > hi_abs(x2) || d2 == 0.0));
-                    double(*t)[33] = sm.t[q];
-                    const double e0 = x0 - n0, e1 = x1 - n1;
-                    const double t0 = d0 * e0, t1 = d1 * e1, t2 = d2 * (x2 - n2);
-                    // (x_j - new_j)(x_k - old_k) / count: mu_k (k > j) is not yet updated when dimension j runs
-                    const double p01 = e0 * d1, p02 = e0 * d2, p12 = e1 * d2;
-                    double q01 = fma(p01, rh, p01 * rl), q02 = fma(p02, rh, p02 * rl), q12 = fma(p12, rh, p12 * rl);
-                    if (!(recip_ok(p01) && recip_ok(p02) && recip_ok(p12))) {
-                        const double c = (double)(base[q] + lane + 1);
-                        q01 = p01 / c; q02 = p02 / c; q12 = p12 / c;                   // zeros, tiny or huge products: IEEE division
-                    }
-                    t[0][lane] = t0; t[1][lane] = t1; t[2][lane] = t2; t[3][lane] = q01; t[4][lane] = q02; t[5][lane] = q12;
-                    unsigned hm = hi_abs(t0);
-                    hm = max(hm, hi_abs(t1)); hm = max(hm, hi_abs(t2)); hm = max(hm, hi_abs(q01)); hm = max(hm, hi_abs(q02)); hm = max(hm, hi_abs(q12));
-                    nonfinite |= hm >= 0x7ff00000u;
-                }
-                if (redone) break;
-                const bool any_bad = __any_sync(0xffffffffu, bad), any_cancel = __any_sync(0xffffffffu, cancel);
-                if (!any_bad && !any_cancel) break;
-                // redo this slot's round on its three chain lanes, then its terms: with the IEEE division when an operand
-                // left the proven range (rare), else with the 4-operation chain; the slot stays wary for the rest of its voxel
-                if (any_cancel) wary[q] = true;
-                if (chain_lane && cq == q) {
-                    mu = mu_start;
-                    if (any_bad) {
-                        for (int k = 0; k < m[q]; k++) {
-                            const double cnt = (double)(base[q] + k + 1);
-                            mu = mu + (xs[k] - mu) / cnt;
-                            mus[k + 1] = mu;
-                        }
-                    } else {
-                        for (int k = 0; k < m[q]; k++) {
-                            const double2 r = rs[k];
-                            const double d = xs[k] - mu;
-                            mu = mu + fma(d, r.x, d * r.y);
-                            mus[k + 1] = mu;
-                        }
-                    }
-                }
-                redone = true;
-                __syncwarp();
+            for (int i = 0; i < kStatsUnroll; i++) {
+                bx[i] = i < ahead ? pnext[(size_t)i * kSortedStride] : T(0);
+                br[i] = rnext[i];
             }
         }
-        prev_chk = __any_sync(0xffffffffu, nonfinite);
-        __syncwarp();
-        // ---- advance the slots; a slot whose last terms were just added writes its voxel out
-        if (chain_lane && my_m > 0) mus[0] = mus[my_m];
-#pragma unroll
-        for (int q = 0; q < kQ; q++) {
-            if (!live[q]) continue;
-            if (m[q] > 0) { base[q] += (unsigned)m[q]; prev_m[q] = m[q]; continue; }
-            // variances m2 / n (normal_distributions.c:86-89), NaN -> 0
-            const double cntn = (double)nn[q];
-            double var = acc / cntn;
-            if (var != var) var = 0.0;
-            const double out = (acc_lane && at < 3) ? var : acc;
-            const double v0 = __shfl_sync(0xffffffffu, out, q * 6 + 0), v1 = __shfl_sync(0xffffffffu, out, q * 6 + 1), v2 = __shfl_sync(0xffffffffu, out, q * 6 + 2);
-            const double c01 = __shfl_sync(0xffffffffu, out, q * 6 + 3), c02 = __shfl_sync(0xffffffffu, out, q * 6 + 4), c12 = __shfl_sync(0xffffffffu, out, q * 6 + 5);
-            const double m0 = __shfl_sync(0xffffffffu, mu, q * 3 + 0), m1 = __shfl_sync(0xffffffffu, mu, q * 3 + 1), m2 = __shfl_sync(0xffffffffu, mu, q * 3 + 2);
-            unsigned label = 0;
-            if (vote_bins > 0) label = vote_from_hist(sm.h[q], vote_bins, lane);
-            if (lane == 0) {
-                double *mo = mean + ((size_t)b * vcap + vv[q]) * 3;
-                mo[0] = m0; mo[1] = m1; mo[2] = m2;
-                double *co = cov + ((size_t)b * vcap + vv[q]) * 9;
-                co[0] = v0; co[1] = c01; co[2] = c02; co[3] = c01; co[4] = v1; co[5] = c12; co[6] = c02; co[7] = c12; co[8] = v2;
-                if (vote_bins > 0) cls[(size_t)b * vcap + vv[q]] = (uint16_t)label;
-            }
-            live[q] = false; prev_m[q] = 0;
-        }
-        __syncwarp();
     }
 }
 
@@ -1564,22 +1453,14 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         if (!w.side) { CK(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&w.ev_join, cudaEventDisableTiming)); }
         CK(cudaEventRecord(w.ev_fork, st));
         CK(cudaStreamWaitEvent(w.side, w.ev_fork, 0));
-        const unsigned max_pairs = (max_heavy + kQ - 1) / kQ;
         // label vote: taken inside the statistics kernels from the label lane of the records they read anyway when the
         // class count fits their shared-memory counters; wide label sets were counted by k_scatter's global atomics
         const int vote_bins = labels && !wide_labels ? nbins : 0;
-        (void)max_pairs;
-        static const int stats_warps = [] { const char *e = getenv("NDNET_B200_STATS_WARPS"); const int v = e ? atoi(e) : 0; return v > 0 && v <= 64 ? v : kStatsWarpsPerCloud; }();
-        static const bool light_first = [] { const char *e = getenv("NDNET_B200_STATS_LIGHT_FIRST"); return e && *e == '1'; }();
-        auto launch_light = [&]() {
-            k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, (size_t)vote_bins * 128 * sizeof(unsigned short), w.side>>>(
-                w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
-        };
-        if (light_first) launch_light();
-        k_stats<T><<<dim3(B, stats_warps), 32, 0, st>>>(
+        k_stats<T><<<dim3(B, (max_heavy + kStatsVoxelsPerWarp - 1) / kStatsVoxelsPerWarp), 32, 0, st>>>(
             w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.recip, w.mean, w.cov, w.cls, vote_bins);
         DBG("k_stats");
-        if (!light_first) launch_light();
+        k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, (size_t)vote_bins * 128 * sizeof(unsigned short), w.side>>>(
+            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
         if (wide_labels) {
             k_votes<T><<<dim3(B, (vcap + 3) / 4), 128, 0, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.hist, nbins, w.cls);
         }
