@@ -157,8 +157,8 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     A(removed, (size_t)nB * vcap);
     A(list_div, (size_t)nB * kcap);
     A(list_seq, (size_t)nB * kcap);
-    A(recip, (size_t)nN + 16);        // k_stats fetches the reciprocal pairs up to two 8-step blocks past the largest count
-    if ((e = fill_recip_table(recip, nN + 16)) != cudaSuccess) { release(); return e; }
+    A(recip, (size_t)nN + 32);        // k_stats fetches the reciprocal pairs up to 23 steps past the largest count
+    if ((e = fill_recip_table(recip, nN + 32)) != cudaSuccess) { release(); return e; }
 #undef A
     return cudaSuccess;
 }

@@ -286,6 +286,7 @@ template <> __device__ __forceinline__ void load_sorted_rec<double>(const double
     x = v.x; y = v.y; z = w.x; label = (unsigned)__double_as_longlong(w.y);
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ unsigned sorted_label(const float *p) { return __float_as_uint(p[3]); }
 __device__ __forceinline__ unsigned sorted_label(const double *p) { return (unsigned)__double_as_longlong(p[3]); }
 

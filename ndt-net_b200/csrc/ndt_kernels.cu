@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(256) k_tile_prefix(const CloudState *__restric
 }
 
 // step 2b: slot totals -> segment starts, heaviest-first processing order, heavy/light split.  grid B, block 1024.
-__global__ void __launch_bounds__(1024) k_offsets(CloudState *__restrict__ states, unsigned vcap,
+__global__ void __launch_bounds__(1024) k_offsets(CloudState *__restrict__ states, unsigned vcap, unsigned heavy_min,
                                                   const unsigned *__restrict__ vox_n,
                                                   unsigned *__restrict__ vox_start, unsigned *__restrict__ vox_order) {
     const int b = blockIdx.x;
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(1024) k_offsets(CloudState *__restrict__ state
     if (tid == 0) {
         unsigned run = 0;
         for (int k = 0; k < 32; k++) { const unsigned c = s_hist[k]; s_hist[k] = run; run += c; }
-        s.n_heavy = s_hist[__clz(kHeavyVoxel) + 1];      // keys 0..clz(kHeavyVoxel) hold the voxels with n >= kHeavyVoxel
+        s.n_heavy = s_hist[__clz(heavy_min) + 1];        // keys 0..clz(heavy_min) hold the voxels with n >= heavy_min (a power of two <= kHeavyVoxel)
     }
     __syncthreads();
     for (unsigned v = tid; v < V; v += blockDim.x) {
@@ -685,7 +685,8 @@ template <> __device__ __forceinline__ double record_coord<float>(float v, bool)
 template <> __device__ __forceinline__ double record_coord<double>(double v, bool label_lane) { return label_lane ? 0.0 : v; }
 
 constexpr int kStatsVoxelsPerWarp = 8;          // four lanes per voxel
-constexpr int kStatsUnroll = 8;                 // steps per block: one 128-byte line of float records, operands fetched a block ahead
+constexpr int kStatsUnroll = 16;                // steps per block; the point operands are fetched a block (16 steps) ahead,
+constexpr int kStatsRecipRing = 8;              // the reciprocal pairs (uniform, mostly L1 hits) 8 steps ahead
 
 // m ? a : b on the bit patterns (m = all ones or zero, loop invariant per lane): two LOP3, no predicate to rebuild per step
 __device__ __forceinline__ double blend_bits(double a, double b, unsigned m) {
@@ -701,13 +702,18 @@ __device__ __forceinline__ double blend_bits(double a, double b, unsigned m) {
 // and receives e0 (c02 = d2 e0).
 // Fast form: straight-line, the quotients in reciprocal form whatever the operands; it only RECORDS whether an operand left
 // the range the reciprocal form is proven for.  The caller then redoes the block with the careful form.
-__device__ __forceinline__ void stats_step_fast(double x, double rh, double rl, int src, unsigned m_j0, unsigned m_j2,
-                                                double &mu, double &m2, double &c, unsigned &bad) {
-    const double d = x - mu;
+// The step is split in two so that the source order already is the software pipeline: the chain part of step i (the only
+// loop-carried latency) is followed by the tail of step i-1, whose operands have arrived by then.
+__device__ __forceinline__ void stats_chain_fast(double x, double rh, double rl, int src, unsigned m_j0,
+                                                 double &mu, double &d, double &e, double &rcv) {
+    d = x - mu;
     mu = mu + fma(d, rh, d * rl);
-    const double e = x - mu;
+    e = x - mu;
+    rcv = __shfl_sync(0xffffffffu, blend_bits(e, d, m_j0), src);
+}
+__device__ __forceinline__ void stats_tail_fast(double d, double e, double rcv, double rh, double rl, unsigned m_j2,
+                                                double &m2, double &c, unsigned &bad) {
     m2 = m2 + d * e;
-    const double rcv = __shfl_sync(0xffffffffu, blend_bits(e, d, m_j0), src);
     const double pr = blend_bits(d, e, m_j2) * rcv;
     c = c + fma(pr, rh, pr * rl);
     note_recip_unsafe(d, bad);
@@ -761,7 +767,7 @@ __global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(const CloudSta
                                               const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                               const unsigned *__restrict__ vox_order, const double2 *__restrict__ recip,
                                               double *__restrict__ mean, double *__restrict__ cov,
-                                              uint16_t *__restrict__ cls, int vote_bins) {
+                                              uint16_t *__restrict__ cls, int vote_bins, int pf_mode) {
     const int b = blockIdx.x;
     const CloudState &s = states[b];
     if (s.status != 0) return;
@@ -788,31 +794,49 @@ __global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(const CloudSta
     const unsigned my_bins = j == 3 ? (unsigned)vote_bins : 0u;
     double mu = 0.0, m2 = 0.0, c = 0.0;
     T bx[kStatsUnroll];
-    double2 br[kStatsUnroll];
+    double2 br[kStatsRecipRing];
 #pragma unroll
-    for (int i = 0; i < kStatsUnroll; i++) {
-        bx[i] = (unsigned)i < n ? p[(size_t)i * kSortedStride] : T(0);
-        br[i] = recip[i];                                  // (the table is padded by two blocks)
-    }
+    for (int i = 0; i < kStatsUnroll; i++) bx[i] = (unsigned)i < n ? p[(size_t)i * kSortedStride] : T(0);
+#pragma unroll
+    for (int i = 0; i < kStatsRecipRing; i++) br[i] = recip[i];          // (the table is padded by two blocks)
     for (unsigned k0 = 0; k0 < nmax; k0 += kStatsUnroll) {
         const int ahead = (int)(n - k0) - kStatsUnroll;    // points of this lane's voxel after this block
-        if (ahead > 4 * kStatsUnroll) prefetch_l2(p + (size_t)(k0 + 5 * kStatsUnroll) * kSortedStride);
-        const double2 *rnext = recip + k0 + kStatsUnroll;
+        if (pf_mode == 0) {
+            if (ahead > 2 * kStatsUnroll) {                 // the lines the loads of the next two blocks will want
+                prefetch_l2(p + (size_t)(k0 + 3 * kStatsUnroll) * kSortedStride);
+                prefetch_l2(p + (size_t)(k0 + 3 * kStatsUnroll + 8) * kSortedStride);
+            }
+        } else {
+            if (ahead > 2 * kStatsUnroll) {
+                prefetch_l1(p + (size_t)(k0 + 3 * kStatsUnroll) * kSortedStride);
+                prefetch_l1(p + (size_t)(k0 + 3 * kStatsUnroll + 8) * kSortedStride);
+            }
+            if (pf_mode == 2) { prefetch_l1(recip + k0 + 2 * kStatsUnroll); prefetch_l1(recip + k0 + 2 * kStatsUnroll + 8); }
+        }
+        const double2 *rnext = recip + k0 + kStatsRecipRing;
         const T *pnext = p + (size_t)(k0 + kStatsUnroll) * kSortedStride;
         if (!__any_sync(0xffffffffu, n - k0 - 1u < (unsigned)kStatsUnroll)) {
             const double mu0 = mu, m20 = m2, c0 = c;
             unsigned bad = 0u;
+            double pd = 0.0, pe = 0.0, prcv = 0.0, prh = 0.0, prl = 0.0;     // the previous step's tail operands
 #pragma unroll
             for (int i = 0; i < kStatsUnroll; i++) {
                 const T raw = bx[i];
-                const double2 r = br[i];
-                // the operands of the same step of the next block travel while this block is on the chain; a finished
-                // voxel's lanes compute on zeros
-                bx[i] = i < ahead ? pnext[(size_t)i * kSortedStride] : T(0);
-                br[i] = rnext[i];
+                const double2 r = br[i % kStatsRecipRing];
+                double d, e, rcv;
+                stats_chain_fast(record_coord<T>(raw, j == 3), r.x, r.y, src, m_j0, mu, d, e, rcv);
+                if (i > 0) stats_tail_fast(pd, pe, prcv, prh, prl, m_j2, m2, c, bad);
                 atomicAdd(my_hist + min(record_label<T>(raw), my_bins) * 32u, 1u);
-                stats_step_fast(record_coord<T>(raw, j == 3), r.x, r.y, src, m_j0, m_j2, mu, m2, c, bad);
+                // this step's registers are free now: fetch the operands of the same step of the next block into them
+                // (a finished voxel's lanes compute on zeros).  The empty asm ties the loads to this point of the chain;
+                // hoisted to the top of the block they would need a second set of registers and a copy per step.
+                const T *pn = pnext; const double2 *rn = rnext;
+                asm volatile("" : "+l"(pn), "+l"(rn) : "d"(mu));
+                bx[i] = i < ahead ? __ldg(pn + (size_t)i * kSortedStride) : T(0);
+                br[i % kStatsRecipRing] = __ldg(rn + i);
+                pd = d; pe = e; prcv = rcv; prh = r.x; prl = r.y;
             }
+            stats_tail_fast(pd, pe, prcv, prh, prl, m_j2, m2, c, bad);
             if (__any_sync(0xffffffffu, bad != 0u)) {      // rare: redo the block from its operands in memory
                 mu = mu0; m2 = m20; c = c0;
                 for (int i = 0; i < kStatsUnroll; i++) {
@@ -837,10 +861,9 @@ __global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(const CloudSta
                 }
             }
 #pragma unroll
-            for (int i = 0; i < kStatsUnroll; i++) {
-                bx[i] = i < ahead ? pnext[(size_t)i * kSortedStride] : T(0);
-                br[i] = rnext[i];
-            }
+            for (int i = 0; i < kStatsUnroll; i++) bx[i] = i < ahead ? pnext[(size_t)i * kSortedStride] : T(0);
+#pragma unroll
+            for (int i = 0; i < kStatsRecipRing; i++) br[i] = recip[k0 + kStatsUnroll + i];
         }
     }
 }
@@ -1433,7 +1456,9 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     }
     tm.mark(ST_OFFSETS, st);
     k_tile_prefix<<<dim3((vcap + 255) / 256, B), 256, 0, st>>>(w.states, vcap, ntiles, w.tile_cnt, w.vox_n); DBG("k_tile_prefix");
-    k_offsets<<<B, 1024, 0, st>>>(w.states, vcap, w.vox_n, w.vox_start, w.vox_order); DBG("k_offsets");
+    // voxels with at least heavy_min points go to k_stats (four lanes each), the rest to k_stats_light (a thread each)
+    static const unsigned heavy_min = [] { const char *e = getenv("NDNET_B200_HEAVY_LOG2"); const int v = e ? atoi(e) : 0; return v >= 3 && v <= 9 ? 1u << v : kHeavyVoxel; }();
+    k_offsets<<<B, 1024, 0, st>>>(w.states, vcap, heavy_min, w.vox_n, w.vox_start, w.vox_order); DBG("k_offsets");
     tm.mark(ST_SCATTER, st);
     const bool wide_labels = labels && nbins > kSmemLabelBins;
     if (wide_labels) CK(cudaMemsetAsync(w.hist, 0, (size_t)B * vcap * nbins * sizeof(unsigned), st));
@@ -1446,7 +1471,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     tm.mark(ST_STATS, st);
     // heavy voxels (a warp each; at most N / kHeavyVoxel of them per cloud), then the light ones (a thread each)
     {
-        unsigned max_heavy = (unsigned)(N / kHeavyVoxel) + 1;
+        unsigned max_heavy = (unsigned)(N / heavy_min) + 1;
         if (max_heavy > vcap) max_heavy = vcap;
         // the light kernel and the votes are independent of the heavy one: fork them onto the side stream so the
         // latency-bound tails overlap
@@ -1456,8 +1481,9 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         // label vote: taken inside the statistics kernels from the label lane of the records they read anyway when the
         // class count fits their shared-memory counters; wide label sets were counted by k_scatter's global atomics
         const int vote_bins = labels && !wide_labels ? nbins : 0;
+        static const int pf_mode = [] { const char *e = getenv("NDNET_B200_STATS_PF"); return e ? atoi(e) : 0; }();
         k_stats<T><<<dim3(B, (max_heavy + kStatsVoxelsPerWarp - 1) / kStatsVoxelsPerWarp), 32, 0, st>>>(
-            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.recip, w.mean, w.cov, w.cls, vote_bins);
+            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.recip, w.mean, w.cov, w.cls, vote_bins, pf_mode);
         DBG("k_stats");
         k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, (size_t)vote_bins * 128 * sizeof(unsigned short), w.side>>>(
             w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
