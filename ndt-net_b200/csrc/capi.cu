@@ -143,7 +143,13 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     A(tile_cnt, (size_t)nB * ntiles_cap * vcap);
     A(hist, (size_t)nB * vcap * (nbins > 0 ? nbins : 1));
     A(point_voxel, (size_t)nB * nN);
-    if ((e = cudaMalloc(&sorted, (size_t)nB * nN * 4 * sizeof(double))) != cudaSuccess) { release(); return e; }     // {x, y, z, label} records
+    // {x, y, z, label} records; k_stats' bulk copies run up to one 32-record stage past a voxel's end, so the buffer is
+    // padded by a stage and starts as zeros (what is read there only has to be finite)
+    {
+        const size_t sorted_bytes = ((size_t)nB * nN + 64) * 4 * sizeof(double);
+        if ((e = cudaMalloc(&sorted, sorted_bytes)) != cudaSuccess) { release(); return e; }
+        if ((e = cudaMemset(sorted, 0, sorted_bytes)) != cudaSuccess) { release(); return e; }
+    }
     A(mean, (size_t)nB * vcap * 3);
     A(cov, (size_t)nB * vcap * 9);
     A(cov_final, (size_t)nB * vcap * 9);

@@ -13,7 +13,8 @@
 #include <cstring>
 
 #ifndef NDT_STATS_MIN_CTAS
-#define NDT_STATS_MIN_CTAS 16                  // one-warp CTAs of k_stats per SM the register allocation must allow (<= 128 registers)
+#define NDT_STATS_MIN_CTAS 12                  // one-warp CTAs of k_stats per SM the register allocation must allow (<= 168 registers: below that the
+                                               // scheduler stops interleaving the tails of earlier steps with the mean chain)
 #endif
 constexpr unsigned kMaxSortedHeavy = 1024;       // k_offsets sorts up to this many heavy voxels exactly (one thread each)
 constexpr int kSelectThreads = 512;             // k_select: three 512-thread CTAs per SM overlap one another's barriers
@@ -685,8 +686,51 @@ template <> __device__ __forceinline__ double record_coord<float>(float v, bool)
 template <> __device__ __forceinline__ double record_coord<double>(double v, bool label_lane) { return label_lane ? 0.0 : v; }
 
 constexpr int kStatsVoxelsPerWarp = 8;          // four lanes per voxel
-constexpr int kStatsUnroll = 16;                // steps per block; the point operands are fetched a block (16 steps) ahead,
-constexpr int kStatsRecipRing = 8;              // the reciprocal pairs (uniform, mostly L1 hits) 8 steps ahead
+constexpr int kStatsUnroll = 16;                // steps per straight-line block
+constexpr int kStatsStage = 32;                 // steps per TMA stage: 32 records of each of the 8 voxels + 32 reciprocal pairs
+constexpr int kStatsStages = 3;                 // stages in flight: the operands are requested 64-96 steps before their use
+
+// Shared memory of one warp of k_stats: a ring of stages filled by 1-D bulk copies (TMA), the label counters, the barriers.
+// The records of a voxel are padded by 16 bytes per stage so that the 4-byte reads of the 32 lanes (8 voxels x {x, y, z,
+// label}) fall into 32 different banks.
+template <typename T> struct StatsSmem {
+    static constexpr int kVoxelElems = kStatsStage * kSortedStride + 16 / (int)sizeof(T);
+    static constexpr unsigned kVoxelBytes = kStatsStage * kSortedStride * sizeof(T);
+    static constexpr unsigned kRecipBytes = kStatsStage * sizeof(double2);
+    alignas(128) T recs[kStatsStages][kStatsVoxelsPerWarp][kVoxelElems];
+    alignas(16) double2 rc[kStatsStages][kStatsStage];
+    alignas(8) unsigned long long bar[kStatsStages];
+    unsigned hist[(kSmemLabelBins + 1) * kStatsVoxelsPerWarp];        // [class][voxel of the warp]; row vote_bins = out of range
+    unsigned dump[32];                                                // increments of the lanes that carry no label
+};
+
+namespace sptx {
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit; bytes and both addresses are multiples of 16
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+}  // namespace sptx
 
 // m ? a : b on the bit patterns (m = all ones or zero, loop invariant per lane): two LOP3, no predicate to rebuild per step
 __device__ __forceinline__ double blend_bits(double a, double b, unsigned m) {
@@ -753,21 +797,24 @@ __device__ __forceinline__ void stats_finish(double *__restrict__ mean, double *
         co[a] = c; co[m] = c;
     } else if (vote_bins > 0) {
         unsigned best = 0, bc = 0;
-        for (int t = 0; t < vote_bins; t++) { const unsigned x = s_hist[t * 32 + q]; if (x > best) { best = x; bc = (unsigned)t; } }
+        for (int t = 0; t < vote_bins; t++) { const unsigned x = s_hist[t * kStatsVoxelsPerWarp + q]; if (x > best) { best = x; bc = (unsigned)t; } }
         cls[slot] = (uint16_t)(best > 0 ? bc : 0u);
     }
 }
 
 // K7 (heavy voxels).  grid (B, ceil(max heavy voxels / 8)), block 32: warp g of a cloud takes entries 8g .. 8g+7 of vox_order
-// (descending size), so the first wave of CTAs holds every cloud's largest voxels.  vote_bins > 0: the label vote is taken
-// here too (shared-memory counters, <= kSmemLabelBins classes): row t of s_hist holds class t, word q the count of the warp's
-// voxel q, words 8..31 take the (discarded) increments of the other lanes so that the vote is branch-free.
+// (descending size), so the first wave of CTAs holds every cloud's largest voxels.  The operands never pass through
+// registers on their way in: the warp asks the TMA unit for the next 32 records of each live voxel and the 32 reciprocal
+// pairs of those counts (nine bulk copies per stage, three stages in flight), waits on the stage's mbarrier and reads the
+// step's operands with two shared-memory loads.  A finished voxel's lanes keep computing on whatever follows in the ring
+// (finite numbers; their results are not used).  vote_bins > 0: the label vote is taken here too (shared-memory counters,
+// <= kSmemLabelBins classes).
 template <typename T>
 __global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
                                               const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                               const unsigned *__restrict__ vox_order, const double2 *__restrict__ recip,
                                               double *__restrict__ mean, double *__restrict__ cov,
-                                              uint16_t *__restrict__ cls, int vote_bins, int pf_mode) {
+                                              uint16_t *__restrict__ cls, int vote_bins) {
     const int b = blockIdx.x;
     const CloudState &s = states[b];
     if (s.status != 0) return;
@@ -775,8 +822,20 @@ __global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(const CloudSta
     const unsigned first = blockIdx.y * kStatsVoxelsPerWarp;
     if (first >= n_heavy) return;
     const int lane = threadIdx.x, q = lane >> 2, j = lane & 3;
-    __shared__ unsigned s_hist[(kSmemLabelBins + 1) * 32];
-    for (int i = lane; i < (vote_bins + 1) * 32; i += 32) s_hist[i] = 0u;
+    using Smem = StatsSmem<T>;
+    __shared__ Smem sm;
+    {
+        // the ring starts as zeros: a lane whose voxel has ended (or that has none) must find finite numbers in it
+        uint4 *z = reinterpret_cast<uint4 *>(&sm);
+        for (int i = lane; i < (int)(sizeof(Smem) / sizeof(uint4)); i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < kStatsStages; t++) sptx::mbar_init(&sm.bar[t], 1);
+        sptx::fence_barrier_init();
+    }
+    sptx::fence_proxy_async_smem();                  // the zero fill (generic proxy) before the bulk copies (async proxy)
     __syncwarp();
     unsigned v = 0, n = 0, st = 0;
     if (first + q < n_heavy) {
@@ -785,86 +844,73 @@ __global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(const CloudSta
         n = vox_start[(size_t)b * (vcap + 1) + v + 1] - st;
     }
     const unsigned nmax = __reduce_max_sync(0xffffffffu, n);           // steps of the warp (uniform)
-    const T *p = sorted + ((size_t)b * N + st) * kSortedStride + j;
+    const unsigned nstages = (nmax + kStatsStage - 1) / kStatsStage;
+    const T *const pv = sorted + ((size_t)b * N + st) * kSortedStride;  // the voxel's records
+    // stage t -> buffer t % kStatsStages: 32 records of every voxel that still has points at step 32 t, and the reciprocals
+    auto request = [&](unsigned t) {
+        const unsigned kb = t * kStatsStage, buf = t % kStatsStages;
+        const bool mine = j == 0 && kb < n;
+        const unsigned live = __popc(__ballot_sync(0xffffffffu, mine));
+        if (lane == 0) sptx::mbar_expect_tx(&sm.bar[buf], live * Smem::kVoxelBytes + Smem::kRecipBytes);
+        __syncwarp();
+        if (mine) sptx::bulk_load(&sm.recs[buf][q][0], pv + (size_t)kb * kSortedStride, Smem::kVoxelBytes, &sm.bar[buf]);
+        if (lane == 0) sptx::bulk_load(&sm.rc[buf][0], recip + kb, Smem::kRecipBytes, &sm.bar[buf]);
+    };
+    for (unsigned t = 0; t < (unsigned)kStatsStages && t < nstages; t++) request(t);
+
     const int src = (lane & ~3) | (j == 0 ? 1 : (j == 1 ? 2 : 0));
     const unsigned m_j0 = j == 0 ? 0xffffffffu : 0u, m_j2 = j == 2 ? 0xffffffffu : 0u;
-    // vote target of this lane: label lanes count class min(label, vote_bins) of their voxel (row vote_bins = out of range,
-    // discarded), the other lanes increment a word of their own in the discarded part of row 0
-    unsigned *const my_hist = s_hist + (j == 3 ? q : 8 + q * 3 + j);
-    const unsigned my_bins = j == 3 ? (unsigned)vote_bins : 0u;
+    // the vote is branch-free (a branch per step would cut the unrolled block into pieces the scheduler cannot overlap):
+    // label lanes count class min(label, vote_bins) in their voxel's column, the other lanes increment a word of their own
+    unsigned *const my_hist = j == 3 ? sm.hist + q : sm.dump + lane;
+    const unsigned my_bins = (unsigned)vote_bins, my_stride = j == 3 ? (unsigned)kStatsVoxelsPerWarp : 0u;
     double mu = 0.0, m2 = 0.0, c = 0.0;
-    T bx[kStatsUnroll];
-    double2 br[kStatsRecipRing];
+    for (unsigned t = 0; t < nstages; t++) {
+        const unsigned buf = t % kStatsStages;
+        sptx::mbar_wait(&sm.bar[buf], (t / kStatsStages) & 1u);
+#pragma unroll 1
+        for (int h = 0; h < kStatsStage / kStatsUnroll; h++) {
+            const unsigned k0 = t * kStatsStage + h * kStatsUnroll;
+            if (k0 >= nmax) break;
+            const T *xb = &sm.recs[buf][q][h * kStatsUnroll * kSortedStride + j];
+            const double2 *rb = &sm.rc[buf][h * kStatsUnroll];
+            if (!__any_sync(0xffffffffu, n - k0 - 1u < (unsigned)kStatsUnroll)) {
+                const double mu0 = mu, m20 = m2, c0 = c;
+                unsigned bad = 0u;
+                double pd = 0.0, pe = 0.0, prcv = 0.0, prh = 0.0, prl = 0.0;     // the previous step's tail operands
 #pragma unroll
-    for (int i = 0; i < kStatsUnroll; i++) bx[i] = (unsigned)i < n ? p[(size_t)i * kSortedStride] : T(0);
-#pragma unroll
-    for (int i = 0; i < kStatsRecipRing; i++) br[i] = recip[i];          // (the table is padded by two blocks)
-    for (unsigned k0 = 0; k0 < nmax; k0 += kStatsUnroll) {
-        const int ahead = (int)(n - k0) - kStatsUnroll;    // points of this lane's voxel after this block
-        if (pf_mode == 0) {
-            if (ahead > 2 * kStatsUnroll) {                 // the lines the loads of the next two blocks will want
-                prefetch_l2(p + (size_t)(k0 + 3 * kStatsUnroll) * kSortedStride);
-                prefetch_l2(p + (size_t)(k0 + 3 * kStatsUnroll + 8) * kSortedStride);
-            }
-        } else {
-            if (ahead > 2 * kStatsUnroll) {
-                prefetch_l1(p + (size_t)(k0 + 3 * kStatsUnroll) * kSortedStride);
-                prefetch_l1(p + (size_t)(k0 + 3 * kStatsUnroll + 8) * kSortedStride);
-            }
-            if (pf_mode == 2) { prefetch_l1(recip + k0 + 2 * kStatsUnroll); prefetch_l1(recip + k0 + 2 * kStatsUnroll + 8); }
-        }
-        const double2 *rnext = recip + k0 + kStatsRecipRing;
-        const T *pnext = p + (size_t)(k0 + kStatsUnroll) * kSortedStride;
-        if (!__any_sync(0xffffffffu, n - k0 - 1u < (unsigned)kStatsUnroll)) {
-            const double mu0 = mu, m20 = m2, c0 = c;
-            unsigned bad = 0u;
-            double pd = 0.0, pe = 0.0, prcv = 0.0, prh = 0.0, prl = 0.0;     // the previous step's tail operands
-#pragma unroll
-            for (int i = 0; i < kStatsUnroll; i++) {
-                const T raw = bx[i];
-                const double2 r = br[i % kStatsRecipRing];
-                double d, e, rcv;
-                stats_chain_fast(record_coord<T>(raw, j == 3), r.x, r.y, src, m_j0, mu, d, e, rcv);
-                if (i > 0) stats_tail_fast(pd, pe, prcv, prh, prl, m_j2, m2, c, bad);
-                atomicAdd(my_hist + min(record_label<T>(raw), my_bins) * 32u, 1u);
-                // this step's registers are free now: fetch the operands of the same step of the next block into them
-                // (a finished voxel's lanes compute on zeros).  The empty asm ties the loads to this point of the chain;
-                // hoisted to the top of the block they would need a second set of registers and a copy per step.
-                const T *pn = pnext; const double2 *rn = rnext;
-                asm volatile("" : "+l"(pn), "+l"(rn) : "d"(mu));
-                bx[i] = i < ahead ? __ldg(pn + (size_t)i * kSortedStride) : T(0);
-                br[i % kStatsRecipRing] = __ldg(rn + i);
-                pd = d; pe = e; prcv = rcv; prh = r.x; prl = r.y;
-            }
-            stats_tail_fast(pd, pe, prcv, prh, prl, m_j2, m2, c, bad);
-            if (__any_sync(0xffffffffu, bad != 0u)) {      // rare: redo the block from its operands in memory
-                mu = mu0; m2 = m20; c = c0;
+                for (int i = 0; i < kStatsUnroll; i++) {
+                    const T raw = xb[i * kSortedStride];
+                    const double2 r = rb[i];
+                    double d, e, rcv;
+                    stats_chain_fast(record_coord<T>(raw, j == 3), r.x, r.y, src, m_j0, mu, d, e, rcv);
+                    if (i > 0) stats_tail_fast(pd, pe, prcv, prh, prl, m_j2, m2, c, bad);
+                    atomicAdd(my_hist + min(record_label<T>(raw), my_bins) * my_stride, 1u);
+                    pd = d; pe = e; prcv = rcv; prh = r.x; prl = r.y;
+                }
+                stats_tail_fast(pd, pe, prcv, prh, prl, m_j2, m2, c, bad);
+                if (__any_sync(0xffffffffu, bad != 0u)) {      // rare: redo the block (its operands are still in the ring)
+                    mu = mu0; m2 = m20; c = c0;
+                    for (int i = 0; i < kStatsUnroll; i++) {
+                        const double2 r = rb[i];
+                        stats_step_careful(record_coord<T>(xb[i * kSortedStride], j == 3), r.x, r.y, (double)(k0 + i + 1), src, m_j0, m_j2, mu, m2, c);
+                    }
+                }
+            } else {
+                // some voxel of the warp ends inside this block
+#pragma unroll 1
                 for (int i = 0; i < kStatsUnroll; i++) {
                     const unsigned k = k0 + i;
-                    const T raw = k < n ? p[(size_t)k * kSortedStride] : T(0);
-                    const double2 r = recip[k];
+                    const T raw = xb[i * kSortedStride];
+                    const double2 r = rb[i];
+                    if (j == 3 && k < n) atomicAdd(&sm.hist[min(record_label<T>(raw), my_bins) * kStatsVoxelsPerWarp + q], 1u);
                     stats_step_careful(record_coord<T>(raw, j == 3), r.x, r.y, (double)(k + 1), src, m_j0, m_j2, mu, m2, c);
+                    if (k + 1 == n) stats_finish(mean, cov, cls, (size_t)b * vcap + v, j, q, n, mu, m2, c, sm.hist, vote_bins);
                 }
             }
-        } else {
-            // some voxel of the warp ends inside this block
-#pragma unroll 1
-            for (int i = 0; i < kStatsUnroll; i++) {
-                const unsigned k = k0 + i;
-                const T raw = k < n ? p[(size_t)k * kSortedStride] : T(0);
-                const double2 r = recip[k];
-                if (k < n) atomicAdd(my_hist + min(record_label<T>(raw), my_bins) * 32u, 1u);
-                stats_step_careful(record_coord<T>(raw, j == 3), r.x, r.y, (double)(k + 1), src, m_j0, m_j2, mu, m2, c);
-                if (k + 1 == n) {
-                    stats_finish(mean, cov, cls, (size_t)b * vcap + v, j, q, n, mu, m2, c, s_hist, vote_bins);
-                    mu = 0.0;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < kStatsUnroll; i++) bx[i] = i < ahead ? pnext[(size_t)i * kSortedStride] : T(0);
-#pragma unroll
-            for (int i = 0; i < kStatsRecipRing; i++) br[i] = recip[k0 + kStatsUnroll + i];
         }
+        __syncwarp();                                       // every lane is done with the buffer
+        if (t + kStatsStages < nstages) request(t + kStatsStages);
     }
 }
 
@@ -1481,9 +1527,8 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         // label vote: taken inside the statistics kernels from the label lane of the records they read anyway when the
         // class count fits their shared-memory counters; wide label sets were counted by k_scatter's global atomics
         const int vote_bins = labels && !wide_labels ? nbins : 0;
-        static const int pf_mode = [] { const char *e = getenv("NDNET_B200_STATS_PF"); return e ? atoi(e) : 0; }();
         k_stats<T><<<dim3(B, (max_heavy + kStatsVoxelsPerWarp - 1) / kStatsVoxelsPerWarp), 32, 0, st>>>(
-            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.recip, w.mean, w.cov, w.cls, vote_bins, pf_mode);
+            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.recip, w.mean, w.cov, w.cls, vote_bins);
         DBG("k_stats");
         k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, (size_t)vote_bins * 128 * sizeof(unsigned short), w.side>>>(
             w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
