@@ -143,10 +143,10 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     A(tile_cnt, (size_t)nB * ntiles_cap * vcap);
     A(hist, (size_t)nB * vcap * (nbins > 0 ? nbins : 1));
     A(point_voxel, (size_t)nB * nN);
-    // {x, y, z, label} records; k_stats' bulk copies run up to one 32-record stage past a voxel's end, so the buffer is
+    // {x, y, z, label} records; k_stats' bulk copies run up to one 64-record stage past a voxel's end, so the buffer is
     // padded by a stage and starts as zeros (what is read there only has to be finite)
     {
-        const size_t sorted_bytes = ((size_t)nB * nN + 64) * 4 * sizeof(double);
+        const size_t sorted_bytes = ((size_t)nB * nN + 128) * 4 * sizeof(double);
         if ((e = cudaMalloc(&sorted, sorted_bytes)) != cudaSuccess) { release(); return e; }
         if ((e = cudaMemset(sorted, 0, sorted_bytes)) != cudaSuccess) { release(); return e; }
     }
@@ -163,8 +163,8 @@ cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
     A(removed, (size_t)nB * vcap);
     A(list_div, (size_t)nB * kcap);
     A(list_seq, (size_t)nB * kcap);
-    A(recip, (size_t)nN + 32);        // k_stats fetches the reciprocal pairs up to 23 steps past the largest count
-    if ((e = fill_recip_table(recip, nN + 32)) != cudaSuccess) { release(); return e; }
+    A(recip, (size_t)nN + 128);       // k_stats fetches the reciprocal pairs in stages of 64, up to a stage past the largest count
+    if ((e = fill_recip_table(recip, nN + 128)) != cudaSuccess) { release(); return e; }
 #undef A
     return cudaSuccess;
 }

@@ -29,7 +29,7 @@ constexpr int kLimWords = 8;                   // per cloud: encoded max x,y,z, 
 constexpr int kStatusNaNInput = -5;            // a coordinate is NaN: refused (the reference's behaviour is undefined, voxel.c:89-91)
 constexpr int kSortedStride = 4;               // voxel-sorted points are {x, y, z, label bits}: one 16-byte store per point
 constexpr int kSmemLabelBins = 64;
-constexpr unsigned kHeavyVoxel = 512;           // voxels with at least this many points go to k_stats (four lanes each), the rest to k_stats_light
+constexpr unsigned kHeavyVoxel = 128;           // voxels with at least this many points go to k_stats (four lanes each), the rest to k_stats_light
 
 // Per-cloud search/grid state (device resident, one per cloud).
 struct CloudState {

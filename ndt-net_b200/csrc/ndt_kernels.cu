@@ -687,8 +687,11 @@ template <> __device__ __forceinline__ double record_coord<double>(double v, boo
 
 constexpr int kStatsVoxelsPerWarp = 8;          // four lanes per voxel
 constexpr int kStatsUnroll = 16;                // steps per straight-line block
-constexpr int kStatsStage = 32;                 // steps per TMA stage: 32 records of each of the 8 voxels + 32 reciprocal pairs
-constexpr int kStatsStages = 3;                 // stages in flight: the operands are requested 64-96 steps before their use
+#ifndef NDT_STATS_STAGE
+#define NDT_STATS_STAGE 64
+#endif
+constexpr int kStatsStage = NDT_STATS_STAGE;    // steps per TMA stage: that many records of each of the 8 voxels + as many reciprocal pairs
+constexpr int kStatsStages = 2;                 // stages in the ring: the operands are requested one to two stages before their use
 
 // Shared memory of one warp of k_stats: a ring of stages filled by 1-D bulk copies (TMA), the label counters, the barriers.
 // The records of a voxel are padded by 16 bytes per stage so that the 4-byte reads of the 32 lanes (8 voxels x {x, y, z,
@@ -805,7 +808,7 @@ __device__ __forceinline__ void stats_finish(double *__restrict__ mean, double *
 // K7 (heavy voxels).  grid (B, ceil(max heavy voxels / 8)), block 32: warp g of a cloud takes entries 8g .. 8g+7 of vox_order
 // (descending size), so the first wave of CTAs holds every cloud's largest voxels.  The operands never pass through
 // registers on their way in: the warp asks the TMA unit for the next 32 records of each live voxel and the 32 reciprocal
-// pairs of those counts (nine bulk copies per stage, three stages in flight), waits on the stage's mbarrier and reads the
+// pairs of those counts (nine bulk copies per stage, the next stage in flight while this one is consumed), waits on the stage's mbarrier and reads the
 // step's operands with two shared-memory loads.  A finished voxel's lanes keep computing on whatever follows in the ring
 // (finite numbers; their results are not used).  vote_bins > 0: the label vote is taken here too (shared-memory counters,
 // <= kSmemLabelBins classes).
@@ -897,15 +900,26 @@ __global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(const CloudSta
                     }
                 }
             } else {
-                // some voxel of the warp ends inside this block
+                // some voxel of the warp ends inside this block: one step at a time, each lane looking for its last point
+                const double mu0 = mu, m20 = m2, c0 = c;
+                unsigned bad = 0u;
 #pragma unroll 1
                 for (int i = 0; i < kStatsUnroll; i++) {
-                    const unsigned k = k0 + i;
                     const T raw = xb[i * kSortedStride];
                     const double2 r = rb[i];
-                    if (j == 3 && k < n) atomicAdd(&sm.hist[min(record_label<T>(raw), my_bins) * kStatsVoxelsPerWarp + q], 1u);
-                    stats_step_careful(record_coord<T>(raw, j == 3), r.x, r.y, (double)(k + 1), src, m_j0, m_j2, mu, m2, c);
-                    if (k + 1 == n) stats_finish(mean, cov, cls, (size_t)b * vcap + v, j, q, n, mu, m2, c, sm.hist, vote_bins);
+                    double d, e, rcv;
+                    stats_chain_fast(record_coord<T>(raw, j == 3), r.x, r.y, src, m_j0, mu, d, e, rcv);
+                    stats_tail_fast(d, e, rcv, r.x, r.y, m_j2, m2, c, bad);
+                    atomicAdd(my_hist + min(record_label<T>(raw), my_bins) * my_stride, 1u);   // (after its end a voxel's counters are dead)
+                    if (k0 + i + 1 == n) stats_finish(mean, cov, cls, (size_t)b * vcap + v, j, q, n, mu, m2, c, sm.hist, vote_bins);
+                }
+                if (__any_sync(0xffffffffu, bad != 0u)) {      // rare: again with the careful form (the votes are in already)
+                    mu = mu0; m2 = m20; c = c0;
+                    for (int i = 0; i < kStatsUnroll; i++) {
+                        const double2 r = rb[i];
+                        stats_step_careful(record_coord<T>(xb[i * kSortedStride], j == 3), r.x, r.y, (double)(k0 + i + 1), src, m_j0, m_j2, mu, m2, c);
+                        if (k0 + i + 1 == n) stats_finish(mean, cov, cls, (size_t)b * vcap + v, j, q, n, mu, m2, c, sm.hist, 0);
+                    }
                 }
             }
         }
@@ -1503,7 +1517,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     tm.mark(ST_OFFSETS, st);
     k_tile_prefix<<<dim3((vcap + 255) / 256, B), 256, 0, st>>>(w.states, vcap, ntiles, w.tile_cnt, w.vox_n); DBG("k_tile_prefix");
     // voxels with at least heavy_min points go to k_stats (four lanes each), the rest to k_stats_light (a thread each)
-    static const unsigned heavy_min = [] { const char *e = getenv("NDNET_B200_HEAVY_LOG2"); const int v = e ? atoi(e) : 0; return v >= 3 && v <= 9 ? 1u << v : kHeavyVoxel; }();
+    static const unsigned heavy_min = [] { const char *e = getenv("NDNET_B200_HEAVY_LOG2"); const int v = e ? atoi(e) : 0; return v >= 3 && (1u << v) <= kHeavyVoxel ? 1u << v : kHeavyVoxel; }();
     k_offsets<<<B, 1024, 0, st>>>(w.states, vcap, heavy_min, w.vox_n, w.vox_start, w.vox_order); DBG("k_offsets");
     tm.mark(ST_SCATTER, st);
     const bool wide_labels = labels && nbins > kSmemLabelBins;
