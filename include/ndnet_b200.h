@@ -249,18 +249,25 @@ int ndnet_b200_ply_sample(ndnet_b200_ply *ply, const int64_t *indexes, size_t n,
 void ndnet_b200_ply_free(ndnet_b200_ply *ply);
 
 /* ------------------------------------------------------------------ (4) training step of the network
- * Train-mode forward and backward of NDTNetSegmentation (/root/reference/ndnet/models/ndtnet.py:33-62,112-164,
- * 218-243) as run by the reference's training loop (/root/reference/tools/train.py:66-76): BatchNorm with batch
- * statistics over all rows (running statistics updated in place, momentum 0.1, eps 1e-5), fp32 throughout.
+ * Train-mode forward and backward of the reference's four networks, recognised from the state_dict keys and shapes:
+ * NDTNetSegmentation / NDTNetClassification (/root/reference/ndnet/models/ndtnet.py:33-62,112-164,181-196,218-243) and
+ * PointNetSegmentation / PointNetClassification (pointnet.py:65-214, any point_dim <= 64), as run by the reference's
+ * training loops (/root/reference/tools/train.py:66-76): BatchNorm with batch statistics over all rows (running
+ * statistics updated in place, momentum 0.1, eps 1e-5), fp32 throughout.
  * `names`/`shapes` describe the module's parameters AND buffers (state_dict keys); `tensors[i]` / `grads[i]` of the
  * forward/backward calls are DEVICE pointers in that same order (grads[i] may be NULL for buffers; int64
  * num_batches_tracked buffers are passed through the same array and incremented).  The loss stays with the caller:
- * forward writes log-probabilities [B,N,C+1], backward takes dL/dlogp of the same shape and OVERWRITES each grads[i].
+ * forward writes the network's output - segmentation: log-probabilities [B,N,C+1]; classification: probabilities
+ * [B,num_classes] - and backward takes dL/d(output) of the same shape and OVERWRITES each grads[i].  `feat` is
+ * [B,N,12] = [mean | covariance] for the NDT networks and [B,N,point_dim] for PointNet (ndnet_b200_trainer_info).
  * B >= 2 (BatchNorm over the FC layers of the T-Nets needs more than one cloud). */
 typedef struct ndnet_b200_trainer ndnet_b200_trainer;
 int ndnet_b200_trainer_create(int device, int n_tensors, const char *const *names, const int64_t *const *shapes,
                               const int *ndims, ndnet_b200_trainer **out);
-int ndnet_b200_trainer_forward(ndnet_b200_trainer *t, const float *feat /* [B,N,12] */, int B, int N,
+/* kind: 0 NDTNetClassification, 1 NDTNetSegmentation, 2 PointNetClassification, 3 PointNetSegmentation; width of a row of
+ * `feat`; outputs per row (segmentation) or per cloud (classification).  Any pointer may be NULL. */
+int ndnet_b200_trainer_info(const ndnet_b200_trainer *t, int *kind, int *point_width, int *outputs);
+int ndnet_b200_trainer_forward(ndnet_b200_trainer *t, const float *feat /* [B,N,point_width] */, int B, int N,
                                float *const *tensors, float *out_logp, int update_running_stats, void *stream);
 int ndnet_b200_trainer_backward(ndnet_b200_trainer *t, const float *dlogp, float *const *tensors, float *const *grads,
                                 void *stream);

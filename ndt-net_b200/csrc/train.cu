@@ -310,6 +310,52 @@ __global__ void k_logsm_bwd(const float *__restrict__ dlogp, const float *__rest
     for (int c = 0; c < C; c++) dZ[r * C + c] = dlogp[r * C + c] - expf(logp[r * C + c]) * s;
 }
 
+// softmax over the C outputs of a row (ndtnet.py:194, pointnet.py:161) and its backward: dZ = p (dP - sum_c dP p)
+__global__ void k_softmax_fwd(const float *__restrict__ Z, long rows, int C, float *__restrict__ out) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float *z = Z + r * C;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; c++) mx = fmaxf(mx, z[c]);
+    float s = 0.f;
+    for (int c = 0; c < C; c++) s += expf(z[c] - mx);
+    const float inv = 1.f / s;
+    for (int c = 0; c < C; c++) out[r * C + c] = expf(z[c] - mx) * inv;
+}
+
+__global__ void k_softmax_bwd(const float *__restrict__ dP, const float *__restrict__ P, long rows, int C, float *__restrict__ dZ) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (int c = 0; c < C; c++) s += dP[r * C + c] * P[r * C + c];
+    for (int c = 0; c < C; c++) dZ[r * C + c] = P[r * C + c] * (dP[r * C + c] - s);
+}
+
+// ReLU of a layer without BatchNorm (the classification heads, ndtnet.py:189-190) and its backward (in place on dA)
+__global__ void k_relu_fwd(const float *__restrict__ Y, long n, float *__restrict__ A) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) A[t] = fmaxf(Y[t], 0.f);
+}
+__global__ void k_relu_bwd(float *__restrict__ dA, const float *__restrict__ A, long n) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && !(A[t] > 0.f)) dA[t] = 0.f;
+}
+
+// torch.nan_to_num(x, nan=0.0) (pointnet.py:117) in place: NaN -> 0, +-inf -> +-FLT_MAX; `finite` remembers which entries
+// were left alone (the gradient of the others is zero)
+__global__ void k_nan_to_num_fwd(float *__restrict__ X, long n, unsigned char *__restrict__ finite) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float v = X[t];
+    const bool ok = isfinite(v);
+    finite[t] = ok ? 1 : 0;
+    if (!ok) X[t] = v != v ? 0.f : (v > 0.f ? 3.402823466e+38f : -3.402823466e+38f);
+}
+__global__ void k_nan_to_num_bwd(float *__restrict__ dX, long n, const unsigned char *__restrict__ finite) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && !finite[t]) dX[t] = 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct Lin { int w = -1, b = -1, in = 0, out = 0; };
 struct Bn { int g = -1, be = -1, rm = -1, rv = -1, nbt = -1; };
@@ -338,9 +384,15 @@ struct Trainer {
     std::map<std::string, int> index;
     std::vector<std::vector<int64_t>> shapes;
     int n_tensors = 0;
-    int F = 0, C = 0;                     // feature_dim, num_classes + 1
+    int F = 0, C = 0;                     // feature_dim, network outputs per row (segmentation: num_classes + 1; classification: num_classes)
+    int kind = 1;                         // 0 NDTNetClassification, 1 NDTNetSegmentation, 2 PointNetClassification, 3 PointNetSegmentation
+    int D = 12;                           // input width: 12 = [mean | covariance] for the NDT networks, point_dim for PointNet
+    bool is_seg() const { return kind == 1 || kind == 3; }
+    bool is_ndt() const { return kind <= 1; }
+    long out_elems() const { return is_seg() ? (long)B * N * C : (long)B * C; }
     TNet t1, t2;
-    Block c1, c2, c3, h1, h2, h3, h4;
+    Block c1, c2, c3, h1, h2, h3, h4;     // h1..h4: segmentation head; classification head: h1..h3 over one row per cloud
+    unsigned char *finite = nullptr;      // PointNet: nan_to_num mask of the transformed input
     int B = 0, N = 0;
     char *arena = nullptr; size_t arena_bytes = 0; size_t zero_begin = 0, zero_end = 0;
     float *X12 = nullptr, *dX12 = nullptr, *X2 = nullptr, *H0 = nullptr, *dH0 = nullptr, *Gf = nullptr, *dGf = nullptr, *dX4 = nullptr;
@@ -426,7 +478,7 @@ static void layout_block(Bump &b, char *base, Block &k, long rows, bool zero_reg
     if (!zero_region) {
         size_t o;
         o = b.take<float>(n); if (base) k.Y = (float *)(base + o);
-        if (k.has_bn) { o = b.take<float>(n); if (base) k.A = (float *)(base + o); } else if (base) k.A = k.Y;
+        if (k.has_bn || k.relu) { o = b.take<float>(n); if (base) k.A = (float *)(base + o); } else if (base) k.A = k.Y;
         o = b.take<float>(n); if (base) k.dA = (float *)(base + o);
         o = b.take<float>(k.lin.out); if (base) k.mean = (float *)(base + o);
         o = b.take<float>(k.lin.out); if (base) k.rstd = (float *)(base + o);
@@ -439,8 +491,10 @@ static void layout_block(Bump &b, char *base, Block &k, long rows, bool zero_reg
 
 static void layout(Trainer &t, Bump &b, char *base, int B, int N) {
     const long M = (long)B * N;
-    Block *big[] = {&t.t1.c1, &t.t1.c2, &t.t1.c3, &t.t2.c1, &t.t2.c2, &t.t2.c3, &t.c1, &t.c2, &t.c3, &t.h1, &t.h2, &t.h3, &t.h4};
-    Block *small[] = {&t.t1.f1, &t.t1.f2, &t.t1.f3, &t.t2.f1, &t.t2.f2, &t.t2.f3};
+    std::vector<Block *> big = {&t.t1.c1, &t.t1.c2, &t.t1.c3, &t.t2.c1, &t.t2.c2, &t.t2.c3, &t.c1, &t.c2, &t.c3};
+    std::vector<Block *> small = {&t.t1.f1, &t.t1.f2, &t.t1.f3, &t.t2.f1, &t.t2.f2, &t.t2.f3};
+    for (Block *k : {&t.h1, &t.h2, &t.h3}) (t.is_seg() ? big : small).push_back(k);
+    if (t.is_seg()) big.push_back(&t.h4);
     for (Block *k : big) layout_block(b, base, *k, M, false);
     for (Block *k : small) layout_block(b, base, *k, B, false);
     size_t o;
@@ -449,12 +503,15 @@ static void layout(Trainer &t, Bump &b, char *base, int B, int N) {
         TAKE(float, n->G, (size_t)B * 1024); TAKE(float, n->dG, (size_t)B * 1024); TAKE(int, n->idx, (size_t)B * 1024);
         TAKE(float, n->T, (size_t)B * n->d * n->d); TAKE(float, n->dT, (size_t)B * n->d * n->d);
     }
-    TAKE(float, t.X12, (size_t)M * 12); TAKE(float, t.dX12, (size_t)M * 12); TAKE(float, t.X2, (size_t)M * 64);
+    TAKE(float, t.X12, (size_t)M * t.D); TAKE(float, t.dX12, (size_t)M * t.D); TAKE(float, t.X2, (size_t)M * 64);
+    if (!t.is_ndt()) { TAKE(unsigned char, t.finite, (size_t)M * t.D); }
+    // (the classification heads keep dH0 too: its first 64 columns carry dX2 through the backward of the trunk)
     TAKE(float, t.H0, (size_t)M * (64 + t.F)); TAKE(float, t.dH0, (size_t)M * (64 + t.F));
     TAKE(float, t.Gf, (size_t)B * t.F); TAKE(float, t.dGf, (size_t)B * t.F); TAKE(float, t.dX4, (size_t)M * t.F);
     TAKE(int, t.idxf, (size_t)B * t.F);
-    TAKE(float, t.logp, (size_t)M * t.C); TAKE(float, t.dZ, (size_t)M * t.C);
-    TAKE(float, t.feat_static, (size_t)M * 12); TAKE(float, t.dlogp_static, (size_t)M * t.C); TAKE(float, t.flat_grad, (size_t)t.flat_elems);
+    const size_t outs = t.is_seg() ? (size_t)M * t.C : (size_t)B * t.C;
+    TAKE(float, t.logp, outs); TAKE(float, t.dZ, outs);
+    TAKE(float, t.feat_static, (size_t)M * t.D); TAKE(float, t.dlogp_static, outs); TAKE(float, t.flat_grad, (size_t)t.flat_elems);
     {
         const long ldT = (M + 3) / 4 * 4;
         const size_t wide = (size_t)(64 + t.F > 1024 ? 64 + t.F : 1024);
@@ -640,7 +697,10 @@ static void block_fwd(const Pass &ps, Block &k, const float *X, long ldx) {
     if (!(ps.t.tf32 && gemm_tf32(ps.st, X, ldx, ps.P(k.lin.w), in, k.Y, out, (int)k.rows, out, in, ps.P(k.lin.b), false,
                                  k.has_bn ? k.red : nullptr, k.has_bn ? k.red + out : nullptr, &stats_fused)))
         gemm(ps.st, X, ldx, 1, ps.P(k.lin.w), in, 1, k.Y, out, (int)k.rows, out, in, ps.P(k.lin.b), false);
-    if (!k.has_bn) return;
+    if (!k.has_bn) {
+        if (k.relu) train_count(), k_relu_fwd<<<cdiv(k.rows * out, 256), 256, 0, ps.st>>>(k.Y, k.rows * out, k.A);
+        return;
+    }
     if (!stats_fused) {
         RedP r{};
         r.P = k.Y; r.ldp = out; r.rows = (int)k.rows; r.cols = out; r.s0 = k.red; r.s1 = k.red + out;
@@ -662,6 +722,8 @@ static void block_bwd(const Pass &ps, Block &k, const float *X, long ldx, float 
         colred<RED_BNBWD>(ps.st, r, 1);
         if (ps.Gr(k.bn.be) && ps.Gr(k.bn.g)) train_count(), k_bnbwd_finalize<<<cdiv(out, 128), 128, 0, ps.st>>>(s0, s1, out, ps.Gr(k.bn.be), ps.Gr(k.bn.g));
         train_count(), k_bnbwd_apply<<<cdiv(k.rows * out, 256), 256, 0, ps.st>>>(k.dA, k.Y, k.relu ? k.A : nullptr, k.rows, out, k.mean, k.rstd, ps.P(k.bn.g), s0, s1);
+    } else if (k.relu) {
+        train_count(), k_relu_bwd<<<cdiv(k.rows * out, 256), 256, 0, ps.st>>>(k.dA, k.A, k.rows * out);
     }
     float *dY = k.dA;
     if (ps.Gr(k.lin.b)) {
@@ -724,22 +786,36 @@ static int forward(Trainer &t, const float *feat, int B, int N, float *const *te
     const long M = (long)B * N;
     Pass ps{t, tensors, nullptr, st, update_running};
     t.feat = feat;
+    const int D = t.D;
     cudaMemsetAsync(t.arena + t.zero_begin, 0, t.zero_end - t.zero_begin, st);
-    tnet_fwd(ps, t.t1, feat, 12);                                                         // ndtnet.py:131-132
-    train_count(), k_apply_t_fwd<<<cdiv(M, 128), 128, 0, st>>>(feat, t.t1.T, M, N, t.X12);              // :134-146
-    block_fwd(ps, t.c1, t.X12, 12);                                                       // :149
+    tnet_fwd(ps, t.t1, feat, D);                                                          // ndtnet.py:131-132, pointnet.py:113
+    if (t.is_ndt()) {
+        train_count(), k_apply_t_fwd<<<cdiv(M, 128), 128, 0, st>>>(feat, t.t1.T, M, N, t.X12);          // ndtnet.py:134-146
+    } else {
+        // x' = T1 x per cloud, rows: x'[n, i] = sum_k x[n, k] T1[i, k]; then nan_to_num (pointnet.py:115-117)
+        gemm(st, feat, D, 1, t.t1.T, D, 1, t.X12, D, N, D, D, nullptr, false, B, (long)N * D, (long)D * D, (long)N * D);
+        train_count(), k_nan_to_num_fwd<<<cdiv(M * D, 256), 256, 0, st>>>(t.X12, M * D, t.finite);
+    }
+    block_fwd(ps, t.c1, t.X12, D);                                                        // :149
     tnet_fwd(ps, t.t2, t.c1.A, 64);                                                       // :152
     gemm(st, t.c1.A, 64, 1, t.t2.T, 1, 64, t.X2, 64, N, 64, 64, nullptr, false, B, (long)N * 64, 4096, (long)N * 64);   // :153-155
     block_fwd(ps, t.c2, t.X2, 64);                                                        // :160
     block_fwd(ps, t.c3, t.c2.A, 128);                                                     // :161
-    train_count(), k_maxpool_fwd<<<dim3(cdiv(t.F, 32), B), 256, 0, st>>>(t.c3.A, N, t.F, t.Gf, t.idxf); // :224
-    train_count(), k_concat_fwd<<<cdiv(M * (64 + t.F), 256), 256, 0, st>>>(t.X2, t.Gf, M, N, t.F, t.H0);   // :227-230
-    block_fwd(ps, t.h1, t.H0, 64 + t.F);                                                  // :233
-    block_fwd(ps, t.h2, t.h1.A, 512);
-    block_fwd(ps, t.h3, t.h2.A, 256);
-    block_fwd(ps, t.h4, t.h3.A, 128);                                                     // :236
-    train_count(), k_logsm_fwd<<<cdiv(M, 128), 128, 0, st>>>(t.h4.Y, M, t.C, t.logp);                    // :239
-    if (out_logp) cudaMemcpyAsync(out_logp, t.logp, sizeof(float) * M * t.C, cudaMemcpyDeviceToDevice, st);
+    train_count(), k_maxpool_fwd<<<dim3(cdiv(t.F, 32), B), 256, 0, st>>>(t.c3.A, N, t.F, t.Gf, t.idxf); // :186, :224
+    if (t.is_seg()) {
+        train_count(), k_concat_fwd<<<cdiv(M * (64 + t.F), 256), 256, 0, st>>>(t.X2, t.Gf, M, N, t.F, t.H0);   // :227-230
+        block_fwd(ps, t.h1, t.H0, 64 + t.F);                                              // :233
+        block_fwd(ps, t.h2, t.h1.A, 512);
+        block_fwd(ps, t.h3, t.h2.A, 256);
+        block_fwd(ps, t.h4, t.h3.A, 128);                                                 // :236
+        train_count(), k_logsm_fwd<<<cdiv(M, 128), 128, 0, st>>>(t.h4.Y, M, t.C, t.logp);                // :239
+    } else {
+        block_fwd(ps, t.h1, t.Gf, t.F);                                                   // ndtnet.py:189-191: one row per cloud
+        block_fwd(ps, t.h2, t.h1.A, 512);
+        block_fwd(ps, t.h3, t.h2.A, 256);
+        train_count(), k_softmax_fwd<<<cdiv(B, 128), 128, 0, st>>>(t.h3.Y, B, t.C, t.logp);              // :194 (probabilities, not logs)
+    }
+    if (out_logp) cudaMemcpyAsync(out_logp, t.logp, sizeof(float) * t.out_elems(), cudaMemcpyDeviceToDevice, st);
     e = cudaGetLastError();
     if (e != cudaSuccess) { t.err = std::string("forward: ") + cudaGetErrorString(e); return -100 - (int)e; }
     return 0;
@@ -761,18 +837,27 @@ static int backward(Trainer &t, const float *dlogp, float *const *tensors, float
     Pass ps{t, tensors, grads, st, 0};
     // the forward's column sums are already folded into mean/rstd: clear every accumulator for this pass
     cudaMemsetAsync(t.arena + t.zero_begin, 0, t.zero_end - t.zero_begin, st);
-    train_count(), k_logsm_bwd<<<cdiv(M, 128), 128, 0, st>>>(dlogp, t.logp, M, t.C, t.h4.dA);
-    block_bwd(ps, t.h4, t.h3.A, 128, t.h3.dA, 128, false);
-    block_bwd(ps, t.h3, t.h2.A, 256, t.h2.dA, 256, false);
-    block_bwd(ps, t.h2, t.h1.A, 512, t.h1.dA, 512, false);
-    block_bwd(ps, t.h1, t.H0, W, t.dH0, W, false);
-    record_bucket(t, 0, st);
-    // dH0 = [dX2 | per-row gradient of the broadcast global feature]
-    {
+    const int D = t.D;
+    if (t.is_seg()) {
+        train_count(), k_logsm_bwd<<<cdiv(M, 128), 128, 0, st>>>(dlogp, t.logp, M, t.C, t.h4.dA);
+        block_bwd(ps, t.h4, t.h3.A, 128, t.h3.dA, 128, false);
+        block_bwd(ps, t.h3, t.h2.A, 256, t.h2.dA, 256, false);
+        block_bwd(ps, t.h2, t.h1.A, 512, t.h1.dA, 512, false);
+        block_bwd(ps, t.h1, t.H0, W, t.dH0, W, false);
+        record_bucket(t, 0, st);
+        // dH0 = [dX2 | per-row gradient of the broadcast global feature]
         RedP r{};
         r.P = t.dH0 + 64; r.ldp = W; r.rows = N; r.cols = t.F; r.batch_stride_rows = N; r.s0 = t.red_gf;
         colred<RED_SUM>(st, r, B);
         train_count(), k_sum_finalize<<<cdiv((long)B * t.F, 128), 128, 0, st>>>(t.red_gf, (long)B * t.F, t.dGf);
+    } else {
+        train_count(), k_softmax_bwd<<<cdiv(B, 128), 128, 0, st>>>(dlogp, t.logp, B, t.C, t.h3.dA);
+        block_bwd(ps, t.h3, t.h2.A, 256, t.h2.dA, 256, false);
+        block_bwd(ps, t.h2, t.h1.A, 512, t.h1.dA, 512, false);
+        block_bwd(ps, t.h1, t.Gf, t.F, t.dGf, t.F, false);
+        record_bucket(t, 0, st);
+        // x_t2 only feeds the trunk here: its gradient (first 64 columns of dH0) starts at zero
+        cudaMemset2DAsync(t.dH0, sizeof(float) * W, 0, sizeof(float) * 64, M, st);
     }
     train_count(), k_maxpool_bwd<<<cdiv(M * t.F, 256), 256, 0, st>>>(t.dGf, t.idxf, N, t.F, M * t.F, t.c3.dA);
     block_bwd(ps, t.c3, t.c2.A, 128, t.c2.dA, 128, false);
@@ -782,9 +867,15 @@ static int backward(Trainer &t, const float *dlogp, float *const *tensors, float
     gemm(st, t.c1.A, 1, 64, t.dH0, 1, W, t.t2.dT, 64, 64, 64, N, nullptr, false, B, (long)N * 64, (long)N * W, 4096);
     tnet_bwd(ps, t.t2, t.c1.A, 64, t.c1.dA, 64, true);
     record_bucket(t, 1, st);
-    block_bwd(ps, t.c1, t.X12, 12, t.dX12, 12, false);
-    train_count(), k_apply_t_bwd<<<B, 256, 0, st>>>(t.feat, t.dX12, N, t.t1.dT);
-    tnet_bwd(ps, t.t1, t.feat, 12, nullptr, 0, false);
+    block_bwd(ps, t.c1, t.X12, D, t.dX12, D, false);
+    if (t.is_ndt()) {
+        train_count(), k_apply_t_bwd<<<B, 256, 0, st>>>(t.feat, t.dX12, N, t.t1.dT);
+    } else {
+        // x' = nan_to_num(T1 x): dT1[i, k] = sum_n dx'[n, i] x[n, k] over the entries nan_to_num left alone
+        train_count(), k_nan_to_num_bwd<<<cdiv(M * D, 256), 256, 0, st>>>(t.dX12, M * D, t.finite);
+        gemm(st, t.dX12, 1, D, t.feat, 1, D, t.t1.dT, D, D, D, N, nullptr, false, B, (long)N * D, (long)N * D, (long)D * D);
+    }
+    tnet_bwd(ps, t.t1, t.feat, D, nullptr, 0, false);
     record_bucket(t, 2, st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { t.err = std::string("backward: ") + cudaGetErrorString(e); return -100 - (int)e; }
@@ -835,12 +926,12 @@ static int forward_entry(Trainer &t, const float *feat, int B, int N, float *con
     cudaError_t e = reserve(t, B, N);
     if (e != cudaSuccess) { t.err = std::string("workspace: ") + cudaGetErrorString(e); return -100 - (int)e; }
     const long M = (long)B * N;
-    cudaMemcpyAsync(t.feat_static, feat, sizeof(float) * M * 12, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(t.feat_static, feat, sizeof(float) * M * t.D, cudaMemcpyDeviceToDevice, st);
     const int rc = run_graphed(t, t.gf, pass_key(t, tensors, update_running ? 1 : 0), st, [&](cudaStream_t s) {
         return forward(t, t.feat_static, B, N, tensors, nullptr, update_running, s);
     });
     if (rc != 0) return rc;
-    cudaMemcpyAsync(out_logp, t.logp, sizeof(float) * M * t.C, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(out_logp, t.logp, sizeof(float) * t.out_elems(), cudaMemcpyDeviceToDevice, st);
     return 0;
 }
 
@@ -852,8 +943,7 @@ static int backward_flat(Trainer &t, const float *dlogp, float *const *tensors, 
         for (int i = 0; i < t.n_tensors; i++) if (t.grad_off[i] >= 0) grads[i] = flat_out + t.grad_off[i];
         return backward(t, dlogp, tensors, grads.data(), st);
     }
-    const long M = (long)t.B * t.N;
-    cudaMemcpyAsync(t.dlogp_static, dlogp, sizeof(float) * M * t.C, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(t.dlogp_static, dlogp, sizeof(float) * t.out_elems(), cudaMemcpyDeviceToDevice, st);
     t.static_grads.assign(t.n_tensors, nullptr);
     for (int i = 0; i < t.n_tensors; i++) if (t.grad_off[i] >= 0) t.static_grads[i] = t.flat_grad + t.grad_off[i];
     const int rc = run_graphed(t, t.gb, pass_key(t, tensors, 2), st, [&](cudaStream_t s) {
@@ -906,26 +996,46 @@ extern "C" int ndnet_b200_trainer_create(int device, int n_tensors, const char *
         delete h;
         return -205;
     };
+    // which of the reference's four networks this state_dict is (ndtnet.py:166-243, pointnet.py:137-214): a segmentation
+    // head has conv4 and BatchNorm layers of its own; the NDT trunk takes 12-wide rows behind a 3x3 input transform, the
+    // PointNet trunk point_dim-wide rows behind a point_dim x point_dim one
     auto it = t.index.find("feature_extractor.conv3.weight");
-    auto ic = t.index.find("conv4.weight");
-    if (it == t.index.end() || ic == t.index.end()) return fail("not an NDTNetSegmentation state_dict");
+    auto i1 = t.index.find("feature_extractor.conv1.weight");
+    auto it1 = t.index.find("feature_extractor.t1.conv1.weight");
+    if (it == t.index.end() || i1 == t.index.end() || it1 == t.index.end()) return fail("not an NDTNet / PointNet state_dict");
+    const bool seg = t.index.count("conv4.weight") != 0;
+    auto ic = t.index.find(seg ? "conv4.weight" : "conv3.weight");
+    if (ic == t.index.end()) return fail("no output layer (conv3 / conv4) in the state_dict");
     t.F = (int)t.shapes[it->second][0];
     t.C = (int)t.shapes[ic->second][0];
+    t.D = (int)t.shapes[i1->second][1];
+    const int d1 = (int)t.shapes[it1->second][1];
+    const bool ndt = t.D == 12 && d1 == 3;
+    if (!ndt && d1 != t.D) return fail("input transform and first layer disagree on the point width");
+    if (t.D < 1 || t.D > 64) return fail("unsupported point width");
+    t.kind = (ndt ? 0 : 2) + (seg ? 1 : 0);
     using namespace train;
     const std::string fe = "feature_extractor";
-    bool ok = bind_tnet(t, t.t1, fe + ".t1", 3) && bind_tnet(t, t.t2, fe + ".t2", 64) &&
-              bind_block(t, t.c1, fe + ".conv1", fe + ".bn1", 12, 64, false) && bind_block(t, t.c2, fe + ".conv2", fe + ".bn2", 64, 128, false) &&
-              bind_block(t, t.c3, fe + ".conv3", fe + ".bn3", 128, t.F, false) && bind_block(t, t.h1, "conv1", "bn1", 64 + t.F, 512, true) &&
-              bind_block(t, t.h2, "conv2", "bn2", 512, 256, true) && bind_block(t, t.h3, "conv3", "bn3", 256, 128, true) &&
-              bind_block(t, t.h4, "conv4", "", 128, t.C, false);
+    bool ok = bind_tnet(t, t.t1, fe + ".t1", d1) && bind_tnet(t, t.t2, fe + ".t2", 64) &&
+              bind_block(t, t.c1, fe + ".conv1", fe + ".bn1", t.D, 64, false) && bind_block(t, t.c2, fe + ".conv2", fe + ".bn2", 64, 128, false) &&
+              bind_block(t, t.c3, fe + ".conv3", fe + ".bn3", 128, t.F, false);
+    if (seg)
+        ok = ok && bind_block(t, t.h1, "conv1", "bn1", 64 + t.F, 512, true) && bind_block(t, t.h2, "conv2", "bn2", 512, 256, true) &&
+             bind_block(t, t.h3, "conv3", "bn3", 256, 128, true) && bind_block(t, t.h4, "conv4", "", 128, t.C, false);
+    else
+        ok = ok && bind_block(t, t.h1, "conv1", "", t.F, 512, true) && bind_block(t, t.h2, "conv2", "", 512, 256, true) &&
+             bind_block(t, t.h3, "conv3", "", 256, t.C, false);
     if (!ok) return fail("tensor binding failed");
     {   // flat gradient layout: parameters (weights, biases, BatchNorm scale/shift) in the order backward finishes them,
         // 16-byte aligned; three buckets (head | trunk conv2-3 + feature T-Net | conv1 + input T-Net)
         t.grad_off.assign(n_tensors, -1);
-        Block *order[] = {&t.h4, &t.h3, &t.h2, &t.h1,
-                          &t.c3, &t.c2, &t.t2.f3, &t.t2.f2, &t.t2.f1, &t.t2.c3, &t.t2.c2, &t.t2.c1,
-                          &t.c1, &t.t1.f3, &t.t1.f2, &t.t1.f1, &t.t1.c3, &t.t1.c2, &t.t1.c1};
-        const int bucket_last[Trainer::kBuckets] = {3, 11, 18};
+        std::vector<Block *> order;
+        if (seg) order.push_back(&t.h4);
+        for (Block *b : {&t.h3, &t.h2, &t.h1}) order.push_back(b);
+        const int head_last = (int)order.size() - 1;
+        for (Block *b : {&t.c3, &t.c2, &t.t2.f3, &t.t2.f2, &t.t2.f1, &t.t2.c3, &t.t2.c2, &t.t2.c1,
+                         &t.c1, &t.t1.f3, &t.t1.f2, &t.t1.f1, &t.t1.c3, &t.t1.c2, &t.t1.c1}) order.push_back(b);
+        const int bucket_last[Trainer::kBuckets] = {head_last, head_last + 8, head_last + 15};
         long off = 0;
         int bucket = 0;
         auto place = [&](int i) {
@@ -935,15 +1045,23 @@ extern "C" int ndnet_b200_trainer_create(int device, int n_tensors, const char *
             t.grad_off[i] = off;
             off += (numel + 3) / 4 * 4;
         };
-        for (int k = 0; k < 19; k++) {
+        for (int k = 0; k < (int)order.size(); k++) {
             Block *b = order[k];
             place(b->lin.w); place(b->lin.b);
             if (b->has_bn) { place(b->bn.g); place(b->bn.be); }
-            if (k == bucket_last[bucket]) t.bucket_end[bucket++] = off;
+            if (bucket < Trainer::kBuckets && k == bucket_last[bucket]) t.bucket_end[bucket++] = off;
         }
         t.flat_elems = off;
     }
     *out = h;
+    return 0;
+}
+
+extern "C" int ndnet_b200_trainer_info(const ndnet_b200_trainer *h, int *kind, int *point_width, int *outputs) {
+    if (!h) return -200;
+    if (kind) *kind = h->t.kind;
+    if (point_width) *point_width = h->t.D;
+    if (outputs) *outputs = h->t.C;
     return 0;
 }
 
@@ -1041,18 +1159,18 @@ extern "C" long ndnet_b200_trainer_debug_buffer(ndnet_b200_trainer *h, const cha
     const float *src = nullptr;
     long count = 0;
     const long M = (long)t.B * t.N;
-    if (n == "t1.T") { src = t.t1.T; count = t.B * 9; }
+    if (n == "t1.T") { src = t.t1.T; count = (long)t.B * t.t1.d * t.t1.d; }
     else if (n == "t2.T") { src = t.t2.T; count = (long)t.B * 4096; }
-    else if (n == "t1.dT") { src = t.t1.dT; count = t.B * 9; }
+    else if (n == "t1.dT") { src = t.t1.dT; count = (long)t.B * t.t1.d * t.t1.d; }
     else if (n == "t2.dT") { src = t.t2.dT; count = (long)t.B * 4096; }
     else if (n == "dH0") { src = t.dH0; count = M * (64 + t.F); }
-    else if (n == "dX12") { src = t.dX12; count = M * 12; }
-    else if (n == "X12") { src = t.X12; count = M * 12; }
+    else if (n == "dX12") { src = t.dX12; count = M * t.D; }
+    else if (n == "X12") { src = t.X12; count = M * t.D; }
     else if (n == "X2") { src = t.X2; count = M * 64; }
     else if (n == "H0") { src = t.H0; count = M * (64 + t.F); }
     else if (n == "Gf") { src = t.Gf; count = (long)t.B * t.F; }
     else if (n == "dGf") { src = t.dGf; count = (long)t.B * t.F; }
-    else if (n == "logp") { src = t.logp; count = M * t.C; }
+    else if (n == "logp") { src = t.logp; count = t.out_elems(); }
     else if (n == "t1.G") { src = t.t1.G; count = (long)t.B * 1024; }
     else if (n == "t2.G") { src = t.t2.G; count = (long)t.B * 1024; }
     else if (n == "t1.dG") { src = t.t1.dG; count = (long)t.B * 1024; }

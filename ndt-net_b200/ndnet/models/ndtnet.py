@@ -5,9 +5,9 @@ signatures, outputs and - so that reference checkpoints load unchanged - the sam
 `model(points, covariances)` - the call the reference's scripts make (tools/seg_viz.py:133, tools/train.py:69) - runs
 the network through libndnet_b200.so whenever the inputs are CUDA tensors: `forward` dispatches to `forward_b200`
 (tcgen05/TMA bf16 GEMMs with fused bias/BN/ReLU/max-pool epilogues in eval mode; the training kernels of train.cu, with
-gradients, when a segmentation module is in training mode).  `forward_torch` is the plain PyTorch fp32 definition of the
-same network: it is what the parity tests compare the CUDA path against, what CPU tensors get, and what a training-mode
-module without CUDA training kernels (the classification head) falls back to so that autograd keeps working.
+gradients, when the module is in training mode - segmentation and classification heads alike).  `forward_torch` is the
+plain PyTorch fp32 definition of the same network: it is what the parity tests compare the CUDA path against and what CPU
+tensors get.
 Set `module.b200 = False` (or NDNET_B200_FORWARD=torch in the environment) to force the PyTorch definition.
 """
 from __future__ import annotations
@@ -108,19 +108,17 @@ class _B200Mixin:
         return self.point_dim == 3 and self.feature_extractor.extra_dim == 9 and (self._kind == 0 or self.num_classes + 1 <= 32)
 
     def forward(self, points: torch.Tensor, covariances: torch.Tensor) -> torch.Tensor:
-        if _use_library(self, points, has_training_kernels=self._kind == 1):
+        if _use_library(self, points, has_training_kernels=True):
             return self.forward_b200(points, covariances)
         return self.forward_torch(points, covariances)
 
     def forward_b200(self, points: torch.Tensor, covariances: torch.Tensor) -> torch.Tensor:
         from ndnet_b200.model import B200Model
         if self.training:
-            if self._kind != 1:
-                raise RuntimeError("forward_b200 in training mode is built for NDTNetSegmentation only; call .eval() first")
-            from ndnet_b200.train import SegTrainer          # train-mode BatchNorm + gradients from train.cu
+            from ndnet_b200.train import NetTrainer          # train-mode BatchNorm + gradients from train.cu
             tr = getattr(self, "_b200_trainer", None)
             if tr is None or tr.device != points.device:
-                tr = SegTrainer(self, points.device, tf32=bool(getattr(self, "b200_tf32", False)))
+                tr = NetTrainer(self, points.device, tf32=bool(getattr(self, "b200_tf32", False)))
                 object.__setattr__(self, "_b200_trainer", tr)
             tr.overlap_allreduce = bool(getattr(self, "b200_overlap_allreduce", False))
             return tr(points, covariances)

@@ -1,8 +1,9 @@
 """Drop-in for the reference's ndnet/models/pointnet.py: PointNet without the covariance branch, for points of
 any width `point_dim` (e.g. the 12-D mean+covariance points of tools/train_pointnet.py).  Same classes,
 arguments, outputs and parameter names (reference: pointnet.py:65-98 PointNet, :137-149 classification head,
-:169-186 segmentation head).  `model(points)` runs the CUDA path (`forward_b200`) for CUDA tensors in eval mode and the
-plain PyTorch fp32 definition (`forward_torch`) otherwise - see ndtnet.py."""
+:169-186 segmentation head).  `model(points)` runs the CUDA path (`forward_b200`) for CUDA tensors - the folded inference
+kernels in eval mode, the training kernels of train.cu (with gradients) in training mode - and the plain PyTorch fp32
+definition (`forward_torch`) otherwise - see ndtnet.py."""
 from __future__ import annotations
 
 import torch
@@ -37,14 +38,20 @@ class _B200PointMixin:
         return 1 <= self.point_dim <= 16 and (self._kind == 2 or self.num_classes + 1 <= 32)
 
     def forward(self, points: torch.Tensor) -> torch.Tensor:
-        if _use_library(self, points, has_training_kernels=False):
+        if _use_library(self, points, has_training_kernels=True):
             return self.forward_b200(points)
         return self.forward_torch(points)
 
     def forward_b200(self, points: torch.Tensor) -> torch.Tensor:
         from ndnet_b200.model import B200Model
         if self.training:
-            raise RuntimeError("forward_b200 folds BatchNorm running statistics: call .eval() first")
+            from ndnet_b200.train import NetTrainer          # train-mode BatchNorm + gradients from train.cu
+            tr = getattr(self, "_b200_trainer", None)
+            if tr is None or tr.device != points.device:
+                tr = NetTrainer(self, points.device, tf32=bool(getattr(self, "b200_tf32", False)))
+                object.__setattr__(self, "_b200_trainer", tr)
+            tr.overlap_allreduce = bool(getattr(self, "b200_overlap_allreduce", False))
+            return tr(points)
         from .ndtnet import _state_stamp
         m = getattr(self, "_b200_model", None)
         stamp = _state_stamp(self)

@@ -1,11 +1,12 @@
-"""Training step of NDTNetSegmentation on the CUDA library (include/ndnet_b200.h (4)).
+"""Training step of the reference's networks on the CUDA library (include/ndnet_b200.h (4)).
 
-`SegTrainer(module)` binds an `ndnet.models.ndtnet.NDTNetSegmentation` (the reference's class layout and state_dict
-keys, /root/reference/ndnet/models/ndtnet.py:198-243) to `ndnet_b200_trainer_*`; calling it in place of
-`module(points, covs)` inside the reference's training loop (/root/reference/tools/train.py:66-76) gives the same
-train-mode forward (batch-statistics BatchNorm, running statistics updated in place) and, through one
-`torch.autograd.Function`, the gradients of every parameter from our kernels instead of torch autograd.  The loss and
-the optimizer stay ordinary torch code.
+`NetTrainer(module)` (alias `SegTrainer`) binds an `ndnet.models.ndtnet.NDTNetSegmentation` / `NDTNetClassification` or
+an `ndnet.models.pointnet.PointNetSegmentation` / `PointNetClassification` (the reference's class layouts and state_dict
+keys, /root/reference/ndnet/models/ndtnet.py:166-243, pointnet.py:137-214) to `ndnet_b200_trainer_*`; calling it in place
+of `module(points, covs)` / `module(points)` inside the reference's training loops (/root/reference/tools/train.py:66-76,
+tools/train_pointnet.py) gives the same train-mode forward (batch-statistics BatchNorm, running statistics updated in
+place) and, through one `torch.autograd.Function`, the gradients of every parameter from our kernels instead of torch
+autograd.  The loss and the optimizer stay ordinary torch code.
 
 Multi-GPU (one process per GPU, scans sharded over the ranks): the gradient average is the training path's only collective
 (SURVEY.md §8e).  `SegTrainer(..., overlap_allreduce=True)` (or `module.b200_overlap_allreduce = True`) launches it from
@@ -57,8 +58,12 @@ class SegTrainer:
         h = C.c_void_p()
         rc = self._L.ndnet_b200_trainer_create(dev.index or 0, n, c_names, c_shapes, c_nd, C.byref(h))
         if rc != 0:
-            raise RuntimeError(f"ndnet_b200_trainer_create failed ({rc}): not an NDTNetSegmentation state_dict?")
+            raise RuntimeError(f"ndnet_b200_trainer_create failed ({rc}): not an NDTNet / PointNet segmentation or classification state_dict?")
         self._h = h
+        kind, width, outs = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._L.ndnet_b200_trainer_info(h, C.byref(kind), C.byref(width), C.byref(outs))
+        self.kind, self.point_width = int(kind.value), int(width.value)
+        self.segmentation, self.takes_covariances = self.kind in (1, 3), self.kind in (0, 1)
         self.tf32 = bool(tf32)
         self._L.ndnet_b200_trainer_set_precision(h, int(self.tf32))
         self._L.ndnet_b200_trainer_set_graph(h, int(bool(graph)))
@@ -66,7 +71,7 @@ class SegTrainer:
         self._flat_elems = int(self._L.ndnet_b200_trainer_grad_layout(h, offs.ctypes.data, n))
         self._grad_off = [int(o) for o in offs]
         assert all((o >= 0) == (k in set(self.param_names)) for o, k in zip(self._grad_off, self.names)), "gradient layout mismatch"
-        self.num_out = int(module.num_classes) + 1
+        self.num_out = int(outs.value)              # segmentation: num_classes + 1 per row; classification: num_classes per cloud
         self.overlap_allreduce = bool(overlap_allreduce)
         self._buckets = []
         for i in range(int(self._L.ndnet_b200_trainer_num_buckets(h))):
@@ -88,13 +93,23 @@ class SegTrainer:
         if rc != 0:
             raise RuntimeError(f"{what} failed ({rc}): {self._L.ndnet_b200_trainer_last_error(self._h).decode()}")
 
-    def __call__(self, points: torch.Tensor, covariances: torch.Tensor) -> torch.Tensor:
-        """(B,N,3), (B,N,9) -> log-probabilities (B,N,num_classes+1), differentiable w.r.t. the module's parameters."""
+    def __call__(self, points: torch.Tensor, covariances: torch.Tensor | None = None) -> torch.Tensor:
+        """NDT networks: (B,N,3), (B,N,9); PointNet: (B,N,point_dim).  Returns what the module's forward returns -
+        segmentation: log-probabilities (B,N,num_classes+1); classification: probabilities (B,num_classes,1) -
+        differentiable w.r.t. the module's parameters."""
         if not self.module.training:
-            raise RuntimeError("SegTrainer normalises with batch statistics and updates the running ones: the module is in eval() "
-                               "mode - call module(points, covs) / forward_b200 (the folded inference kernels) instead")
-        feat = torch.cat((points, covariances), dim=2).float().contiguous()
-        return _SegTrainFn.apply(self, feat, *[p for _, p in self.module.named_parameters()])
+            raise RuntimeError("the trainer normalises with batch statistics and updates the running ones: the module is in eval() "
+                               "mode - call module(...) / forward_b200 (the folded inference kernels) instead")
+        if self.takes_covariances:
+            if covariances is None:
+                raise TypeError("this network takes (points, covariances)")
+            feat = torch.cat((points, covariances), dim=2).float().contiguous()
+        else:
+            feat = points.float().contiguous()
+        if feat.shape[2] != self.point_width:
+            raise RuntimeError(f"rows of width {feat.shape[2]} for a network built for {self.point_width}")
+        out = _SegTrainFn.apply(self, feat, *[p for _, p in self.module.named_parameters()])
+        return out if self.segmentation else out.unsqueeze(2)
 
     def debug_buffer(self, name: str) -> torch.Tensor:
         """Flat copy of an internal buffer of the last pass (test hook), e.g. "h3.dA", "t2.c1.Y", "t1.T"."""
@@ -114,6 +129,9 @@ class SegTrainer:
             pass
 
 
+NetTrainer = SegTrainer
+
+
 class _SegTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, trainer: SegTrainer, feat: torch.Tensor, *params):
@@ -122,7 +140,7 @@ class _SegTrainFn(torch.autograd.Function):
         for t in tensors:
             if not (t.is_cuda and t.is_contiguous()):
                 raise RuntimeError("parameters and buffers must be contiguous CUDA tensors")
-        out = torch.empty((B, N, trainer.num_out), dtype=torch.float32, device=feat.device)
+        out = torch.empty((B, N, trainer.num_out) if trainer.segmentation else (B, trainer.num_out), dtype=torch.float32, device=feat.device)
         stream = torch.cuda.current_stream(feat.device).cuda_stream
         rc = trainer._L.ndnet_b200_trainer_forward(trainer._h, feat.data_ptr(), B, N, trainer._ptr_array(tensors), out.data_ptr(),
                                                    int(trainer.module.training), stream)

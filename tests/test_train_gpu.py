@@ -416,3 +416,64 @@ def test_graph_replayed_pass_matches_the_layer_replay():
     tr2 = SegTrainer(_net(768, C, 9), graph=False)
     out2 = tr2(pts, cov)
     assert out2.shape == out.shape
+
+
+# ---- the other three networks of the reference: NDTNetClassification, PointNetClassification, PointNetSegmentation ----
+def _other_net(kind, point_dim, F, C, seed):
+    from ndnet.models.ndtnet import NDTNetClassification
+    from ndnet.models.pointnet import PointNetClassification, PointNetSegmentation
+    if kind == "ndt_cls":
+        net = NDTNetClassification(num_classes=C, feature_dim=F)
+    elif kind == "pn_cls":
+        net = PointNetClassification(point_dim=point_dim, num_classes=C, feature_dim=F)
+    else:
+        net = PointNetSegmentation(point_dim=point_dim, num_classes=C, feature_dim=F)
+    net.load_state_dict(deterministic_state_dict(net, seed))
+    return net.cuda().train()
+
+
+@pytest.mark.parametrize("kind,point_dim,B,N,F,C", [("ndt_cls", 3, 4, 200, 768, 40), ("ndt_cls", 3, 8, 77, 1024, 512),
+                                                    ("pn_cls", 3, 4, 200, 768, 40), ("pn_cls", 12, 6, 130, 768, 16),
+                                                    ("pn_seg", 3, 4, 200, 768, 28), ("pn_seg", 12, 5, 96, 1024, 16)])
+def test_the_other_heads_train_through_the_library(kind, point_dim, B, N, F, C):
+    """`model(...)` of a training-mode module on CUDA tensors (the call of tools/train.py:69 / train_pointnet.py) runs
+    train.cu for every network of the reference; outputs and gradients against fp64 autograd of the PyTorch definition,
+    same yardstick as the segmentation network above."""
+    from ndnet_b200 import _lib
+    net_a = _other_net(kind, point_dim, F, C, 5)
+    net_b = copy.deepcopy(net_a)
+    net_64 = copy.deepcopy(net_a).double()
+    p, c = inputs(B * 977 + N, B, N)
+    rng = np.random.default_rng(B * 31 + N)
+    if kind == "ndt_cls":
+        args = (torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda())
+    else:
+        x = np.concatenate([p, c], axis=2)[:, :, :point_dim] if point_dim <= 12 else None
+        args = (torch.from_numpy(np.ascontiguousarray(x)).cuda(),)
+    if kind == "pn_seg":
+        gt = np.zeros((B, N, C + 1), np.float32)
+        np.put_along_axis(gt, rng.integers(0, C + 1, (B, N))[..., None], 1.0, axis=2)
+        fn = lambda pred, gt: -(pred * gt).sum() / (B * N)                       # noqa: E731
+    else:
+        gt = np.zeros((B, C, 1), np.float32)
+        np.put_along_axis(gt, rng.integers(0, C, (B, 1))[..., None], 1.0, axis=1)
+        fn = lambda pred, gt: -(torch.log(pred + 1e-6) * gt).sum() / B           # noqa: E731
+    gt = torch.from_numpy(gt).cuda()
+    out_a = net_a.forward_torch(*args)
+    fn(out_a, gt).backward()
+    out_64 = net_64.forward_torch(*[a.double() for a in args])
+    fn(out_64, gt.double()).backward()
+    before = _lib.lib().ndnet_b200_launch_count()
+    out_b = net_b(*args)                                   # training mode + CUDA tensors -> the library
+    assert _lib.lib().ndnet_b200_launch_count() > before, "model(...) did not launch the library's kernels"
+    fn(out_b, gt).backward()
+    assert out_b.shape == out_a.shape
+    e32 = (out_a.double() - out_64).abs().max().item()
+    eb = (out_b.double() - out_64).abs().max().item()
+    assert eb <= max(3 * e32, 2e-4), (eb, e32)
+    _compare_grads(net_64, net_b)
+    for (name, ba), (_, bb) in zip(net_a.named_buffers(), net_b.named_buffers()):
+        if name.endswith("num_batches_tracked"):
+            assert int(ba) == int(bb), name
+        else:
+            assert torch.allclose(ba, bb, atol=1e-5, rtol=1e-4), name      # two fp32 summation orders of the batch statistics
