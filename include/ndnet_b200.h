@@ -128,6 +128,13 @@ int ndnet_b200_downsample_batch_host(ndnet_b200_ctx *ctx, const void *points, in
                                      float *out_feat, double *out_feat64, uint16_t *out_labels, int32_t *out_voxel,
                                      ndnet_b200_cloud_info *info, void *stream);
 
+/* One-hot rows <-> class tags on the device, for callers that hold labels the way the reference's Python entry does
+ * (ndnet/preprocessing/ndtnet_preprocessing.py:34 `argmax` of [rows, width] one-hot rows -> tag; :55-57 tag -> one-hot
+ * row).  onehot: device f32 [rows, width]; labels: device uint16 [rows].  The first maximal entry wins (numpy / torch
+ * argmax).  Enqueued on `stream`. */
+int ndnet_b200_onehot_to_labels(const float *onehot, long rows, int width, uint16_t *labels, void *stream);
+int ndnet_b200_labels_to_onehot(const uint16_t *labels, long rows, int width, float *onehot, void *stream);
+
 /* Debug/inspection: copy per-point voxel ids of the last batch ([B,N] int32, -1 = never voxelised) to a
  * device buffer.  Used by the parity tests ("voxel ids and per-voxel membership bit-exact"). */
 int ndnet_b200_keep_point_voxels(ndnet_b200_ctx *ctx, int enable);   /* off by default (costs 4 B/point of HBM writes) */

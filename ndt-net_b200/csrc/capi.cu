@@ -283,6 +283,41 @@ extern "C" int ndnet_b200_downsample_batch(ndnet_b200_ctx *c, const void *points
     return 0;
 }
 
+// ---- one-hot <-> class tag (ndtnet_preprocessing.py:34,55-57): the reference-facing call hands labels over as one-hot
+// rows; one thread per row, neighbouring threads read neighbouring rows (every 128-byte line is used in full from L1)
+__global__ void k_onehot_to_label(const float *__restrict__ onehot, long rows, int width, uint16_t *__restrict__ label) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float *o = onehot + r * width;
+    float best = o[0];
+    int bi = 0;
+    for (int c = 1; c < width; c++) { const float v = o[c]; if (v > best || (v != v && best == best)) { best = v; bi = c; } }   // first maximum, NaN counts as the largest (torch.argmax)
+    label[r] = (uint16_t)bi;
+}
+__global__ void k_label_to_onehot(const uint16_t *__restrict__ label, long rows, int width, float *__restrict__ onehot) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * width) return;
+    onehot[t] = (int)label[t / width] == (int)(t % width) ? 1.f : 0.f;
+}
+
+extern "C" int ndnet_b200_onehot_to_labels(const float *onehot, long rows, int width, uint16_t *labels, void *stream) {
+    if (!onehot || !labels || rows < 0 || width < 1 || width > 65536) return -200;
+    if (rows == 0) return 0;
+    ndt::count_launches(1);
+    k_onehot_to_label<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(onehot, rows, width, labels);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -100 - (int)e;
+}
+
+extern "C" int ndnet_b200_labels_to_onehot(const uint16_t *labels, long rows, int width, float *onehot, void *stream) {
+    if (!onehot || !labels || rows < 0 || width < 1) return -200;
+    if (rows == 0) return 0;
+    ndt::count_launches(1);
+    k_label_to_onehot<<<(unsigned)((rows * width + 255) / 256), 256, 0, (cudaStream_t)stream>>>(labels, rows, width, onehot);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -100 - (int)e;
+}
+
 extern "C" int ndnet_b200_downsample_batch_host(ndnet_b200_ctx *c, const void *points, int dtype, const uint16_t *labels,
                                                 int B, long N, int num_classes, long D, unsigned flags, float *out_feat,
                                                 double *out_feat64, uint16_t *out_labels, int32_t *out_voxel,

@@ -726,7 +726,11 @@ static void block_bwd(const Pass &ps, Block &k, const float *X, long ldx, float 
         train_count(), k_relu_bwd<<<cdiv(k.rows * out, 256), 256, 0, ps.st>>>(k.dA, k.A, k.rows * out);
     }
     float *dY = k.dA;
-    if (ps.Gr(k.lin.b)) {
+    if (ps.Gr(k.lin.b) && k.has_bn) {
+        // a bias in front of a train-mode BatchNorm has no effect on the output: its gradient, the column sums of the
+        // BatchNorm input gradient, is identically zero (autograd returns the rounding noise of that sum)
+        cudaMemsetAsync(ps.Gr(k.lin.b), 0, sizeof(float) * out, ps.st);
+    } else if (ps.Gr(k.lin.b)) {
         RedP r{};
         r.P = dY; r.ldp = out; r.rows = (int)k.rows; r.cols = out; r.s0 = k.red_bias;
         colred<RED_SUM>(ps.st, r, 1);

@@ -7,6 +7,7 @@ from typing import Tuple
 
 import torch
 
+from ndnet_b200 import _lib
 from ndnet_b200.engine import default_engine
 
 
@@ -32,16 +33,27 @@ def ndt_preprocessing(num_nds: int, points: torch.Tensor, classes: torch.Tensor 
     ncls = 0
     if classes is not None:
         ncls = int(num_classes)
-        # one-hot -> tag (:34); torch.argmax returns the first maximal index like numpy
-        labels = torch.argmax(classes.to(dev), dim=2).to(torch.int16)
+        # one-hot -> tag (:34, numpy argmax: the first maximal index), by the library's own kernel
+        onehot = classes.to(device=dev, dtype=torch.float32).contiguous()
+        if onehot.dim() != 3 or onehot.shape[:2] != pts.shape[:2]:
+            raise ValueError("classes must be shaped (batch, num_points, num_classes + 1)")
+        labels = torch.empty(onehot.shape[:2], dtype=torch.int16, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ndnet_b200_onehot_to_labels(onehot.data_ptr(), onehot.shape[0] * onehot.shape[1], onehot.shape[2],
+                                                       labels.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"ndnet_b200_onehot_to_labels failed ({rc})")
     eng = default_engine(dev)
     out = eng.downsample(pts, int(num_nds), labels, ncls, nan_to_num=True, want_info=False)
     points_new = out.feat[:, :, 0:3].contiguous()
     covs_new = out.feat[:, :, 3:12].contiguous()
     classes_new = None
     if classes is not None:
-        idx = out.labels.to(torch.int64) & 0xFFFF
-        classes_new = torch.zeros((pts.shape[0], int(num_nds), ncls + 1), dtype=torch.float32, device=dev)
-        classes_new.scatter_(2, idx.unsqueeze(-1), 1.0)   # (:55-57)
+        classes_new = torch.empty((pts.shape[0], int(num_nds), ncls + 1), dtype=torch.float32, device=dev)   # (:55-57)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ndnet_b200_labels_to_onehot(out.labels.data_ptr(), pts.shape[0] * int(num_nds), ncls + 1,
+                                                       classes_new.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"ndnet_b200_labels_to_onehot failed ({rc})")
         classes_new = classes_new.to(out_device)
     return points_new.to(out_device), covs_new.to(out_device), classes_new

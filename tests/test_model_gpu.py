@@ -77,14 +77,16 @@ def test_classification_forward_matches_torch_fp32(B, N):
     assert torch.allclose(got.sum(1), torch.ones_like(got[:, 0]), atol=1e-4)
 
 
-def test_forward_b200_refuses_training_mode_without_a_training_path():
-    """Eval-mode kernels fold the running statistics; only the segmentation module has training kernels (train.cu)."""
+def test_forward_b200_in_training_mode_is_the_training_path_for_every_head():
+    """Eval-mode kernels fold the running statistics; a training-mode module goes to the training kernels (train.cu),
+    classification heads included, and gets an autograd node."""
     net = NDTNetClassification()
     net.load_state_dict(deterministic_state_dict(net, 1))
     net = net.cuda().train()
     p, c = inputs(1, 2, 64)
-    with pytest.raises(RuntimeError):
-        net.forward_b200(torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda())
+    out = net.forward_b200(torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda())
+    assert out.shape == (2, net.num_classes, 1) and out.requires_grad
+    assert torch.allclose(out.sum(1), torch.ones_like(out.sum(1)), atol=1e-4)        # probabilities (ndtnet.py:194)
 
 
 def test_end_to_end_ndt_then_network():
@@ -253,8 +255,8 @@ def test_pointnet_forward_matches_torch_fp32():
 
 def test_model_call_runs_the_library_not_torch():
     """`model(points, covs)` - what tools/seg_viz.py:133 and tools/train.py:69 call - launches this library's kernels
-    (the launch counter moves) for CUDA inputs, in eval mode and in training mode of the segmentation module, and keeps
-    the PyTorch definition for CPU tensors, for opted-out modules and for training-mode heads without CUDA backward."""
+    (the launch counter moves) for CUDA inputs, in eval mode and in training mode (segmentation and classification heads),
+    and keeps the PyTorch definition for CPU tensors and for opted-out modules."""
     from ndnet_b200 import _lib
     L = _lib.lib()
     net = _seg()
@@ -285,5 +287,7 @@ def test_model_call_runs_the_library_not_torch():
     cls.load_state_dict(deterministic_state_dict(cls, 1))
     cls = cls.cuda().train()
     n0 = L.ndnet_b200_launch_count()
-    out = cls(pc * 0.02, cc * 0.02)                   # no CUDA backward for this head: PyTorch graph
-    assert L.ndnet_b200_launch_count() == n0 and out.requires_grad
+    out = cls(pc * 0.02, cc * 0.02)                   # the classification head trains through the library too
+    assert L.ndnet_b200_launch_count() - n0 >= 50 and out.requires_grad
+    out[:, 0].sum().backward()
+    assert all(q.grad is not None for q in cls.parameters())

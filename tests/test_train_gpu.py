@@ -221,7 +221,13 @@ class _Replay:
         dY = self.buf(name + ".dA", rows, out)
         self.close(dY, dY_want, name + ".dY", scale)
         self.close(self.grads[lin + ".weight"].view(out, -1), dY.t() @ X, lin + ".weight.grad")
-        self.close(self.grads[lin + ".bias"], dY.sum(0), lin + ".bias.grad", dY.abs().sum(0))   # sums to ~0 before a BatchNorm
+        if bn:
+            # a bias in front of a train-mode BatchNorm: the library writes the analytic gradient, exactly 0 (the columns of
+            # dY sum to zero by construction; autograd returns the rounding noise of that sum - the whole-graph tests
+            # above bound it against fp64 autograd)
+            assert float(self.grads[lin + ".bias"].abs().max()) == 0.0, lin + ".bias.grad"
+        else:
+            self.close(self.grads[lin + ".bias"], dY.sum(0), lin + ".bias.grad", dY.abs().sum(0))
         return dY, dY @ self.W(lin)
 
     def scatter_max(self, dG, A, C):
