@@ -76,6 +76,11 @@ typedef struct ndnet_b200_ctx ndnet_b200_ctx;
 #define NDNET_B200_NAN_TO_NUM 1u /* NaN/+-inf -> 0 in the f32 features (ndtnet_preprocessing.py:66-69) */
 #define NDNET_B200_LABELS_U8 2u  /* `labels` holds one BYTE per point instead of the reference's uint16 (num_classes <= 255):
                                     fewer bytes to move when the scans come from the host */
+#define NDNET_B200_TEXTBOOK_KL 4u /* the algorithm the reference's README documents (README.md:6) instead of what its compiled
+                                    core does: population covariances (off-diagonal sums divided once by the voxel's count,
+                                    nothing factorised in place), the Kullback-Leibler divergence of the two Gaussians
+                                    (mean term included), the LEAST divergent distributions removed first.  Default off:
+                                    parity with the reference is defined on the legacy behaviour. */
 
 /* Per-cloud record written by ndnet_b200_downsample_batch (device memory, one per cloud). */
 typedef struct ndnet_b200_cloud_info {

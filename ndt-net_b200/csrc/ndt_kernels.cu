@@ -758,13 +758,16 @@ __device__ __forceinline__ void stats_chain_fast(double x, double rh, double rl,
     e = x - mu;
     rcv = __shfl_sync(0xffffffffu, blend_bits(e, d, m_j0), src);
 }
+// kTextbook (NDNET_B200_TEXTBOOK_KL): the off-diagonal sum takes the products themselves and is divided by the final count
+// once, at the end - the population covariance - instead of the legacy per-step division by the running count.
+template <bool kTextbook>
 __device__ __forceinline__ void stats_tail_fast(double d, double e, double rcv, double rh, double rl, unsigned m_j2,
                                                 double &m2, double &c, unsigned &bad) {
     m2 = m2 + d * e;
     const double pr = blend_bits(d, e, m_j2) * rcv;
-    c = c + fma(pr, rh, pr * rl);
+    c = c + (kTextbook ? pr : fma(pr, rh, pr * rl));
     note_recip_unsafe(d, bad);
-    note_recip_unsafe(pr, bad);
+    if (!kTextbook) note_recip_unsafe(pr, bad);
 }
 
 // out-of-line IEEE divisions for operands outside the reciprocal form's proven range (tiny, huge, non-finite): rare
@@ -772,6 +775,7 @@ static __device__ __noinline__ double quotient_rare(double u, double cnt) { retu
 
 // Careful form: IEEE division wherever the reciprocal form is not proven, NaN -> 0 on the off-diagonal sum
 // (normal_distributions.c:98-100; a sum that is not NaN stays not NaN under a finite addend, so the fast form needs no test).
+template <bool kTextbook>
 __device__ __forceinline__ void stats_step_careful(double x, double rh, double rl, double cnt, int src, unsigned m_j0, unsigned m_j2,
                                                    double &mu, double &m2, double &c) {
     const double d = x - mu;
@@ -780,18 +784,20 @@ __device__ __forceinline__ void stats_step_careful(double x, double rh, double r
     m2 = m2 + d * e;
     const double rcv = __shfl_sync(0xffffffffu, blend_bits(e, d, m_j0), src);
     const double pr = blend_bits(d, e, m_j2) * rcv;
-    c = c + (recip_ok(pr) ? fma(pr, rh, pr * rl) : quotient_rare(pr, cnt));
+    c = c + (kTextbook ? pr : (recip_ok(pr) ? fma(pr, rh, pr * rl) : quotient_rare(pr, cnt)));
     if (exp_all_ones(c) && c != c) c = 0.0;
 }
 
 // a voxel's last point was just added: lane j < 3 writes its mean, its variance m2 / n (normal_distributions.c:86-89, NaN -> 0)
 // and its off-diagonal sum (mirrored); the label lane writes the vote (most frequent class, lowest index on ties, 0 when
 // nothing was counted, :107-121)
+template <bool kTextbook>
 __device__ __forceinline__ void stats_finish(double *__restrict__ mean, double *__restrict__ cov, uint16_t *__restrict__ cls, size_t slot,
                                              int j, int q, unsigned n, double mu, double m2, double c, const unsigned *s_hist, int vote_bins) {
     if (j < 3) {
         double var = m2 / (double)n;
         if (var != var) var = 0.0;
+        if (kTextbook) { c = c / (double)n; if (c != c) c = 0.0; }
         mean[slot * 3 + j] = mu;
         double *co = cov + slot * 9;
         co[j * 4] = var;
@@ -812,7 +818,7 @@ __device__ __forceinline__ void stats_finish(double *__restrict__ mean, double *
 // step's operands with two shared-memory loads.  A finished voxel's lanes keep computing on whatever follows in the ring
 // (finite numbers; their results are not used).  vote_bins > 0: the label vote is taken here too (shared-memory counters,
 // <= kSmemLabelBins classes).
-template <typename T>
+template <typename T, bool kTextbook>
 __global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(const CloudState *__restrict__ states, unsigned vcap, long N,
                                               const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                               const unsigned *__restrict__ vox_order, const double2 *__restrict__ recip,
@@ -887,16 +893,16 @@ __global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(const CloudSta
                     const double2 r = rb[i];
                     double d, e, rcv;
                     stats_chain_fast(record_coord<T>(raw, j == 3), r.x, r.y, src, m_j0, mu, d, e, rcv);
-                    if (i > 0) stats_tail_fast(pd, pe, prcv, prh, prl, m_j2, m2, c, bad);
+                    if (i > 0) stats_tail_fast<kTextbook>(pd, pe, prcv, prh, prl, m_j2, m2, c, bad);
                     atomicAdd(my_hist + min(record_label<T>(raw), my_bins) * my_stride, 1u);
                     pd = d; pe = e; prcv = rcv; prh = r.x; prl = r.y;
                 }
-                stats_tail_fast(pd, pe, prcv, prh, prl, m_j2, m2, c, bad);
+                stats_tail_fast<kTextbook>(pd, pe, prcv, prh, prl, m_j2, m2, c, bad);
                 if (__any_sync(0xffffffffu, bad != 0u)) {      // rare: redo the block (its operands are still in the ring)
                     mu = mu0; m2 = m20; c = c0;
                     for (int i = 0; i < kStatsUnroll; i++) {
                         const double2 r = rb[i];
-                        stats_step_careful(record_coord<T>(xb[i * kSortedStride], j == 3), r.x, r.y, (double)(k0 + i + 1), src, m_j0, m_j2, mu, m2, c);
+                        stats_step_careful<kTextbook>(record_coord<T>(xb[i * kSortedStride], j == 3), r.x, r.y, (double)(k0 + i + 1), src, m_j0, m_j2, mu, m2, c);
                     }
                 }
             } else {
@@ -909,16 +915,16 @@ __global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(const CloudSta
                     const double2 r = rb[i];
                     double d, e, rcv;
                     stats_chain_fast(record_coord<T>(raw, j == 3), r.x, r.y, src, m_j0, mu, d, e, rcv);
-                    stats_tail_fast(d, e, rcv, r.x, r.y, m_j2, m2, c, bad);
+                    stats_tail_fast<kTextbook>(d, e, rcv, r.x, r.y, m_j2, m2, c, bad);
                     atomicAdd(my_hist + min(record_label<T>(raw), my_bins) * my_stride, 1u);   // (after its end a voxel's counters are dead)
-                    if (k0 + i + 1 == n) stats_finish(mean, cov, cls, (size_t)b * vcap + v, j, q, n, mu, m2, c, sm.hist, vote_bins);
+                    if (k0 + i + 1 == n) stats_finish<kTextbook>(mean, cov, cls, (size_t)b * vcap + v, j, q, n, mu, m2, c, sm.hist, vote_bins);
                 }
                 if (__any_sync(0xffffffffu, bad != 0u)) {      // rare: again with the careful form (the votes are in already)
                     mu = mu0; m2 = m20; c = c0;
                     for (int i = 0; i < kStatsUnroll; i++) {
                         const double2 r = rb[i];
-                        stats_step_careful(record_coord<T>(xb[i * kSortedStride], j == 3), r.x, r.y, (double)(k0 + i + 1), src, m_j0, m_j2, mu, m2, c);
-                        if (k0 + i + 1 == n) stats_finish(mean, cov, cls, (size_t)b * vcap + v, j, q, n, mu, m2, c, sm.hist, 0);
+                        stats_step_careful<kTextbook>(record_coord<T>(xb[i * kSortedStride], j == 3), r.x, r.y, (double)(k0 + i + 1), src, m_j0, m_j2, mu, m2, c);
+                        if (k0 + i + 1 == n) stats_finish<kTextbook>(mean, cov, cls, (size_t)b * vcap + v, j, q, n, mu, m2, c, sm.hist, 0);
                     }
                 }
             }
@@ -935,7 +941,7 @@ __global__ void __launch_bounds__(32, NDT_STATS_MIN_CTAS) k_stats(const CloudSta
 // of a warp is at the same count; see div_by_count for why the reciprocal form is the correctly rounded quotient).
 // vote_bins > 0: the label vote (normal_distributions.c:107-121) is taken here too, in per-thread 16-bit counters.
 // grid (ceil(vcap/128), B), block 128, dynamic smem vote_bins * 128 * 2 bytes.
-template <typename T>
+template <typename T, bool kTextbook>
 __global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restrict__ states, unsigned vcap, long N,
                                                      const T *__restrict__ sorted, const unsigned *__restrict__ vox_start,
                                                      const unsigned *__restrict__ vox_order,
@@ -982,6 +988,8 @@ __global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restric
         const double rh = r.x, rl = r.y;
         // RN(u / c): reciprocal form inside its proven range, IEEE division otherwise
 #define QDIV(u) (recip_ok(u) ? fma((u), rh, (u) * rl) : (u) / (double)(k + 1))
+        // off-diagonal addend: the legacy quotient by the running count, or (textbook mode) the product itself
+#define CDIV(u) (kTextbook ? (u) : QDIV(u))
         // j = 0
         const double d0 = x0 - mu0;
         const double o0 = mu0;
@@ -989,18 +997,19 @@ __global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restric
         const double e0 = x0 - mu0;
         m20 += (x0 - o0) * e0;
         const double f1 = x1 - mu1, f2 = x2 - mu2;                                                  // mu1, mu2 still old
-        { const double u = e0 * f1; c01 += QDIV(u); if (exp_all_ones(c01) && c01 != c01) c01 = 0.0; }
-        { const double u = e0 * f2; c02 += QDIV(u); if (exp_all_ones(c02) && c02 != c02) c02 = 0.0; }
+        { const double u = e0 * f1; c01 += CDIV(u); if (exp_all_ones(c01) && c01 != c01) c01 = 0.0; }
+        { const double u = e0 * f2; c02 += CDIV(u); if (exp_all_ones(c02) && c02 != c02) c02 = 0.0; }
         // j = 1
         const double o1 = mu1;
         mu1 = mu1 + QDIV(f1);
         const double e1 = x1 - mu1;
         m21 += (x1 - o1) * e1;
-        { const double u = e1 * f2; c12 += QDIV(u); if (exp_all_ones(c12) && c12 != c12) c12 = 0.0; }
+        { const double u = e1 * f2; c12 += CDIV(u); if (exp_all_ones(c12) && c12 != c12) c12 = 0.0; }
         // j = 2
         const double o2 = mu2;
         mu2 = mu2 + QDIV(f2);
         m22 += (x2 - o2) * (x2 - mu2);
+#undef CDIV
 #undef QDIV
     }
     const double cn = (double)n;
@@ -1008,6 +1017,12 @@ __global__ void __launch_bounds__(128) k_stats_light(const CloudState *__restric
     if (v0 != v0) v0 = 0.0;
     if (v1 != v1) v1 = 0.0;
     if (v2 != v2) v2 = 0.0;
+    if (kTextbook) {
+        c01 = c01 / cn; c02 = c02 / cn; c12 = c12 / cn;
+        if (c01 != c01) c01 = 0.0;
+        if (c02 != c02) c02 = 0.0;
+        if (c12 != c12) c12 = 0.0;
+    }
     double *mo = mean + ((size_t)b * vcap + v) * 3;
     mo[0] = mu0; mo[1] = mu1; mo[2] = mu2;
     double *co = cov + ((size_t)b * vcap + v) * 9;
@@ -1170,6 +1185,74 @@ __global__ void __launch_bounds__(64) k_kl(const CloudState *__restrict__ states
     for (int i = 0; i < 9; i++) cf[i] = A[i];
 }
 
+// K8t  textbook mode (NDNET_B200_TEXTBOOK_KL; the algorithm the reference's README describes, README.md:6): the
+// Kullback-Leibler divergence of the two Gaussians themselves,
+//   KL(p || q) = 1/2 [ tr(Sq^-1 Sp) + (mq - mp)^T Sq^-1 (mq - mp) - 3 + ln(det Sq / det Sp) ],
+// on the population covariances (nothing is factorised in place, no call sees another call's leftovers), for every
+// occupied voxel p and each of its occupied 6-neighbours q in enum order.  Pairs with fewer than two points on either
+// side, a covariance that is not positive definite (det <= 0 or a non-positive leading minor) or a non-finite result
+// get no entry.  cov_final = the covariance itself.  grid (ceil(vcap/64), B), block 64.
+__device__ __forceinline__ bool spd_det_inv(const double S[9], double &det, double inv[9]) {
+    // symmetric 3x3: cofactors, determinant by the first row, leading minors for positive definiteness
+    const double a = S[0], b = S[1], c = S[2], d = S[4], e = S[5], f = S[8];
+    const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+    det = a * c00 + b * c01 + c * c02;
+    if (!(a > 0.0) || !(a * d - b * b > 0.0) || !(det > 0.0)) return false;
+    const double r = 1.0 / det;
+    inv[0] = c00 * r; inv[1] = c01 * r; inv[2] = c02 * r;
+    inv[3] = inv[1]; inv[4] = (a * f - c * c) * r; inv[5] = (b * c - a * e) * r;
+    inv[6] = inv[2]; inv[7] = inv[5]; inv[8] = (a * d - b * b) * r;
+    return true;
+}
+
+__global__ void __launch_bounds__(64) k_kl_textbook(const CloudState *__restrict__ states, unsigned vcap,
+                                                    const uint2 *__restrict__ bitmap, size_t bitmap_stride,
+                                                    const unsigned *__restrict__ vox_cell, const unsigned *__restrict__ vox_n,
+                                                    const double *__restrict__ mean, const double *__restrict__ cov,
+                                                    double *__restrict__ cov_final, double *__restrict__ kl_div,
+                                                    unsigned char *__restrict__ kl_flag) {
+    const int b = blockIdx.y;
+    const CloudState &s = states[b];
+    if (s.status != 0) return;
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= s.V) return;
+    const uint2 *bm = bitmap + (size_t)b * bitmap_stride;
+    const unsigned *vn = vox_n + (size_t)b * vcap;
+    const double *cv = cov + (size_t)b * vcap * 9, *mu = mean + (size_t)b * vcap * 3;
+    const int lx = s.len[0], ly = s.len[1], lz = s.len[2];
+    const unsigned cell = vox_cell[(size_t)b * vcap + v];
+    double P[9], Pinv[9], pdet;
+#pragma unroll
+    for (int i = 0; i < 9; i++) P[i] = cv[(size_t)v * 9 + i];
+    double *cf = cov_final + ((size_t)b * vcap + v) * 9;
+#pragma unroll
+    for (int i = 0; i < 9; i++) cf[i] = P[i];
+    const bool p_ok = vn[v] > 1 && spd_det_inv(P, pdet, Pinv);
+    double *out_div = kl_div + ((size_t)b * vcap + v) * kDirs;
+    unsigned char *out_flag = kl_flag + ((size_t)b * vcap + v) * kDirs;
+#pragma unroll 1
+    for (int d = 0; d < kDirs; d++) {
+        out_flag[d] = 0;
+        const int q = neighbor_slot(bm, cell, lx, ly, lz, d);
+        if (q < 0 || !p_ok || vn[q] <= 1) continue;
+        double Q[9], Qinv[9], qdet;
+#pragma unroll
+        for (int i = 0; i < 9; i++) Q[i] = cv[(size_t)q * 9 + i];
+        if (!spd_det_inv(Q, qdet, Qinv)) continue;
+        double tr = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) tr += Qinv[i * 3 + k] * P[k * 3 + i];
+        const double d0 = mu[(size_t)q * 3 + 0] - mu[(size_t)v * 3 + 0], d1 = mu[(size_t)q * 3 + 1] - mu[(size_t)v * 3 + 1],
+                     d2 = mu[(size_t)q * 3 + 2] - mu[(size_t)v * 3 + 2];
+        const double maha = d0 * (Qinv[0] * d0 + Qinv[1] * d1 + Qinv[2] * d2) + d1 * (Qinv[3] * d0 + Qinv[4] * d1 + Qinv[5] * d2) +
+                            d2 * (Qinv[6] * d0 + Qinv[7] * d1 + Qinv[8] * d2);
+        const double div = 0.5 * (tr + maha - 3.0 + log(qdet / pdet));
+        if (isfinite(div)) { out_div[d] = div; out_flag[d] = 1; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K9  divergence list: compaction in insertion order, NaN rule (A14), stable descending sort
 // (kullback_leibler.c:181-195), prune walk (ndt.c:45-72) and ascending compaction (ndt.c:75-117).
@@ -1273,7 +1356,9 @@ __global__ void __launch_bounds__(kSelectThreads, 3) k_select(CloudState *__rest
             const unsigned pos = s_carry + pos_in;
             CHK(pos < kcap, 1);
             if (pos < kcap) {
-                gk[pos] = desc_key(isn ? excl : d);
+                // legacy: descending divergence (the list head, removed first, holds the LARGEST divergences - what the
+                // compiled reference does); textbook: ascending (the most redundant distributions go first, README.md:6)
+                gk[pos] = (flags & 4u) ? ~desc_key(d) : desc_key(isn ? excl : d);
                 gs[pos] = q;
             }
         }
@@ -1329,7 +1414,7 @@ __global__ void __launch_bounds__(kSelectThreads, 3) k_select(CloudState *__rest
         const bool first = i < K && firstpos[seq[i] / kDirs] == i;
         unsigned total;
         const unsigned r = s_carry + block_scan_step(first ? 1u : 0u, s_warp, total);
-        if (first && r < to_remove && (unsigned long)i + r < (unsigned long)K) {
+        if (first && r < to_remove && ((flags & 4u) || (unsigned long)i + r < (unsigned long)K)) {
             removed[seq[i] / kDirs] = 1;
             walk_local = i + 1;
         }
@@ -1484,6 +1569,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     const unsigned vcap = w.vcap;
     const int ntiles = (int)((N + kRankTile - 1) / kRankTile);
     const int nbins = num_classes + 1;
+    const bool textbook = (flags & 4u) != 0;          // NDNET_B200_TEXTBOOK_KL
     StageTimer &tm = w.timer;
     if (tm.enabled && !tm.created) { for (auto &e : tm.ev) cudaEventCreate(&e); tm.created = true; }
     tm.mark(ST_LIMITS, st);
@@ -1541,11 +1627,17 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         // label vote: taken inside the statistics kernels from the label lane of the records they read anyway when the
         // class count fits their shared-memory counters; wide label sets were counted by k_scatter's global atomics
         const int vote_bins = labels && !wide_labels ? nbins : 0;
-        k_stats<T><<<dim3(B, (max_heavy + kStatsVoxelsPerWarp - 1) / kStatsVoxelsPerWarp), 32, 0, st>>>(
-            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.recip, w.mean, w.cov, w.cls, vote_bins);
-        DBG("k_stats");
-        k_stats_light<T><<<dim3((vcap + 127) / 128, B), 128, (size_t)vote_bins * 128 * sizeof(unsigned short), w.side>>>(
-            w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
+        const dim3 heavy_grid(B, (max_heavy + kStatsVoxelsPerWarp - 1) / kStatsVoxelsPerWarp), light_grid((vcap + 127) / 128, B);
+        const size_t light_smem = (size_t)vote_bins * 128 * sizeof(unsigned short);
+        if (textbook) {
+            k_stats<T, true><<<heavy_grid, 32, 0, st>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.recip, w.mean, w.cov, w.cls, vote_bins);
+            DBG("k_stats");
+            k_stats_light<T, true><<<light_grid, 128, light_smem, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
+        } else {
+            k_stats<T, false><<<heavy_grid, 32, 0, st>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.recip, w.mean, w.cov, w.cls, vote_bins);
+            DBG("k_stats");
+            k_stats_light<T, false><<<light_grid, 128, light_smem, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.vox_order, w.mean, w.cov, w.cls, vote_bins);
+        }
         if (wide_labels) {
             k_votes<T><<<dim3(B, (vcap + 3) / 4), 128, 0, w.side>>>(w.states, vcap, N, (const T *)w.sorted, w.vox_start, w.hist, nbins, w.cls);
         }
@@ -1554,8 +1646,12 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         DBG("k_stats_light/k_votes");
     }
     tm.mark(ST_KL, st);
-    k_kl<<<dim3((vcap + 63) / 64, B), 64, 0, st>>>(w.states, vcap, w.bitmap, w.bitmap_stride, w.vox_cell, w.vox_n, w.cov,
-                                                  w.cov_final, w.kl_div, w.kl_flag);
+    if (textbook)
+        k_kl_textbook<<<dim3((vcap + 63) / 64, B), 64, 0, st>>>(w.states, vcap, w.bitmap, w.bitmap_stride, w.vox_cell, w.vox_n, w.mean, w.cov,
+                                                               w.cov_final, w.kl_div, w.kl_flag);
+    else
+        k_kl<<<dim3((vcap + 63) / 64, B), 64, 0, st>>>(w.states, vcap, w.bitmap, w.bitmap_stride, w.vox_cell, w.vox_n, w.cov,
+                                                      w.cov_final, w.kl_div, w.kl_flag);
     DBG("k_kl");
     tm.mark(ST_SELECT, st);
     {

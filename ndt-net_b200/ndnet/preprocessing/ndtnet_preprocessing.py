@@ -3,6 +3,7 @@ arguments and return values, but the per-cloud Python loop (GPU->CPU->C->CPU->GP
 batched call into libndnet_b200.so on the current CUDA stream."""
 from __future__ import annotations
 
+import os
 from typing import Tuple
 
 import torch
@@ -11,9 +12,11 @@ from ndnet_b200 import _lib
 from ndnet_b200.engine import default_engine
 
 
-def ndt_preprocessing(num_nds: int, points: torch.Tensor, classes: torch.Tensor = None, num_classes: int = None
-                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+def ndt_preprocessing(num_nds: int, points: torch.Tensor, classes: torch.Tensor = None, num_classes: int = None,
+                      textbook_kl: bool = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """points: (batch, num_points, 3) float tensor; classes: (batch, num_points, num_classes+1) one-hot or None.
+    textbook_kl (not in the reference's signature; default: environment NDNET_B200_TEXTBOOK_KL=1, else off) selects the
+    algorithm the reference's README documents instead of the behaviour of its compiled core.
 
     Returns (points_new [B,num_nds,3], covs_new [B,num_nds,9], classes_new [B,num_nds,num_classes+1] or None),
     float32 on points.device, NaN/inf replaced by 0 (ndtnet_preprocessing.py:66-69)."""
@@ -44,7 +47,9 @@ def ndt_preprocessing(num_nds: int, points: torch.Tensor, classes: torch.Tensor 
         if rc != 0:
             raise RuntimeError(f"ndnet_b200_onehot_to_labels failed ({rc})")
     eng = default_engine(dev)
-    out = eng.downsample(pts, int(num_nds), labels, ncls, nan_to_num=True, want_info=False)
+    if textbook_kl is None:
+        textbook_kl = os.environ.get("NDNET_B200_TEXTBOOK_KL", "") == "1"
+    out = eng.downsample(pts, int(num_nds), labels, ncls, nan_to_num=True, want_info=False, textbook_kl=bool(textbook_kl))
     points_new = out.feat[:, :, 0:3].contiguous()
     covs_new = out.feat[:, :, 3:12].contiguous()
     classes_new = None

@@ -24,6 +24,7 @@ assert INFO_DTYPE.itemsize == 128
 F32, F64 = 0, 1
 NAN_TO_NUM = 1
 LABELS_U8 = 2
+TEXTBOOK_KL = 4
 
 _lib = None
 

@@ -56,8 +56,10 @@ class NdtEngine:
 
     def downsample(self, points: torch.Tensor, num_desired: int, labels: torch.Tensor | None = None,
                    num_classes: int = 0, nan_to_num: bool = True, want_f64: bool = False, want_voxel: bool = False,
-                   want_info: bool = True) -> NdtBatch:
-        """points: CUDA tensor [B, N, 3] f32 or f64; labels: CUDA int16/uint16 [B, N] or None."""
+                   want_info: bool = True, textbook_kl: bool = False) -> NdtBatch:
+        """points: CUDA tensor [B, N, 3] f32 or f64; labels: CUDA int16/uint16 [B, N] or None.
+        textbook_kl: the README's algorithm (true covariances and KL, least divergent removed first) instead of the
+        compiled reference's behaviour (include/ndnet_b200.h NDNET_B200_TEXTBOOK_KL)."""
         assert points.is_cuda and points.dim() == 3 and points.shape[2] == 3
         assert points.dtype in (torch.float32, torch.float64)
         points = points.contiguous()
@@ -79,7 +81,7 @@ class NdtEngine:
         with torch.cuda.device(dev):
             rc = self._L.ndnet_b200_downsample_batch(
                 self._h, points.data_ptr(), _lib.F32 if points.dtype == torch.float32 else _lib.F64, lab_ptr, B, N,
-                int(num_classes), D, _lib.NAN_TO_NUM if nan_to_num else 0, feat.data_ptr(),
+                int(num_classes), D, (_lib.NAN_TO_NUM if nan_to_num else 0) | (_lib.TEXTBOOK_KL if textbook_kl else 0), feat.data_ptr(),
                 feat64.data_ptr() if want_f64 else None, out_lab.data_ptr() if out_lab is not None else None,
                 voxel.data_ptr() if want_voxel else None, info_dev.data_ptr() if want_info else None, stream)
         self._check(rc, "ndnet_b200_downsample_batch")
