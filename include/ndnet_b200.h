@@ -145,7 +145,10 @@ int ndnet_b200_labels_to_onehot(const uint16_t *labels, long rows, int width, fl
 int ndnet_b200_keep_point_voxels(ndnet_b200_ctx *ctx, int enable);   /* off by default (costs 4 B/point of HBM writes) */
 int ndnet_b200_last_point_voxels(ndnet_b200_ctx *ctx, int32_t *out_dev, void *stream);
 /* Debug/inspection: the pre-prune divergence list of cloud b of the last batch, in list order.
- * Host buffers of capacity `cap`; returns the number of entries or a negative error. */
+ * Host buffers of capacity `cap`; returns the number of entries or a negative error.  The batched calls only sort the head
+ * of the list that the prune walk can reach; ndnet_b200_keep_kl_list(ctx, 1) BEFORE the batch makes them sort and keep all
+ * of it (the legacy ndt_downsample always does: its handles carry the list for prune_nds). */
+int ndnet_b200_keep_kl_list(ndnet_b200_ctx *ctx, int enable);
 long ndnet_b200_last_kl_list(ndnet_b200_ctx *ctx, int b, double *div, int32_t *p_voxel, int32_t *q_voxel, long cap);
 
 /* Instrumentation for bench.py.  launch_count: kernels launched by this library since it was loaded.

@@ -90,14 +90,14 @@ static cudaError_t alloc(T *&p, size_t count) {
 // Frees the device arrays and resets every capacity to zero (a later reserve() starts from scratch); the side
 // stream and its events survive so that a workspace can grow without re-creating them (destroy() ends them).
 void Workspace::release() {
-    const bool keep = keep_point_voxels;
+    const bool keep = keep_point_voxels, keep_list = keep_kl_list;
     cudaStream_t keep_side = side; cudaEvent_t keep_fork = ev_fork, keep_join = ev_join;
     const StageTimer keep_timer = timer;
     void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, vox_order, slot_rank, tile_cnt, hist, point_voxel, sorted,
                     mean, cov, cov_final, cls, kl_div, kl_flag, key, seq, firstpos, removed, list_div, list_seq, recip};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = Workspace();
-    keep_point_voxels = keep;
+    keep_point_voxels = keep; keep_kl_list = keep_list;
     side = keep_side; ev_fork = keep_fork; ev_join = keep_join;
     timer = keep_timer;
 }
@@ -502,8 +502,15 @@ extern "C" int ndnet_b200_last_point_voxels(ndnet_b200_ctx *c, int32_t *out_dev,
     return e == cudaSuccess ? 0 : fail(c, e, "last_point_voxels");
 }
 
+extern "C" int ndnet_b200_keep_kl_list(ndnet_b200_ctx *c, int enable) {
+    if (!c) return -200;
+    c->ws.keep_kl_list = enable != 0;
+    return 0;
+}
+
 extern "C" long ndnet_b200_last_kl_list(ndnet_b200_ctx *c, int b, double *div, int32_t *p_voxel, int32_t *q_voxel, long cap) {
     if (!c || b < 0 || b >= c->ws.last_B) return -200;
+    if (!c->ws.keep_kl_list) { c->err = "enable ndnet_b200_keep_kl_list before the batch"; return -204; }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return fail(c, e, "synchronise");
     ndt::CloudSummary cs;
@@ -562,6 +569,7 @@ ndnet_b200_ctx *default_ctx() {
         int dev = 0;
         if (const char *e = getenv("NDNET_B200_DEVICE")) dev = atoi(e);
         if (ndnet_b200_create(&g_ctx, dev) != 0) g_ctx = nullptr;
+        else g_ctx->ws.keep_kl_list = true;           // the legacy handles carry the whole sorted list (prune() walks on from it)
     }
     return g_ctx;
 }

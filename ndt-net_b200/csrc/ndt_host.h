@@ -49,6 +49,7 @@ struct Workspace {
     int *point_voxel = nullptr;
     void *sorted = nullptr;
     bool keep_point_voxels = false;   // inspection only: k_rank also records every point's voxel id
+    bool keep_kl_list = false;        // the whole sorted divergence list of every cloud stays behind (legacy handles, inspection)
     double *mean = nullptr, *cov = nullptr, *cov_final = nullptr;
     double2 *recip = nullptr;         // {RN(1/c), residual} for c = 1..N_cap (k_stats' divisions by the running count)
     uint16_t *cls = nullptr;

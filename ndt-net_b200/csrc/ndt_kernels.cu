@@ -1279,7 +1279,39 @@ __device__ __forceinline__ unsigned block_scan_step(unsigned val, unsigned *s_wa
     return woff + inc - val;
 }
 
-__global__ void __launch_bounds__(kSelectThreads, 3) k_select(CloudState *__restrict__ states, unsigned vcap, long num_desired,
+// smallest bin whose inclusive prefix count reaches `target` (>= 1), and the count in front of it.  Every thread calls it.
+__device__ __forceinline__ void find_rank_bin(const unsigned *hist, int nbins, unsigned target, unsigned *s_warp, unsigned *s_out,
+                                              unsigned &bin, unsigned &before) {
+    const int per = (nbins + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int b0 = (int)threadIdx.x * per;
+    unsigned sum = 0;
+    for (int k = 0; k < per; k++) if (b0 + k < nbins) sum += hist[b0 + k];
+    unsigned total;
+    const unsigned excl = block_scan_step(sum, s_warp, total);
+    if (threadIdx.x == 0) { s_out[0] = (unsigned)nbins - 1u; s_out[1] = total - hist[nbins - 1]; }     // target beyond the total: last bin
+    __syncthreads();
+    if (excl < target && target <= excl + sum) {
+        unsigned run = excl;
+        for (int k = 0; k < per; k++) {
+            const unsigned c = hist[b0 + k];
+            if (run + c >= target) { s_out[0] = (unsigned)(b0 + k); s_out[1] = run; break; }
+            run += c;
+        }
+    }
+    __syncthreads();
+    bin = s_out[0]; before = s_out[1];
+    __syncthreads();
+}
+
+constexpr int kSelectPartialCap = 2048;         // candidates the partial selection sorts in shared memory
+constexpr int kSelectPartialThreads = 256;
+
+// kPartial: only the head of the sorted list is produced - the walk removes the first V - D distinct p's and every p owns at
+// most six entries, so it never looks past entry 6 (V - D); those entries are found by a two-level radix selection on the
+// keys (12 + 11 bits) and sorted alone (<= 2048 of the ~6400 entries of a scan).  The full list (legacy handles, inspection)
+// is kept by the kPartial = false instantiation.
+template <int kThreads, bool kPartial>
+__global__ void __launch_bounds__(kThreads, kPartial ? 5 : 3) k_select(CloudState *__restrict__ states, unsigned vcap, long num_desired,
                                                  const unsigned *__restrict__ vox_cell, const unsigned *__restrict__ vox_n,
                                                  const double *__restrict__ mean, const double *__restrict__ cov_final,
                                                  const uint16_t *__restrict__ cls, int has_labels,
@@ -1368,14 +1400,60 @@ __global__ void __launch_bounds__(kSelectThreads, 3) k_select(CloudState *__rest
     }
     const unsigned K = s_carry;
     CHK(K <= kcap && V <= vcap, 2);
-    // ---- 2. stable sort (key ascending == divergence descending, then insertion sequence ascending)
-    unsigned P = 1; while (P < K) P <<= 1;
+    // ---- 2. stable sort (key ascending == divergence descending, then insertion sequence ascending) of the first Ks
+    //         entries of that order
+    unsigned Ks = K;
+    bool selected = false;
+    if (kPartial) {
+        __shared__ unsigned s_sel[4];
+        const unsigned long need64 = 6ul * (unsigned long)(V - (unsigned)D);
+        const unsigned need = need64 < (unsigned long)K ? (unsigned)need64 : K;
+        if (need == 0) Ks = 0;
+        else if (need < K) {
+            unsigned *hist = (unsigned *)s_dyn;                               // 4096 bins, then 2048 bins
+            for (int i = tid; i < 4096; i += blockDim.x) hist[i] = 0u;
+            __syncthreads();
+            for (unsigned i = tid; i < K; i += blockDim.x) atomicAdd(&hist[(unsigned)(gk[i] >> 52)], 1u);
+            __syncthreads();
+            unsigned binA, beforeA;
+            find_rank_bin(hist, 4096, need, s_warp, s_sel, binA, beforeA);
+            for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0u;
+            __syncthreads();
+            for (unsigned i = tid; i < K; i += blockDim.x) {
+                const unsigned long long k = gk[i];
+                if ((unsigned)(k >> 52) == binA) atomicAdd(&hist[(unsigned)(k >> 41) & 0x7ffu], 1u);
+            }
+            __syncthreads();
+            unsigned binB, beforeB;
+            find_rank_bin(hist, 2048, need - beforeA, s_warp, s_sel, binB, beforeB);
+            const unsigned cand = beforeA + beforeB + hist[binB];
+            __syncthreads();
+            if (cand <= (unsigned)kSelectPartialCap && (int)cand <= smem_cap) {
+                // the candidates are exactly the first `cand` entries of the sorted order (everything below a key boundary)
+                unsigned Pc = 1; while (Pc < cand) Pc <<= 1;
+                unsigned long long *ck = s_dyn;
+                unsigned *cs = (unsigned *)(s_dyn + Pc);
+                if (tid == 0) s_sel[2] = 0u;
+                __syncthreads();
+                for (unsigned i = tid; i < K; i += blockDim.x) {
+                    const unsigned long long k = gk[i];
+                    const unsigned a = (unsigned)(k >> 52), bsub = (unsigned)(k >> 41) & 0x7ffu;
+                    if (a < binA || (a == binA && bsub <= binB)) { const unsigned at = atomicAdd(&s_sel[2], 1u); ck[at] = k; cs[at] = gs[i]; }
+                }
+                __syncthreads();
+                CHK(s_sel[2] == cand, 6);
+                Ks = cand;
+                selected = true;
+            }
+        }
+    }
+    unsigned P = 1; while (P < Ks) P <<= 1;
     const bool in_smem = (int)P <= smem_cap;
     CHK(in_smem || P <= kpad, 3);
     unsigned long long *key = in_smem ? s_dyn : gk;
     unsigned *seq = in_smem ? (unsigned *)(s_dyn + P) : gs;
-    if (in_smem) { for (unsigned i = tid; i < K; i += blockDim.x) { key[i] = gk[i]; seq[i] = gs[i]; } }
-    for (unsigned i = K + tid; i < P; i += blockDim.x) { key[i] = ~0ull; seq[i] = 0xFFFFFFFFu; }
+    if (in_smem && !selected) { for (unsigned i = tid; i < Ks; i += blockDim.x) { key[i] = gk[i]; seq[i] = gs[i]; } }
+    for (unsigned i = Ks + tid; i < P; i += blockDim.x) { key[i] = ~0ull; seq[i] = 0xFFFFFFFFu; }
     __syncthreads();
     for (unsigned k = 2; k <= P; k <<= 1) {
         for (unsigned j = k >> 1; j > 0; j >>= 1) {
@@ -1393,7 +1471,7 @@ __global__ void __launch_bounds__(kSelectThreads, 3) k_select(CloudState *__rest
         }
     }
     // keep the sorted list (for the legacy handles / inspection)
-    if (list_div) {
+    if (list_div && !kPartial) {
         double *ld = list_div + (size_t)b * kcap; unsigned *ls = list_seq + (size_t)b * kcap;
         for (unsigned i = tid; i < K; i += blockDim.x) { const unsigned q = seq[i]; CHK(q < nslots, 4); ld[i] = kd[q]; ls[i] = q; }
     }
@@ -1403,15 +1481,15 @@ __global__ void __launch_bounds__(kSelectThreads, 3) k_select(CloudState *__rest
     unsigned char *removed = g_removed + (size_t)b * vcap;
     for (unsigned v = tid; v < V; v += blockDim.x) { firstpos[v] = 0xFFFFFFFFu; removed[v] = 0; }
     __syncthreads();
-    for (unsigned i = tid; i < K; i += blockDim.x) { CHK(seq[i] / kDirs < V, 5); atomicMin(&firstpos[seq[i] / kDirs], i); }
+    for (unsigned i = tid; i < Ks; i += blockDim.x) { CHK(seq[i] / kDirs < V, 5); atomicMin(&firstpos[seq[i] / kDirs], i); }
     __syncthreads();
     const unsigned to_remove = (unsigned)((unsigned long)V - (unsigned long)D);   // V >= D on acceptance
     if (tid == 0) s_carry = 0;
     __syncthreads();
     unsigned walk_local = 0;       // max over threads of (pos+1) for removed entries
-    for (unsigned base = 0; base < K; base += blockDim.x) {
+    for (unsigned base = 0; base < Ks; base += blockDim.x) {
         const unsigned i = base + tid;
-        const bool first = i < K && firstpos[seq[i] / kDirs] == i;
+        const bool first = i < Ks && firstpos[seq[i] / kDirs] == i;
         unsigned total;
         const unsigned r = s_carry + block_scan_step(first ? 1u : 0u, s_warp, total);
         if (first && r < to_remove && ((flags & 4u) || (unsigned long)i + r < (unsigned long)K)) {
@@ -1656,17 +1734,26 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     tm.mark(ST_SELECT, st);
     {
         const size_t kcap = (size_t)vcap * kDirs;
-        size_t P = 1; while (P < kcap) P <<= 1;
-        int smem_cap = (int)P;
-        size_t bytes = P * 12;
-        const size_t max_dyn = 200 * 1024;
-        while (bytes > max_dyn) { smem_cap >>= 1; bytes = (size_t)smem_cap * 12; }
         static bool attr_set[64] = {};   // function attributes are per device
         int dev = 0; cudaGetDevice(&dev);
-        if (!attr_set[dev & 63]) { CK(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn)); attr_set[dev & 63] = true; }
-        k_select<<<B, kSelectThreads, bytes, st>>>(w.states, vcap, D, w.vox_cell, w.vox_n, w.mean, w.cov_final, w.cls, labels ? 1 : 0,
-                                         w.kl_div, w.kl_flag, w.key, w.seq, kcap, smem_cap, w.firstpos, w.removed, flags,
-                                         out_feat, out_feat64, out_labels, out_voxel, w.list_div, w.list_seq, info);
+        const size_t max_dyn = 200 * 1024;
+        if (!attr_set[dev & 63]) { CK(cudaFuncSetAttribute(k_select<kSelectThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn)); attr_set[dev & 63] = true; }
+        if (w.keep_kl_list) {
+            // the whole sorted list stays behind (legacy handles: the prune() continuation walks it; inspection)
+            size_t P = 1; while (P < kcap) P <<= 1;
+            int smem_cap = (int)P;
+            size_t bytes = P * 12;
+            while (bytes > max_dyn) { smem_cap >>= 1; bytes = (size_t)smem_cap * 12; }
+            k_select<kSelectThreads, false><<<B, kSelectThreads, bytes, st>>>(
+                w.states, vcap, D, w.vox_cell, w.vox_n, w.mean, w.cov_final, w.cls, labels ? 1 : 0, w.kl_div, w.kl_flag, w.key, w.seq, kcap,
+                smem_cap, w.firstpos, w.removed, flags, out_feat, out_feat64, out_labels, out_voxel, w.list_div, w.list_seq, info);
+        } else {
+            // only the head of the list is sorted (in 24 KB of shared memory); a selection that does not fit sorts in the
+            // global scratch
+            k_select<kSelectPartialThreads, true><<<B, kSelectPartialThreads, (size_t)kSelectPartialCap * 12, st>>>(
+                w.states, vcap, D, w.vox_cell, w.vox_n, w.mean, w.cov_final, w.cls, labels ? 1 : 0, w.kl_div, w.kl_flag, w.key, w.seq, kcap,
+                kSelectPartialCap, w.firstpos, w.removed, flags, out_feat, out_feat64, out_labels, out_voxel, w.list_div, w.list_seq, info);
+        }
         DBG("k_select");
     }
     DBG("end");

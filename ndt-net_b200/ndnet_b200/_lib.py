@@ -107,6 +107,8 @@ def lib() -> C.CDLL:
     L.ndnet_b200_ply_free.argtypes = [vp]
     L.ndnet_b200_trainer_create.restype = i
     L.ndnet_b200_trainer_create.argtypes = [i, i, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i), C.POINTER(vp)]
+    L.ndnet_b200_keep_kl_list.restype = i
+    L.ndnet_b200_keep_kl_list.argtypes = [vp, i]
     L.ndnet_b200_onehot_to_labels.restype = i
     L.ndnet_b200_onehot_to_labels.argtypes = [vp, l, i, vp, vp]
     L.ndnet_b200_labels_to_onehot.restype = i
@@ -155,7 +157,7 @@ EXPORTED = [
     "ndnet_b200_model_tap", "ndnet_b200_model_set_fused_head", "ndnet_b200_test_fail_next_reserve",
     "ndnet_b200_infer_host", "ndnet_b200_infer_host_u8", "ndnet_b200_infer_host_async", "ndnet_b200_infer_wait", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline", "ndnet_b200_set_device_chunk",
     "ndnet_b200_ply_load", "ndnet_b200_ply_num_points", "ndnet_b200_ply_sample", "ndnet_b200_ply_free",
-    "ndnet_b200_onehot_to_labels", "ndnet_b200_labels_to_onehot", "ndnet_b200_trainer_create", "ndnet_b200_trainer_info", "ndnet_b200_trainer_forward", "ndnet_b200_trainer_backward", "ndnet_b200_trainer_last_error",
+    "ndnet_b200_keep_kl_list", "ndnet_b200_onehot_to_labels", "ndnet_b200_labels_to_onehot", "ndnet_b200_trainer_create", "ndnet_b200_trainer_info", "ndnet_b200_trainer_forward", "ndnet_b200_trainer_backward", "ndnet_b200_trainer_last_error",
     "ndnet_b200_trainer_backward_flat", "ndnet_b200_trainer_grad_layout", "ndnet_b200_trainer_set_graph",
     "ndnet_b200_trainer_num_buckets", "ndnet_b200_trainer_bucket_range", "ndnet_b200_trainer_set_deferred_copy", "ndnet_b200_trainer_bucket_ready",
     "ndnet_b200_trainer_set_precision", "ndnet_b200_debug_train_gemm", "ndnet_b200_trainer_debug_buffer", "ndnet_b200_trainer_destroy",

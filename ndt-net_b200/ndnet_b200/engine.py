@@ -134,6 +134,11 @@ class NdtEngine:
     def keep_point_voxels(self, enable: bool = True) -> None:
         self._check(self._L.ndnet_b200_keep_point_voxels(self._h, 1 if enable else 0), "ndnet_b200_keep_point_voxels")
 
+    def keep_kl_list(self, enable: bool = True) -> None:
+        """The batched calls sort only the head of the divergence list; enable this before a batch whose whole sorted list
+        `last_kl_list` is to return."""
+        self._check(self._L.ndnet_b200_keep_kl_list(self._h, 1 if enable else 0), "ndnet_b200_keep_kl_list")
+
     def last_point_voxels(self, B: int, N: int) -> torch.Tensor:
         out = torch.empty((B, N), dtype=torch.int32, device=self.device)
         self._check(self._L.ndnet_b200_last_point_voxels(self._h, out.data_ptr(),

@@ -29,6 +29,7 @@ def engine():
     from ndnet_b200.engine import NdtEngine
     e = NdtEngine(0)
     e.keep_point_voxels(True)      # the parity tests compare every point's voxel id
+    e.keep_kl_list(True)           # ... and the whole sorted divergence list
     return e
 
 
@@ -328,3 +329,28 @@ def test_failed_workspace_allocation_leaves_a_usable_context():
     third = e.downsample(bigger, 300, nan_to_num=False, want_f64=True)
     assert same_bits(third.feat64[:2].cpu().numpy(), first.feat64.cpu().numpy())
     e.close()
+
+
+def test_partial_sort_selects_what_the_full_sort_selects(engine):
+    """The batched calls sort only the head of the divergence list (the part the prune walk can reach, found by a radix
+    selection); with ndnet_b200_keep_kl_list the whole list is sorted.  Same retained set, rows, labels and bookkeeping on
+    LiDAR-like and object clouds, several n_desired_nds (few and many removals), a labelled batch."""
+    from ndnet_b200.engine import NdtEngine
+    from ndnet_b200.synth import lidar_batch, modelnet_cloud
+    part = NdtEngine(0)                       # keep_kl_list off: the production configuration
+    pts, lab = lidar_batch(6, 40000, seed0=300, with_labels=True)
+    objs = np.stack([modelnet_cloud(2048, s) for s in range(6)])
+    for cloud, labels, ncls, ds in ((pts, lab, 28, (1000, 400, 64)), (objs, None, 0, (512, 128, 16))):
+        t = torch.from_numpy(cloud).cuda()
+        l = None if labels is None else torch.from_numpy(labels.astype(np.int16)).cuda()
+        for d in ds:
+            a = engine.downsample(t, d, l, ncls, nan_to_num=False, want_f64=True, want_voxel=True)
+            b = part.downsample(t, d, l, ncls, nan_to_num=False, want_f64=True, want_voxel=True)
+            assert torch.equal(a.voxel, b.voxel), d
+            assert same_bits(a.feat64.cpu().numpy(), b.feat64.cpu().numpy()), d
+            if l is not None:
+                assert torch.equal(a.labels, b.labels), d
+            for k in ("status", "prune_status", "num_voxels", "num_valid", "num_kl", "num_kl_after", "num_out", "num_survivors"):
+                assert np.array_equal(a.info[k], b.info[k]), (d, k)
+    with pytest.raises(RuntimeError):
+        part.last_kl_list(0, 16)              # the whole list was not kept

@@ -24,7 +24,9 @@ REL = 1e-9
 @pytest.fixture(scope="module")
 def engine():
     from ndnet_b200.engine import NdtEngine
-    return NdtEngine(0)
+    e = NdtEngine(0)
+    e.keep_kl_list(True)           # the tests read the whole sorted divergence list
+    return e
 
 
 CASES = [("lidar-6k", lambda: lidar_cloud(6000, 3), 200), ("lidar-20k", lambda: lidar_cloud(20000, 5), 500),
