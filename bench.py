@@ -416,7 +416,8 @@ def run_ours(args):
                      "ndt_pipeline": {"ms_per_step": sum(stage_ms[n] for n in STAGES),
                                       "achieved": ALGO_BYTES_PER_CLOUD * B / (sum(stage_ms[n] for n in STAGES) * 1e-3) / 1e9,
                                       "frac": ALGO_BYTES_PER_CLOUD * B / (sum(stage_ms[n] for n in STAGES) * 1e-3) / 1e9 / peak},
-                     "peak_source": peak_src, "stage_ms_per_step": stage_ms},
+                     "peak_source": peak_src, "stage_ms_per_step": stage_ms,
+                     "stage_ms_per_512_scans": {k: v * 512.0 / B for k, v in stage_ms.items()}},
     }
     if train3 is not None:
         line["train_config3"] = train3
@@ -523,10 +524,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="scans per GPU per step")
+    ap.add_argument("--batch", type=int, default=2048, help="scans per GPU per step")
     ap.add_argument("--lanes", type=int, default=8, help="pipeline lanes (internal streams) of the infer calls")
     ap.add_argument("--chunk", type=int, default=64, help="scans per pipeline chunk of the host-buffer (e2e) path")
-    ap.add_argument("--device-chunk", type=int, default=128, help="scans per pipeline chunk of the device-buffer path")
+    ap.add_argument("--device-chunk", type=int, default=512, help="scans per pipeline chunk of the device-buffer path (four in flight)")
     ap.add_argument("--cpu-clouds", type=int, default=48, help="scans in the cpu_baseline sample")
     ap.add_argument("--ref-clouds", type=int, default=8, help="scans per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")

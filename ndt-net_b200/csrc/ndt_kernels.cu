@@ -1666,7 +1666,10 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         if (chunks > kCountCtasPerCloud) chunks = kCountCtasPerCloud;
         if (chunks < 1) chunks = 1;
         for (int it = 0; it < kMaxGuessIterations; it++) {
-            k_count<T><<<dim3(chunks, B), 256, 0, st>>>(pts, N, w.states, w.bitmap, w.bitmap_stride); DBG("k_count");
+            // scans rarely need more than five passes (3.2 on average): the late launches, which mostly find every cloud done,
+            // take a quarter of the CTAs (a cloud that is still searching then walks longer spans)
+            const int c_it = it < 6 ? chunks : (chunks + 3) / 4;
+            k_count<T><<<dim3(c_it, B), 256, 0, st>>>(pts, N, w.states, w.bitmap, w.bitmap_stride); DBG("k_count");
             k_decide<<<B, 256, 0, st>>>(w.states, w.lim_enc, w.bitmap, w.bitmap_stride, w.vox_cell, vcap, D, 1); DBG("k_decide");
         }
     }
