@@ -235,6 +235,11 @@ int ndnet_b200_set_pipeline(ndnet_b200_ctx *ctx, int lanes, int chunk);
 /* Chunk size of ndnet_b200_infer_device only (default 128): with the scans already in HBM there are no copies to hide,
  * and fewer, larger chunks run faster (4 x 128 beats 8 x 64 by 3-4 % at 512 scans). */
 int ndnet_b200_set_device_chunk(ndnet_b200_ctx *ctx, int chunk);
+/* Staggered lanes (on != 0): a chunk's front - bounding box, voxel-size search, voxel assignment, the kernels that stream
+ * every point from HBM - starts behind the front of the chunk before it, so that the front of chunk k runs beside the
+ * statistics / divergences / selection / network of chunk k-1 instead of all lanes walking through the same stage side by
+ * side.  The environment variable NDNET_B200_STAGGER=0|1 overrides the setting. */
+int ndnet_b200_set_stagger(ndnet_b200_ctx *ctx, int on);
 
 /* ------------------------------------------------------------------ (3) ASCII-PLY ingest
  * Replaces the per-line Python loop of /root/reference/ndnet/datasets/CARLA_Seg.py:96-183 (`get_data_pcl`):

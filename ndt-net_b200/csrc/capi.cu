@@ -49,6 +49,7 @@ struct ndnet_b200_ctx {
     std::vector<Lane> lanes;
     int n_lanes = 2;
     int chunk = 64;          // scans per chunk of ndnet_b200_infer_host (copies overlap kernels: more, smaller chunks)
+    bool stagger = false;    // lanes start their fronts one behind the other (infer_pipelined)
     int chunk_device = 128;  // scans per chunk of ndnet_b200_infer_device (no copies to hide: fewer, larger chunks)
     cudaEvent_t start_ev = nullptr;
     // host -> device copies of ndnet_b200_infer_host all go through ONE stream, in chunk order: copies issued on the lanes'
@@ -91,14 +92,15 @@ static cudaError_t alloc(T *&p, size_t count) {
 // stream and its events survive so that a workspace can grow without re-creating them (destroy() ends them).
 void Workspace::release() {
     const bool keep = keep_point_voxels, keep_list = keep_kl_list;
-    cudaStream_t keep_side = side; cudaEvent_t keep_fork = ev_fork, keep_join = ev_join;
+    cudaStream_t keep_side = side; cudaEvent_t keep_fork = ev_fork, keep_join = ev_join, keep_front = ev_front;
+    const bool keep_mark = mark_front;
     const StageTimer keep_timer = timer;
     void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, vox_order, slot_rank, tile_cnt, hist, point_voxel, sorted,
                     mean, cov, cov_final, cls, kl_div, kl_flag, key, seq, firstpos, removed, list_div, list_seq, recip};
     for (void *p : ptrs) if (p) cudaFree(p);
     *this = Workspace();
     keep_point_voxels = keep; keep_kl_list = keep_list;
-    side = keep_side; ev_fork = keep_fork; ev_join = keep_join;
+    side = keep_side; ev_fork = keep_fork; ev_join = keep_join; ev_front = keep_front; mark_front = keep_mark;
     timer = keep_timer;
 }
 
@@ -107,8 +109,9 @@ void Workspace::destroy() {
     if (timer.created) { for (auto &e : timer.ev) cudaEventDestroy(e); timer = StageTimer(); }
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_front) cudaEventDestroy(ev_front);
     if (side) cudaStreamDestroy(side);
-    side = nullptr; ev_fork = ev_join = nullptr;
+    side = nullptr; ev_fork = ev_join = ev_front = nullptr;
 }
 
 cudaError_t Workspace::reserve(int B, long N, long D, int bins) {
@@ -365,6 +368,12 @@ extern "C" int ndnet_b200_set_pipeline(ndnet_b200_ctx *c, int lanes, int chunk) 
     return 0;
 }
 
+extern "C" int ndnet_b200_set_stagger(ndnet_b200_ctx *c, int on) {
+    if (!c) return -200;
+    c->stagger = on != 0;
+    return 0;
+}
+
 extern "C" int ndnet_b200_set_device_chunk(ndnet_b200_ctx *c, int chunk) {
     if (!c || chunk < 1) return -200;
     c->chunk_device = chunk;
@@ -400,11 +409,20 @@ static int infer_pipelined(ndnet_b200_ctx *c, ndnet_b200_model *model, const voi
     // kernels; device buffers - c->chunk_device (measured on B200, 512 scans: 4 x 128 beats 8 x 64 by 3-4 %, 1 x 512 loses 3 %)
     int chunk = host_io ? c->chunk : c->chunk_device;
     if (host_io && (B + L - 1) / L < chunk) chunk = (B + L - 1) / L;
+    // staggered lanes: a chunk's front (limits, search, voxel assignment - the kernels that stream every point from HBM)
+    // starts behind the front of the chunk before it, so that the lanes do not walk through the same stage side by side
+    // (four lanes in lock-step share the HBM in the front and leave it idle in the back): the front of chunk k runs beside
+    // the statistics / divergences / selection / network of chunk k-1
+    static const int stagger_env = [] { const char *v = getenv("NDNET_B200_STAGGER"); return v ? atoi(v) : -1; }();
+    const bool stagger = stagger_env >= 0 ? stagger_env != 0 : c->stagger;
+    cudaEvent_t prev_front = nullptr;
     int lane_i = 0;
     for (int b0 = 0; b0 < B; b0 += chunk, lane_i = (lane_i + 1) % L) {
         const int nb = B - b0 < chunk ? B - b0 : chunk;
         ndnet_b200_ctx::Lane &l = c->lanes[lane_i];
         if (!host_io && (e = cudaStreamWaitEvent(l.stream, c->start_ev, 0)) != cudaSuccess) return fail(c, e, "stream wait");
+        l.ws.mark_front = stagger;
+        if (stagger && prev_front && (e = cudaStreamWaitEvent(l.stream, prev_front, 0)) != cudaSuccess) return fail(c, e, "stream wait");
         const char *psrc = (const char *)points + (size_t)b0 * N * 3 * esz;
         const uint16_t *lsrc = labels ? (const uint16_t *)((const char *)labels + (size_t)b0 * N * lsz) : nullptr;
         float *odst = out + (size_t)b0 * out_elems_per_cloud;
@@ -426,6 +444,7 @@ static int infer_pipelined(ndnet_b200_ctx *c, ndnet_b200_model *model, const voi
         l.ws.last_B = nb; l.ws.last_N = N; l.ws.last_D = D;
         if ((e = ndt::run_batch(l.ws, dp, dtype, dl, nb, N, num_classes, D, NDNET_B200_NAN_TO_NUM | label_flags, l.d_feat, nullptr, nullptr, nullptr,
                                 nullptr, l.stream)) != cudaSuccess) return fail(c, e, "ndt::run_batch");
+        prev_front = stagger ? l.ws.ev_front : nullptr;
         if (host_io) {       // the NDT kernels are the only readers of the lane's input buffers
             if ((e = cudaEventRecord(l.consumed, l.stream)) != cudaSuccess) return fail(c, e, "event record");
             l.used = true;

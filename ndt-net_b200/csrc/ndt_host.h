@@ -60,6 +60,10 @@ struct Workspace {
     StageTimer timer;
     cudaStream_t side = nullptr;       // side stream for kernels that are independent of the main chain
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // recorded behind k_scatter when mark_front is set: the bandwidth-bound half of the chain (limits, search, voxel
+    // assignment) is enqueued up to here; the pipelined calls start the next chunk's front behind it (capi.cu)
+    cudaEvent_t ev_front = nullptr;
+    bool mark_front = false;
     // of the last run
     int last_B = 0; long last_N = 0; long last_D = 0;
 

@@ -1695,6 +1695,10 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
             wide_labels ? w.hist : nullptr, nbins);
         DBG("k_scatter");
     }
+    if (w.mark_front) {
+        if (!w.ev_front) CK(cudaEventCreateWithFlags(&w.ev_front, cudaEventDisableTiming));
+        CK(cudaEventRecord(w.ev_front, st));
+    }
     tm.mark(ST_STATS, st);
     // heavy voxels (a warp each; at most N / kHeavyVoxel of them per cloud), then the light ones (a thread each)
     {

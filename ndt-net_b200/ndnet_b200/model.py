@@ -158,8 +158,11 @@ class B200Model:
                                f"{self._L.ndnet_b200_last_error(self.engine.handle).decode()}")
         return out.unsqueeze(-1) if self.kind == KIND_CLS else out
 
-    def set_pipeline(self, lanes: int, chunk: int, device_chunk: int | None = None) -> None:
-        """lanes x chunk scans for infer_host; `device_chunk` scans per chunk for infer_device (library default 128)."""
+    def set_pipeline(self, lanes: int, chunk: int, device_chunk: int | None = None, stagger: bool | None = None) -> None:
+        """lanes x chunk scans for infer_host; `device_chunk` scans per chunk for infer_device (library default 128);
+        `stagger`: a chunk's front (limits, search, voxel assignment) starts behind the front of the chunk before it."""
+        if stagger is not None:
+            self._L.ndnet_b200_set_stagger(self.engine.handle, 1 if stagger else 0)
         rc = self._L.ndnet_b200_set_pipeline(self.engine.handle, int(lanes), int(chunk))
         if rc != 0:
             raise RuntimeError(f"ndnet_b200_set_pipeline failed ({rc})")
