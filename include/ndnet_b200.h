@@ -240,6 +240,12 @@ int ndnet_b200_set_device_chunk(ndnet_b200_ctx *ctx, int chunk);
  * statistics / divergences / selection / network of chunk k-1 instead of all lanes walking through the same stage side by
  * side.  The environment variable NDNET_B200_STAGGER=0|1 overrides the setting. */
 int ndnet_b200_set_stagger(ndnet_b200_ctx *ctx, int on);
+/* CUDA-graph replay of the NDT chain inside ndnet_b200_downsample_batch.  mode -1 (default): batches of at most ~4 M points
+ * (32 scans of 120 k), where the ~55 dependent launches of the chain are bound by launch latency; 0: never; 1: every batch.
+ * A shape gets its graph the second time it is seen; the graph runs on buffers the context owns (the scans are copied in and
+ * the results out, device to device, around one cudaGraphLaunch), results are bit-identical to the direct launches.  A call
+ * whose stream is itself being captured launches directly into the caller's graph.  NDNET_B200_NDT_GRAPH=-1|0|1 overrides. */
+int ndnet_b200_set_ndt_graph(ndnet_b200_ctx *ctx, int mode);
 
 /* ------------------------------------------------------------------ (3) ASCII-PLY ingest
  * Replaces the per-line Python loop of /root/reference/ndnet/datasets/CARLA_Seg.py:96-183 (`get_data_pcl`):

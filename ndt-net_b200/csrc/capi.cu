@@ -52,6 +52,27 @@ struct ndnet_b200_ctx {
     bool stagger = false;    // lanes start their fronts one behind the other (infer_pipelined)
     int chunk_device = 128;  // scans per chunk of ndnet_b200_infer_device (no copies to hide: fewer, larger chunks)
     cudaEvent_t start_ev = nullptr;
+    // CUDA-graph replay of the NDT chain for small batches (ndnet_b200_downsample_batch): ~55 dependent launches, most of
+    // them a few microseconds long, are launch-latency bound below a few dozen scans
+    struct NdtGraph {
+        int dtype = 0, B = 0, num_classes = 0; long N = 0, D = 0; unsigned flags = 0, wants = 0, ws_flags = 0;
+        unsigned long ws_generation = 0, stamp = 0;
+        cudaGraphExec_t exec = nullptr;
+        int state = 0;                 // 0: free slot; 1: shape seen once (launched directly); 2: graph ready; 3: capture failed (launch directly)
+        void *in_pts = nullptr; uint16_t *in_lab = nullptr;
+        float *o_feat = nullptr; double *o_feat64 = nullptr; uint16_t *o_lab = nullptr; int32_t *o_vox = nullptr; NdtCloudInfo *o_info = nullptr;
+        long launches = 0;
+        void destroy() {
+            if (exec) cudaGraphExecDestroy(exec);
+            void *p[] = {in_pts, in_lab, o_feat, o_feat64, o_lab, o_vox, o_info};
+            for (void *q : p) if (q) cudaFree(q);
+            *this = NdtGraph();
+        }
+    };
+    std::vector<NdtGraph> graphs;
+    int graph_mode = -1;               // -1: batches of at most kGraphAutoPoints points; 0: never; 1: every batch
+    unsigned long graph_clock = 0;
+    cudaStream_t graph_stream = nullptr;
     // host -> device copies of ndnet_b200_infer_host all go through ONE stream, in chunk order: copies issued on the lanes'
     // own streams are served concurrently by the copy engine, so every chunk's data would arrive near the end of the
     // step and the kernels could not overlap the transfer
@@ -94,6 +115,7 @@ void Workspace::release() {
     const bool keep = keep_point_voxels, keep_list = keep_kl_list;
     cudaStream_t keep_side = side; cudaEvent_t keep_fork = ev_fork, keep_join = ev_join, keep_front = ev_front;
     const bool keep_mark = mark_front;
+    const unsigned long keep_gen = generation + 1;
     const StageTimer keep_timer = timer;
     void *ptrs[] = {states, lim_enc, bitmap, vox_cell, vox_n, vox_start, vox_order, slot_rank, tile_cnt, hist, point_voxel, sorted,
                     mean, cov, cov_final, cls, kl_div, kl_flag, key, seq, firstpos, removed, list_div, list_seq, recip};
@@ -102,6 +124,7 @@ void Workspace::release() {
     keep_point_voxels = keep; keep_kl_list = keep_list;
     side = keep_side; ev_fork = keep_fork; ev_join = keep_join; ev_front = keep_front; mark_front = keep_mark;
     timer = keep_timer;
+    generation = keep_gen;
 }
 
 void Workspace::destroy() {
@@ -214,6 +237,8 @@ extern "C" void ndnet_b200_destroy(ndnet_b200_ctx *c) {
     }
     if (c->start_ev) cudaEventDestroy(c->start_ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (auto &g : c->graphs) g.destroy();
+    if (c->graph_stream) cudaStreamDestroy(c->graph_stream);
     delete c;
 }
 
@@ -269,6 +294,92 @@ extern "C" const char *ndnet_b200_last_error(const ndnet_b200_ctx *c) { return c
 // batched entry points
 // ------------------------------------------------------------------------------------------------
 struct ndnet_b200_model { mlp::Model m; };
+// ---- CUDA-graph replay of the NDT chain ---------------------------------------------------------
+// A captured graph holds addresses, so it runs on buffers the context owns: the caller's scans are copied in (14 bytes per
+// point, device to device) and the results copied out around one cudaGraphLaunch.  Worth it only where the chain is bound
+// by launch latency: 120 k-point scans, 2 per call: ~55 launches of 2-10 us each.
+constexpr long kGraphAutoPoints = 4L << 20;        // automatic mode: batches of at most ~4 M points (32 scans of 120 k)
+constexpr size_t kGraphCacheEntries = 4;
+
+static int downsample_graphed(ndnet_b200_ctx *c, const void *points, int dtype, const uint16_t *labels, int B, long N, int num_classes,
+                              long D, unsigned flags, float *out_feat, double *out_feat64, uint16_t *out_labels, int32_t *out_voxel,
+                              NdtCloudInfo *info, cudaStream_t st) {
+    using G = ndnet_b200_ctx::NdtGraph;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return 1; }   // the caller is capturing: its graph takes our kernels
+    const unsigned wants = (labels ? 1u : 0u) | (out_feat ? 2u : 0u) | (out_feat64 ? 4u : 0u) | (out_labels ? 8u : 0u) | (out_voxel ? 16u : 0u) | (info ? 32u : 0u);
+    const unsigned ws_flags = (c->ws.keep_point_voxels ? 1u : 0u) | (c->ws.keep_kl_list ? 2u : 0u);
+    const size_t esz = dtype == 0 ? 4 : 8, lsz = (flags & NDNET_B200_LABELS_U8) ? 1 : 2;
+    G *g = nullptr;
+    for (auto &e : c->graphs)
+        if (e.state != 0 && e.dtype == dtype && e.B == B && e.N == N && e.num_classes == num_classes && e.D == D && e.flags == flags && e.wants == wants &&
+            e.ws_flags == ws_flags && e.ws_generation == c->ws.generation) { g = &e; break; }
+    cudaError_t e;
+    if (!g) {
+        // a shape seen for the first time is launched directly and remembered; it gets its graph when it comes back.
+        // Graphs of a workspace that no longer exists go first, then the least recently used entry.
+        for (auto &x : c->graphs) if (x.state != 0 && x.ws_generation != c->ws.generation) x.destroy();
+        G *slot = nullptr;
+        for (auto &x : c->graphs) if (x.state == 0) { slot = &x; break; }
+        if (!slot && c->graphs.size() < kGraphCacheEntries) { c->graphs.emplace_back(); slot = &c->graphs.back(); }
+        if (!slot) { slot = &c->graphs[0]; for (auto &x : c->graphs) if (x.stamp < slot->stamp) slot = &x; slot->destroy(); }
+        slot->dtype = dtype; slot->B = B; slot->N = N; slot->num_classes = num_classes; slot->D = D; slot->flags = flags; slot->wants = wants;
+        slot->ws_flags = ws_flags; slot->ws_generation = c->ws.generation; slot->state = 1; slot->stamp = ++c->graph_clock;
+        return 1;
+    }
+    g->stamp = ++c->graph_clock;
+    if (g->state == 3) return 1;
+    if (g->state == 1) {
+        G &n = *g;
+#define GA(ptr, bytes) if ((e = cudaMalloc((void **)&(ptr), (bytes))) != cudaSuccess) { n.destroy(); cudaGetLastError(); return 1; }
+        GA(n.in_pts, (size_t)B * N * 3 * esz);
+        if (labels) GA(n.in_lab, (size_t)B * N * lsz);
+        if (out_feat) GA(n.o_feat, (size_t)B * D * 12 * 4);
+        if (out_feat64) GA(n.o_feat64, (size_t)B * D * 12 * 8);
+        if (out_labels) GA(n.o_lab, (size_t)B * D * 2);
+        if (out_voxel) GA(n.o_vox, (size_t)B * D * 4);
+        if (info) GA(n.o_info, (size_t)B * sizeof(NdtCloudInfo));
+#undef GA
+        if (!c->graph_stream && (e = cudaStreamCreateWithFlags(&c->graph_stream, cudaStreamNonBlocking)) != cudaSuccess) { n.destroy(); return fail(c, e, "stream create"); }
+        // capture on the context's own stream (recording only: nothing executes until the graph is launched).  The chain
+        // has run directly at least once on this context, so whatever it creates lazily (side stream, events, function
+        // attributes) exists.
+        const long before = ndt::launches();
+        cudaGraph_t graph = nullptr;
+        if ((e = cudaStreamBeginCapture(c->graph_stream, cudaStreamCaptureModeThreadLocal)) == cudaSuccess) {
+            const cudaError_t er = ndt::run_batch(c->ws, n.in_pts, dtype, n.in_lab, B, N, num_classes, D, flags, n.o_feat, n.o_feat64, n.o_lab, n.o_vox,
+                                                  n.o_info, c->graph_stream);
+            e = cudaStreamEndCapture(c->graph_stream, &graph);
+            if (er != cudaSuccess) e = er;
+        }
+        n.launches = ndt::launches() - before;
+        ndt::count_launches(-n.launches);              // recorded, not launched
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&n.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {                        // no graph for this shape: this and later calls launch directly
+            cudaGetLastError();
+            const G key = n;
+            n.destroy();
+            n.dtype = key.dtype; n.B = key.B; n.N = key.N; n.num_classes = key.num_classes; n.D = key.D; n.flags = key.flags; n.wants = key.wants;
+            n.ws_flags = key.ws_flags; n.ws_generation = key.ws_generation; n.stamp = key.stamp; n.state = 3;
+            return 1;
+        }
+        n.state = 2;
+    }
+    if ((e = cudaMemcpyAsync(g->in_pts, points, (size_t)B * N * 3 * esz, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return fail(c, e, "D2D points");
+    if (labels && (e = cudaMemcpyAsync(g->in_lab, labels, (size_t)B * N * lsz, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return fail(c, e, "D2D labels");
+    if ((e = cudaGraphLaunch(g->exec, st)) != cudaSuccess) return fail(c, e, "cudaGraphLaunch");
+    ndt::count_launches(g->launches);
+#define GO(dst, src, bytes) if (dst && (e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return fail(c, e, "D2D results")
+    GO(out_feat, g->o_feat, (size_t)B * D * 12 * 4);
+    GO(out_feat64, g->o_feat64, (size_t)B * D * 12 * 8);
+    GO(out_labels, g->o_lab, (size_t)B * D * 2);
+    GO(out_voxel, g->o_vox, (size_t)B * D * 4);
+    GO(info, g->o_info, (size_t)B * sizeof(NdtCloudInfo));
+#undef GO
+    return 0;
+}
+
 extern "C" int ndnet_b200_downsample_batch(ndnet_b200_ctx *c, const void *points, int dtype, const uint16_t *labels,
                                            int B, long N, int num_classes, long D, unsigned flags, float *out_feat,
                                            double *out_feat64, uint16_t *out_labels, int32_t *out_voxel,
@@ -280,9 +391,23 @@ extern "C" int ndnet_b200_downsample_batch(ndnet_b200_ctx *c, const void *points
     e = c->ws.reserve(B, N, D, num_classes + 1);
     if (e != cudaSuccess) return fail(c, e, "workspace allocation");
     c->ws.last_B = B; c->ws.last_N = N; c->ws.last_D = D;
+    c->ws.mark_front = false;
+    static const int graph_env = [] { const char *v = getenv("NDNET_B200_NDT_GRAPH"); return v ? atoi(v) : -2; }();
+    const int gmode = graph_env >= -1 ? graph_env : c->graph_mode;
+    if (N > 0 && !c->ws.timer.enabled && (gmode == 1 || (gmode == -1 && (long)B * N <= kGraphAutoPoints))) {
+        const int r = downsample_graphed(c, points, dtype, labels, B, N, num_classes, D, flags, out_feat, out_feat64, out_labels, out_voxel,
+                                         (NdtCloudInfo *)info, (cudaStream_t)stream);
+        if (r <= 0) return r;          // 0: replayed; < 0: a CUDA error.  1: no graph for this call - launch the kernels directly
+    }
     e = ndt::run_batch(c->ws, points, dtype, labels, B, N, num_classes, D, flags, out_feat, out_feat64, out_labels,
                        out_voxel, (NdtCloudInfo *)info, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(c, e, "ndt::run_batch");
+    return 0;
+}
+
+extern "C" int ndnet_b200_set_ndt_graph(ndnet_b200_ctx *c, int mode) {
+    if (!c || mode < -1 || mode > 1) return -200;
+    c->graph_mode = mode;
     return 0;
 }
 

@@ -38,6 +38,7 @@ struct NdtCloudInfo {
 // Device workspace for a batch of up to B_cap clouds x N_cap points, D_cap desired distributions.
 struct Workspace {
     int B_cap = 0; long N_cap = 0; long D_cap = 0; int bins_cap = 0;
+    unsigned long generation = 0;  // bumped whenever the arrays are freed (captured graphs hold their addresses)
     unsigned vcap = 0;             // max occupied voxels per cloud = floor(1.2*D)+2
     size_t bitmap_stride = 0;      // uint2 {bits, prefix} words per cloud
     int ntiles_cap = 0;

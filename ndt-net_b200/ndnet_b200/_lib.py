@@ -98,6 +98,8 @@ def lib() -> C.CDLL:
     L.ndnet_b200_set_device_chunk.argtypes = [vp, i]
     L.ndnet_b200_set_stagger.restype = i
     L.ndnet_b200_set_stagger.argtypes = [vp, i]
+    L.ndnet_b200_set_ndt_graph.restype = i
+    L.ndnet_b200_set_ndt_graph.argtypes = [vp, i]
     L.ndnet_b200_ply_load.restype = i
     L.ndnet_b200_ply_load.argtypes = [i, vp, C.c_size_t, i, i, i, vp, C.POINTER(vp), C.POINTER(C.c_ulong), C.POINTER(l),
                                       C.POINTER(l)]
@@ -157,7 +159,7 @@ EXPORTED = [
     "ndnet_b200_last_search_passes",
     "ndnet_b200_model_create", "ndnet_b200_model_input_dim", "ndnet_b200_model_destroy", "ndnet_b200_model_forward",
     "ndnet_b200_model_tap", "ndnet_b200_model_set_fused_head", "ndnet_b200_test_fail_next_reserve",
-    "ndnet_b200_infer_host", "ndnet_b200_infer_host_u8", "ndnet_b200_infer_host_async", "ndnet_b200_infer_wait", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline", "ndnet_b200_set_device_chunk", "ndnet_b200_set_stagger",
+    "ndnet_b200_infer_host", "ndnet_b200_infer_host_u8", "ndnet_b200_infer_host_async", "ndnet_b200_infer_wait", "ndnet_b200_infer_device", "ndnet_b200_set_pipeline", "ndnet_b200_set_device_chunk", "ndnet_b200_set_stagger", "ndnet_b200_set_ndt_graph",
     "ndnet_b200_ply_load", "ndnet_b200_ply_num_points", "ndnet_b200_ply_sample", "ndnet_b200_ply_free",
     "ndnet_b200_keep_kl_list", "ndnet_b200_onehot_to_labels", "ndnet_b200_labels_to_onehot", "ndnet_b200_trainer_create", "ndnet_b200_trainer_info", "ndnet_b200_trainer_forward", "ndnet_b200_trainer_backward", "ndnet_b200_trainer_last_error",
     "ndnet_b200_trainer_backward_flat", "ndnet_b200_trainer_grad_layout", "ndnet_b200_trainer_set_graph",

@@ -134,6 +134,11 @@ class NdtEngine:
     def keep_point_voxels(self, enable: bool = True) -> None:
         self._check(self._L.ndnet_b200_keep_point_voxels(self._h, 1 if enable else 0), "ndnet_b200_keep_point_voxels")
 
+    def set_graph(self, mode: int) -> None:
+        """CUDA-graph replay of the NDT chain: -1 automatic (small batches, the default), 0 never, 1 every batch
+        (include/ndnet_b200.h ndnet_b200_set_ndt_graph)."""
+        self._check(self._L.ndnet_b200_set_ndt_graph(self._h, int(mode)), "ndnet_b200_set_ndt_graph")
+
     def keep_kl_list(self, enable: bool = True) -> None:
         """The batched calls sort only the head of the divergence list; enable this before a batch whose whole sorted list
         `last_kl_list` is to return."""

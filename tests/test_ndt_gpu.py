@@ -354,3 +354,42 @@ def test_partial_sort_selects_what_the_full_sort_selects(engine):
                 assert np.array_equal(a.info[k], b.info[k]), (d, k)
     with pytest.raises(RuntimeError):
         part.last_kl_list(0, 16)              # the whole list was not kept
+
+
+def test_graph_replay_equals_direct_launches():
+    """ndnet_b200_set_ndt_graph: the captured chain, replayed on the context's own buffers, returns bit for bit what the direct
+    launches return - for new scans of the same shape (the graph re-reads its inputs), with labels, and the launch counter
+    advances by the same amount; a new shape goes back to direct launches until it is seen again."""
+    from ndnet_b200 import _lib
+    from ndnet_b200.engine import NdtEngine
+    from ndnet_b200.synth import lidar_batch
+    L = _lib.lib()
+    direct, graphed = NdtEngine(0), NdtEngine(0)
+    direct.set_graph(0)
+    graphed.set_graph(1)
+    B, N, D, C = 3, 20000, 150, 12
+
+    def run(e, seed, n=N):
+        p, l = lidar_batch(B, n, seed0=seed, with_labels=True, num_classes=C)
+        pt, lt = torch.from_numpy(p).cuda(), torch.from_numpy(l.astype(np.int16)).cuda()
+        n0 = L.ndnet_b200_launch_count()
+        o = e.downsample(pt, D, lt, C, nan_to_num=False, want_f64=True, want_voxel=True)
+        torch.cuda.synchronize()
+        return o, L.ndnet_b200_launch_count() - n0
+
+    for call, seed in enumerate([11, 11, 12, 13, 11]):      # calls 0-1: direct + capture; 2-4: replays on other scans
+        a, na = run(direct, seed)
+        b, nb = run(graphed, seed)
+        assert na == nb and na > 40, (call, na, nb)
+        assert same_bits(a.feat64.cpu().numpy(), b.feat64.cpu().numpy()), call
+        assert torch.equal(a.feat, b.feat) and torch.equal(a.voxel, b.voxel) and torch.equal(a.labels, b.labels), call
+        assert a.info.tobytes() == b.info.tobytes(), call
+        assert np.any(a.info["num_out"] > 0), call
+    # another shape in between, then the first shape again: still the same answers
+    a, _ = run(direct, 21, n=N + 8)
+    b, _ = run(graphed, 21, n=N + 8)
+    assert same_bits(a.feat64.cpu().numpy(), b.feat64.cpu().numpy())
+    a, _ = run(direct, 14)
+    b, _ = run(graphed, 14)
+    assert same_bits(a.feat64.cpu().numpy(), b.feat64.cpu().numpy()) and torch.equal(a.voxel, b.voxel)
+    direct.close(); graphed.close()
