@@ -11,7 +11,7 @@ mkdir -p $o
 stamp() { echo "$(date +%T) $*" >> $o/progress_$tag.log; }
 if [ "$mode" = check ]; then
     stamp tests
-    ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $o/r2_gputest_$tag.log 2>&1
+    ( time timeout 900 python -m pytest tests -m gpu -q --maxfail=8 ) > $o/r2_gputest_$tag.log 2>&1
     stamp smoke
     timeout 180 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $o/r2_smoke_$tag.log 2>&1
     stamp bench
@@ -23,6 +23,8 @@ if [ "$mode" = check ]; then
     stamp done
     tail -3 $o/r2_gputest_$tag.log
 elif [ "$mode" = ncu ]; then
+    stamp tests
+    ( time timeout 600 python -m pytest tests -m gpu -q --maxfail=8 ) > $o/r2_gputest_$tag.log 2>&1
     cap() {   # cap <name> <kernel regex> <skip> <count>
         stamp "ncu $1"
         timeout 420 ncu --set full --clock-control none -k "$2" --launch-skip $3 -c $4 -f -o $o/prof_$1_$tag \
