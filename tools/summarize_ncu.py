@@ -41,9 +41,19 @@ def launches(path, out):
     print("wrote", out)
 
 
+def raw_page(rep):
+    """rows of the raw page: from a .ncu-rep, or from the CSV `ncu -i <rep> --page raw --csv` wrote on the GPU box"""
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    lines = raw.splitlines()
+    start = next(i for i, ln in enumerate(lines) if ln.startswith('"ID"'))
+    return list(csv.reader(lines[start:]))
+
+
 def kernel(rep, name, batch, out):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+    rows = raw_page(rep)
     H, U = rows[0], rows[1]
     kn = H.index("Kernel Name")
     base = lambda r: r[kn].split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()   # noqa: E731
@@ -80,8 +90,7 @@ def _main():
 
 def table(rep, out, title):
     """One row per captured launch of a multi-kernel report."""
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+    rows = raw_page(rep)
     H = rows[0]
     ix = {h: i for i, h in enumerate(H)}
     cols = [("gpu__time_duration.sum", "dur"), ("launch__grid_size", "grid"), ("launch__registers_per_thread", "regs"),
