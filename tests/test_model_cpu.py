@@ -53,3 +53,34 @@ def test_state_dict_keys_follow_the_reference_layout():
         assert k in keys, k
     assert NDTNetSegmentation(num_classes=28).state_dict()["conv1.weight"].shape == (512, 1088, 1)
     assert NDTNetClassification().state_dict()["conv3.weight"].shape == (512, 256, 1)
+
+
+def test_drop_in_modules_match_reference_in_training_mode():
+    """The GPU training tests compare the library with these modules' forward_torch in train() mode; here that definition is
+    pinned to the reference's own modules in the same mode (tests/golden/model_ref_train_golden.npz, made by
+    make_model_train_golden.py from /root/reference): forward on batch statistics, the loss of tools/train.py:74, every
+    parameter gradient and the BatchNorm running statistics after the step, for all four networks."""
+    from ndnet.models.pointnet import PointNetClassification, PointNetSegmentation
+    from tests.golden.make_model_train_golden import FULL_GRADS, cases, run_case
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_ref_train_golden.npz"))
+    mods = {"NDTNetSegmentation": NDTNetSegmentation, "NDTNetClassification": NDTNetClassification,
+            "PointNetSegmentation": PointNetSegmentation, "PointNetClassification": PointNetClassification}
+    torch.manual_seed(0)
+    for name, net, args, target, seed in cases(mods):
+        r = run_case(net, args, target, seed, forward=net.forward_torch)
+        assert r["out"].shape == g[f"{name}.out"].shape, name
+        assert np.allclose(r["out"], g[f"{name}.out"], rtol=2e-4, atol=2e-5), (name, np.abs(r["out"] - g[f"{name}.out"]).max())
+        assert abs(r["loss"] - float(g[f"{name}.loss"])) <= 1e-5 * abs(float(g[f"{name}.loss"])), name
+        assert list(r["grad_names"]) == list(g[f"{name}.grad_names"]), name          # same parameters, same order
+        scale = np.maximum(g[f"{name}.grad_abs_sum"], 1e-12)
+        # a bias in front of a train-mode BatchNorm has an analytically zero gradient: what both sides hold there is rounding
+        # noise, hence the absolute term (1e-6 of the network's largest gradient sum)
+        noise = 1e-6 * float(g[f"{name}.grad_abs_sum"].max())
+        assert np.all(np.abs(r["grad_abs_sum"] - g[f"{name}.grad_abs_sum"]) <= 2e-3 * scale + noise), name
+        assert np.all(np.abs(r["grad_sum"] - g[f"{name}.grad_sum"]) <= 2e-3 * scale + noise), name
+        for k in FULL_GRADS:
+            if f"{name}.grad.{k}" in g:
+                ref = g[f"{name}.grad.{k}"]
+                assert np.allclose(r["grad." + k], ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max() + 1e-9), (name, k)
+        assert list(r["bn_names"]) == list(g[f"{name}.bn_names"]), name
+        assert np.allclose(r["bn_sum"], g[f"{name}.bn_sum"], rtol=1e-4, atol=1e-5), name
