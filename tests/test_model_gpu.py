@@ -232,6 +232,14 @@ def test_pipelined_inference_equals_single_stream_calls():
     m.infer_host(hp, 300, hl, 28, outs[2], wait=False)
     m.infer_wait()
     assert torch.equal(outs[0], ref.cpu()) and torch.equal(outs[1], ref2.cpu()) and torch.equal(outs[2], ref.cpu())
+    # staggered lanes (ndnet_b200_set_stagger: a chunk's front starts behind the previous chunk's front): same results
+    m.set_pipeline(2, 3, 2, stagger=True)
+    got_st = m.infer_device(tp, 300, tl, 28)
+    out_st = torch.empty((7, 300, 29), dtype=torch.float32).pin_memory()
+    m.infer_host(hp, 300, hl, 28, out_st)
+    torch.cuda.synchronize()
+    m.set_pipeline(2, 3, stagger=False)
+    assert torch.equal(ref, got_st) and torch.equal(ref.cpu(), out_st)
 
 
 def test_pointnet_forward_matches_torch_fp32():
