@@ -1303,7 +1303,8 @@ __device__ __forceinline__ void find_rank_bin(const unsigned *hist, int nbins, u
     __syncthreads();
 }
 
-constexpr int kSelectPartialCap = 2048;         // candidates the partial selection sorts in shared memory
+constexpr int kSelectPartialCap = 2048;         // candidates the partial selection sorts in shared memory (24 KB) at D ~ 1000 ...
+constexpr int kSelectPartialCapMax = 16384;     // ... and at most, for large D (196 KB): the host sizes the launch by 6 (Vcap - D)
 constexpr int kSelectPartialThreads = 256;
 
 // kPartial: only the head of the sorted list is produced - the walk removes the first V - D distinct p's and every p owns at
@@ -1428,7 +1429,7 @@ __global__ void __launch_bounds__(kThreads, kPartial ? 5 : 3) k_select(CloudStat
             find_rank_bin(hist, 2048, need - beforeA, s_warp, s_sel, binB, beforeB);
             const unsigned cand = beforeA + beforeB + hist[binB];
             __syncthreads();
-            if (cand <= (unsigned)kSelectPartialCap && (int)cand <= smem_cap) {
+            if ((int)cand <= smem_cap) {
                 // the candidates are exactly the first `cand` entries of the sorted order (everything below a key boundary)
                 unsigned Pc = 1; while (Pc < cand) Pc <<= 1;
                 unsigned long long *ck = s_dyn;
@@ -1755,11 +1756,21 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
                 w.states, vcap, D, w.vox_cell, w.vox_n, w.mean, w.cov_final, w.cls, labels ? 1 : 0, w.kl_div, w.kl_flag, w.key, w.seq, kcap,
                 smem_cap, w.firstpos, w.removed, flags, out_feat, out_feat64, out_labels, out_voxel, w.list_div, w.list_seq, info);
         } else {
-            // only the head of the list is sorted (in 24 KB of shared memory); a selection that does not fit sorts in the
-            // global scratch
-            k_select<kSelectPartialThreads, true><<<B, kSelectPartialThreads, (size_t)kSelectPartialCap * 12, st>>>(
+            // only the head of the list is sorted, in shared memory sized for what the walk can reach: 6 (V - D) <= 6 (Vcap - D)
+            // entries - 24 KB at D = 1000, 96 KB at D = 4096 (BASELINE config 5); a selection that does not fit the largest
+            // launch (D beyond ~13 k) sorts in the global scratch
+            size_t reach = 6 * ((size_t)vcap - (size_t)(D < (long)vcap ? D : (long)vcap));
+            if (reach > kcap) reach = kcap;
+            int cap = kSelectPartialCap;
+            while ((size_t)cap < reach && cap < kSelectPartialCapMax) cap <<= 1;
+            static bool part_attr_set[64] = {};
+            if (cap > 4096 && !part_attr_set[dev & 63]) {
+                CK(cudaFuncSetAttribute(k_select<kSelectPartialThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelectPartialCapMax * 12));
+                part_attr_set[dev & 63] = true;
+            }
+            k_select<kSelectPartialThreads, true><<<B, kSelectPartialThreads, (size_t)cap * 12, st>>>(
                 w.states, vcap, D, w.vox_cell, w.vox_n, w.mean, w.cov_final, w.cls, labels ? 1 : 0, w.kl_div, w.kl_flag, w.key, w.seq, kcap,
-                kSelectPartialCap, w.firstpos, w.removed, flags, out_feat, out_feat64, out_labels, out_voxel, w.list_div, w.list_seq, info);
+                cap, w.firstpos, w.removed, flags, out_feat, out_feat64, out_labels, out_voxel, w.list_div, w.list_seq, info);
         }
         DBG("k_select");
     }

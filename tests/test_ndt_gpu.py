@@ -340,7 +340,9 @@ def test_partial_sort_selects_what_the_full_sort_selects(engine):
     part = NdtEngine(0)                       # keep_kl_list off: the production configuration
     pts, lab = lidar_batch(6, 40000, seed0=300, with_labels=True)
     objs = np.stack([modelnet_cloud(2048, s) for s in range(6)])
-    for cloud, labels, ncls, ds in ((pts, lab, 28, (1000, 400, 64)), (objs, None, 0, (512, 128, 16))):
+    from ndnet_b200.synth import lidar_cloud
+    big = lidar_cloud(120000, 62)[None]       # D = 4096: the launch grows its shared memory with D; D = 16000: 17 k reachable
+    for cloud, labels, ncls, ds in ((pts, lab, 28, (1000, 400, 64)), (objs, None, 0, (512, 128, 16)), (big, None, 0, (4096, 16000))):   # entries, beyond the largest launch: global-memory sort
         t = torch.from_numpy(cloud).cuda()
         l = None if labels is None else torch.from_numpy(labels.astype(np.int16)).cuda()
         for d in ds:
