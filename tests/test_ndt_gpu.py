@@ -382,7 +382,7 @@ def test_graph_replay_equals_direct_launches():
     for call, seed in enumerate([11, 11, 12, 13, 11]):      # calls 0-1: direct + capture; 2-4: replays on other scans
         a, na = run(direct, seed)
         b, nb = run(graphed, seed)
-        assert na == nb and na > 40, (call, na, nb)
+        assert na == nb and na >= 20, (call, na, nb)
         assert same_bits(a.feat64.cpu().numpy(), b.feat64.cpu().numpy()), call
         assert same_bits(a.feat.cpu().numpy(), b.feat.cpu().numpy()), call          # nan_to_num is off: NaNs compare by bits
         assert torch.equal(a.voxel, b.voxel) and torch.equal(a.labels, b.labels), call
