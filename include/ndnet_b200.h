@@ -233,7 +233,8 @@ int ndnet_b200_infer_device(ndnet_b200_ctx *ctx, ndnet_b200_model *model, const 
  * Defaults: 2 lanes, 64 scans.  The lane count is fixed at the first infer call. */
 int ndnet_b200_set_pipeline(ndnet_b200_ctx *ctx, int lanes, int chunk);
 /* Chunk size of ndnet_b200_infer_device only (default 128): with the scans already in HBM there are no copies to hide,
- * and fewer, larger chunks run faster (4 x 128 beats 8 x 64 by 3-4 % at 512 scans). */
+ * and fewer, larger chunks run faster (2048 scans per call: 64-scan chunks 92 k clouds/s, 128: 108 k, 256: 127 k, 512 and
+ * above: 132-135 k; bench.py uses 512). */
 int ndnet_b200_set_device_chunk(ndnet_b200_ctx *ctx, int chunk);
 /* Staggered lanes (on != 0): a chunk's front - bounding box, voxel-size search, voxel assignment, the kernels that stream
  * every point from HBM - starts behind the front of the chunk before it, so that the front of chunk k runs beside the
