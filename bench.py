@@ -416,7 +416,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm",
-                     "kernel": dict(DOMINANT_KERNEL, search=f"k_count (x{passes.value:.2f} launches that do work, of 15; "
+                     "kernel": dict(DOMINANT_KERNEL, search=f"k_count (x{passes.value:.2f} passes that do work per scan: 6 launches + k_search_tail; "
                                                             f"{evals.value:.2f} guesses evaluated per scan)")[dom],
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "scans_per_launch": LB,

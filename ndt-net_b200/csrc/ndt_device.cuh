@@ -13,6 +13,7 @@
 namespace ndt {
 
 constexpr int kMaxGuessIterations = 15;     // include/ndnet_core/ndt.h:43
+constexpr int kSearchPairLaunches = 6;      // (k_count, k_decide) launch pairs of the voxel-size search; k_search_tail runs whatever rounds remain
 constexpr double kMinVoxelGuess = 0.01;     // ndt.h:41
 constexpr double kMaxVoxelGuess = 30.0;     // ndt.h:42
 constexpr double kUpperThreshold = 0.2;     // ndt.h:38

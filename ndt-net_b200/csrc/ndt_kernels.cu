@@ -150,10 +150,14 @@ __device__ void skip_small_grids(CloudState &s, unsigned long D) {
 // On acceptance it also builds the voxel directory: per word {bits, prefix popcount} and the list of
 // occupied cell ids in ascending order (slot -> cell).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_decide(CloudState *__restrict__ states, const unsigned long long *__restrict__ lim_enc,
-                                                uint2 *__restrict__ bitmap, size_t bitmap_stride,
-                                                unsigned *__restrict__ vox_cell, unsigned vcap, long num_desired, int phase) {
-    const int b = blockIdx.x;
+// (a device function: k_decide runs it once per launch, k_search_tail once per round; block of 256 threads.)
+// `states` and `bitmap` carry NO __restrict__ here, in k_decide and in k_search_tail: thread 0 writes the new search state
+// (grid, word count, status) and the other threads read it behind a barrier, round after round in k_search_tail.  With
+// __restrict__ the compiler may keep a value loaded before the barrier (it did, once everything was inlined into the tail's
+// loop: the bitmap of the next guess was cleared with the PREVIOUS guess's word count by every thread but thread 0).
+__device__ __forceinline__ void decide_body(CloudState *states, const unsigned long long *__restrict__ lim_enc,
+                                            uint2 *bitmap, size_t bitmap_stride,
+                                            unsigned *__restrict__ vox_cell, unsigned vcap, long num_desired, int phase, int b) {
     CloudState &s = states[b];
     uint2 *bm = bitmap + (size_t)b * bitmap_stride;
     __shared__ unsigned s_part[8];
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(256) k_decide(CloudState *__restrict__ states,
         if (s.status != 1) return;
         // count occupied cells of the pass
         unsigned cnt = 0;
-        for (unsigned w = tid; w < s.nwords; w += blockDim.x) cnt += __popc(bm[w].x);
+        for (unsigned w = tid; w < s.nwords; w += blockDim.x) cnt += __popc(__ldcg(&bm[w].x));     // L2: set by atomics, possibly in this very kernel (k_search_tail)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) s_part[wid] = cnt;
@@ -214,16 +218,17 @@ __global__ void __launch_bounds__(256) k_decide(CloudState *__restrict__ states,
         }
         __syncthreads();
     }
+    const unsigned nwords_now = *(volatile unsigned *)&s.nwords;      // thread 0 may just have set the next guess's grid
     if (s_action == 1) {
-        for (unsigned w = tid; w < s.nwords; w += blockDim.x) bm[w] = make_uint2(0u, 0u);
+        for (unsigned w = tid; w < nwords_now; w += blockDim.x) bm[w] = make_uint2(0u, 0u);
     } else if (s_action == 2) {
         // exclusive prefix popcount over the words + slot -> cell list
         __shared__ unsigned s_carry;
         if (tid == 0) s_carry = 0;
         __syncthreads();
-        for (unsigned base = 0; base < s.nwords; base += blockDim.x) {
+        for (unsigned base = 0; base < nwords_now; base += blockDim.x) {
             const unsigned w = base + tid;
-            const unsigned bits = w < s.nwords ? bm[w].x : 0u;
+            const unsigned bits = w < nwords_now ? __ldcg(&bm[w].x) : 0u;
             const unsigned c = __popc(bits);
             unsigned inc = c;
 #pragma unroll
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(256) k_decide(CloudState *__restrict__ states,
             unsigned blk_total = 0;
             for (int k = 0; k < 8; k++) blk_total += s_part[k];
             const unsigned excl = s_carry + woff + inc - c;
-            if (w < s.nwords) {
+            if (w < nwords_now) {
                 bm[w].y = excl;
                 unsigned rest = bits, k = 0;
                 while (rest) {
@@ -250,6 +255,12 @@ __global__ void __launch_bounds__(256) k_decide(CloudState *__restrict__ states,
             __syncthreads();
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_decide(CloudState *states, const unsigned long long *__restrict__ lim_enc,
+                                                uint2 *bitmap, size_t bitmap_stride,
+                                                unsigned *__restrict__ vox_cell, unsigned vcap, long num_desired, int phase) {
+    decide_body(states, lim_enc, bitmap, bitmap_stride, vox_cell, vcap, num_desired, phase, (int)blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -311,14 +322,13 @@ __device__ __forceinline__ void count_span(const T *__restrict__ p, long begin, 
     }
 }
 
+// one pass over cloud b as CTA `cta` of `nctas` (k_count: its grid; k_search_tail: the only one)
 template <typename T>
-__global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N, CloudState *__restrict__ states,
-                                               uint2 *__restrict__ bitmap, size_t bitmap_stride) {
-    const int b = blockIdx.y;
+__device__ __forceinline__ void count_pass(const T *__restrict__ pts, long N, CloudState *states,
+                                           uint2 *bitmap, size_t bitmap_stride, int b, int cta, int nctas,
+                                           unsigned *s_bits, unsigned *s_fail) {
     CloudState &s = states[b];
     if (s.status != 1) return;                           // converged or failed clouds cost one exiting CTA per launch slot
-    __shared__ unsigned s_bits[kSmemBitmapBits / 32];
-    __shared__ unsigned s_fail[kWorkers];
     const T *p = pts + (size_t)b * N * 3;
     uint2 *bm = bitmap + (size_t)b * bitmap_stride;
     const unsigned G = s.G, nwords = s.nwords;
@@ -332,7 +342,7 @@ __global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N
     const bool use_smem = G <= kSmemBitmapBits;
 
     if (s.risky) {
-        if (blockIdx.x != 0) return;
+        if (cta != 0) return;
         if (threadIdx.x < kWorkers) s_fail[threadIdx.x] = kDropped;
         if (use_smem) for (unsigned w = threadIdx.x; w < nwords; w += blockDim.x) s_bits[w] = 0u;
         __syncthreads();
@@ -358,9 +368,9 @@ __global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N
 
     // this CTA's contiguous span of the cloud (a multiple of 4 * 256 points, so every thread's groups of four are
     // 16-byte aligned when the cloud is)
-    long per = (n_used + gridDim.x - 1) / gridDim.x;
+    long per = (n_used + nctas - 1) / nctas;
     per = (per + 1023) / 1024 * 1024;
-    const long begin = (long)blockIdx.x * per;
+    const long begin = (long)cta * per;
     if (begin >= n_used) return;
     const GridCtx gc = make_grid_ctx(s);
     const long end = begin + per < n_used ? begin + per : n_used;
@@ -377,6 +387,37 @@ __global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N
             const unsigned v = s_bits[w];
             if (v) atomicOr(&bm[w].x, v);
         }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_count(const T *__restrict__ pts, long N, CloudState *__restrict__ states,
+                                               uint2 *__restrict__ bitmap, size_t bitmap_stride) {
+    __shared__ unsigned s_bits[kSmemBitmapBits / 32];
+    __shared__ unsigned s_fail[kWorkers];
+    count_pass<T>(pts, N, states, bitmap, bitmap_stride, (int)blockIdx.y, (int)blockIdx.x, (int)gridDim.x, s_bits, s_fail);
+}
+
+// The rest of the search in ONE launch: after kSearchPairLaunches (count, decide) pairs nearly every cloud has its voxel size
+// (3.2 passes on average); the clouds that are still searching finish here, one CTA per cloud running count and decide rounds
+// back to back (a pass by a single CTA takes longer than by eight, but a launch pair for finished clouds - ~10 us, nine of
+// them per batch - costs more than the rare straggler).  grid B, block 256.  No __restrict__ on the state and the bitmap
+// (see decide_body); the fences do between rounds what the launch boundary does between k_count and k_decide.
+template <typename T>
+__global__ void __launch_bounds__(256) k_search_tail(const T *__restrict__ pts, long N, CloudState *states,
+                                                     const unsigned long long *__restrict__ lim_enc, uint2 *bitmap,
+                                                     size_t bitmap_stride, unsigned *__restrict__ vox_cell, unsigned vcap, long num_desired) {
+    __shared__ unsigned s_bits[kSmemBitmapBits / 32];
+    __shared__ unsigned s_fail[kWorkers];
+    const int b = blockIdx.x;
+    for (int round = 0; round < kMaxGuessIterations; round++) {
+        if (*(volatile int *)&states[b].status != 1) return;      // written by thread 0 in front of a barrier of the previous round
+        count_pass<T>(pts, N, states, bitmap, bitmap_stride, b, 0, 1, s_bits, s_fail);
+        __threadfence();                                 // the pass's atomics on the bitmap words have reached L2 ...
+        __syncthreads();                                 // ... before any thread counts them
+        decide_body(states, lim_enc, bitmap, bitmap_stride, vox_cell, vcap, num_desired, 1, b);
+        __threadfence();                                 // the cleared words / the new search state are in L2 ...
+        __syncthreads();                                 // ... before the next round's atomics and loads touch them
     }
 }
 
@@ -1666,13 +1707,13 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
         int chunks = (int)((N + kCountPointsPerCta - 1) / kCountPointsPerCta);
         if (chunks > kCountCtasPerCloud) chunks = kCountCtasPerCloud;
         if (chunks < 1) chunks = 1;
-        for (int it = 0; it < kMaxGuessIterations; it++) {
-            // scans rarely need more than five passes (3.2 on average): the late launches, which mostly find every cloud done,
-            // take a quarter of the CTAs (a cloud that is still searching then walks longer spans)
-            const int c_it = it < 6 ? chunks : (chunks + 3) / 4;
-            k_count<T><<<dim3(c_it, B), 256, 0, st>>>(pts, N, w.states, w.bitmap, w.bitmap_stride); DBG("k_count");
+        // scans rarely need more than five passes (3.2 on average): kSearchPairLaunches (count, decide) launch pairs, then one
+        // launch in which the clouds that are still searching run their remaining rounds (k_search_tail)
+        for (int it = 0; it < kSearchPairLaunches; it++) {
+            k_count<T><<<dim3(chunks, B), 256, 0, st>>>(pts, N, w.states, w.bitmap, w.bitmap_stride); DBG("k_count");
             k_decide<<<B, 256, 0, st>>>(w.states, w.lim_enc, w.bitmap, w.bitmap_stride, w.vox_cell, vcap, D, 1); DBG("k_decide");
         }
+        k_search_tail<T><<<B, 256, 0, st>>>(pts, N, w.states, w.lim_enc, w.bitmap, w.bitmap_stride, w.vox_cell, vcap, D); DBG("k_search_tail");
     }
     tm.mark(ST_RANK, st);
     if (N > 0) {
@@ -1776,7 +1817,7 @@ static cudaError_t run_typed(Workspace &w, const T *pts, const uint16_t *labels,
     }
     DBG("end");
     tm.mark(ST_COUNT, st);
-    count_launches(3 + 2 * kMaxGuessIterations + (N > 0 ? 2 : 0) + 6 + (wide_labels ? 1 : 0));
+    count_launches(3 + 2 * kSearchPairLaunches + 1 + (N > 0 ? 2 : 0) + 6 + (wide_labels ? 1 : 0));
     if (tm.enabled) {
         CK(cudaEventSynchronize(tm.ev[ST_COUNT]));
         for (int i = 0; i < ST_COUNT; i++) { float ms = 0; cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]); tm.ms[i] += ms; }
